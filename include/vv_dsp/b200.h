@@ -1,0 +1,110 @@
+/*
+ * vv_dsp/b200.h -- batched, device-resident extension of the STFT handle API.
+ *
+ * NOT in the reference: its API is one host frame per call (include/vv_dsp/spectral/
+ * stft.h:30-56), which cannot express BASELINE's batched workloads.  These entry
+ * points are defined so that, frame for frame, they equal looping the per-frame API
+ * the way the reference's own callers do:
+ *   analysis   tools/dump_stft_roundtrip.c:44-45   process(h, x + f*hop, spec)
+ *   synthesis  tools/dump_stft_roundtrip.c:46-54   reconstruct(h, spec, recon + f*hop,
+ *              norm + f*hop); y[i] = norm[i] > 1e-12 ? recon[i]/norm[i] : 0
+ *
+ * Layouts (row-major, contiguous unless a pitch is given):
+ *   signals   [batch][signal_pitch]         float32, n valid samples per row
+ *   spectra   [batch][frames][spec_pitch]   bins k = 0..fft_size/2 (fft_size/2+1 per
+ *             frame, the Hermitian half; X[fft_size-k] = conj X[k] is implied).
+ *             vv_dsp_cpx for COMPLEX, float32 for POWER (re^2+im^2, what
+ *             include/vv_dsp/features/mel.h:74-77 consumes) and MAGNITUDE (sqrtf).
+ *   A pitch of 0 means dense (n, resp. fft_size/2+1).  No padding is ever added
+ *   behind the caller's back.
+ *
+ * Memory spaces: every buffer argument carries its own space.  HOST buffers are
+ * caller-owned host memory (pinned memory makes the copies asynchronous and
+ * overlapped); DEVICE buffers are CUDA device pointers on the handle's device.
+ * If every buffer of a call is DEVICE the call only enqueues work on the handle's
+ * stream (vv_dsp_stft_set_stream) and returns; otherwise it returns after the
+ * results are in host memory.
+ *
+ * Batched entry points need a power-of-two fft_size in [256, 8192] (the Stockham
+ * kernels); other sizes return VV_DSP_ERROR_UNSUPPORTED here and are served by the
+ * per-frame API.  There is no CPU fallback anywhere.
+ */
+#ifndef VV_DSP_B200_H
+#define VV_DSP_B200_H
+
+#include <stddef.h>
+#include "vv_dsp/vv_dsp_types.h"
+#include "vv_dsp/spectral/stft.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vv_dsp_mem_space {
+    VV_DSP_MEM_HOST = 0,
+    VV_DSP_MEM_DEVICE = 1
+} vv_dsp_mem_space;
+
+/* The reference's four coexisting frame-count rules:
+ *   VALID        n < fft ? 0 : 1 + (n-fft)/hop          src/core/framing.c:66-67, dump tool loop
+ *   SPECTROGRAM  n < fft ? 1 : 1 + (n-fft+hop)/hop      src/spectral/stft.c:119 (zero-padded tail)
+ *   PADDED_TAIL  frames while start+fft <= n+(fft-hop)  tests/spectral_tests.c:101 (zero-padded tail)
+ *   CENTER       ceil(n/hop), frame centred at f*hop, edge-inclusive reflect padding
+ *                src/core/framing.c:61-63,21-56,86-102 */
+typedef enum vv_dsp_frame_convention {
+    VV_DSP_FRAMES_VALID = 0,
+    VV_DSP_FRAMES_SPECTROGRAM = 1,
+    VV_DSP_FRAMES_PADDED_TAIL = 2,
+    VV_DSP_FRAMES_CENTER = 3
+} vv_dsp_frame_convention;
+
+typedef enum vv_dsp_spec_kind {
+    VV_DSP_SPEC_COMPLEX = 0,
+    VV_DSP_SPEC_POWER = 1,
+    VV_DSP_SPEC_MAGNITUDE = 2
+} vv_dsp_spec_kind;
+
+/* frame count for a signal of n samples under a convention; fft_size/2+1 */
+size_t vv_dsp_stft_num_frames(const vv_dsp_stft* h, size_t n, vv_dsp_frame_convention convention);
+size_t vv_dsp_stft_num_bins(const vv_dsp_stft* h);
+
+/* Bind the handle to a caller-owned cudaStream_t (NULL = the handle's own stream). */
+vv_dsp_status vv_dsp_stft_set_stream(vv_dsp_stft* h, void* cuda_stream);
+/* Block until everything enqueued on the handle's stream has finished. */
+vv_dsp_status vv_dsp_stft_synchronize(vv_dsp_stft* h);
+
+/* Analysis of `batch` signals: framing + window + real FFT (+ |X|^2 or |X|) fused in
+ * one kernel.  *out_frames receives the per-signal frame count (may be NULL). */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_forward(
+    vv_dsp_stft* h,
+    const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch, size_t n, size_t signal_pitch,
+    vv_dsp_frame_convention convention, vv_dsp_spec_kind kind,
+    void* out, vv_dsp_mem_space out_space, size_t spec_pitch, size_t* out_frames);
+
+/* Synthesis: inverse real FFT + synthesis window + overlap-add of `frames` frames per
+ * signal at positions f*hop, into n_out samples per signal (positions >= n_out are
+ * dropped like vv_dsp_overlap_add does, src/core/framing.c:139-145; positions no
+ * frame covers are 0).  normalise != 0 divides by the accumulated sum of w^2 with the
+ * callers' guard (norm > 1e-12 ? y/norm : 0); normalise == 0 returns the raw sum. */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_inverse(
+    vv_dsp_stft* h,
+    const vv_dsp_cpx* spectra, vv_dsp_mem_space spectra_space, size_t batch, size_t frames, size_t spec_pitch,
+    vv_dsp_real* out, vv_dsp_mem_space out_space, size_t n_out, size_t out_pitch, int normalise);
+
+/* One-signal host convenience: ISTFT with window-sum normalisation
+ * (= reconstruct-all-frames + the caller-side divide of tools/dump_stft_roundtrip.c:50-54). */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_istft(vv_dsp_stft* h, const vv_dsp_cpx* half_spectra, size_t frames,
+                                                 vv_dsp_real* out, size_t n_out);
+
+/* Library / device introspection */
+const char* vv_dsp_b200_version(void);
+/* last CUDA error text seen by the calling thread ("" if none) */
+const char* vv_dsp_b200_last_error(void);
+/* number of kernels this process has launched through the library (bench.py's gpu_launches) */
+unsigned long long vv_dsp_b200_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VV_DSP_B200_H */

@@ -1,0 +1,80 @@
+/*
+ * vvb200_cuda.h -- the thin C-ABI between the C99 host library (csrc/host/ *.c) and
+ * the CUDA translation units (csrc/cuda/ *.cu).  Plain pointers and sizes only; no
+ * CUDA or torch types cross it (streams travel as void*).  INTERNAL: consumers bind
+ * vv_dsp/ *.h; this header exists so the host side stays pure C99.
+ *
+ * Every function returns 0 on success or a vv_dsp_status-compatible code
+ * (4 = CUDA failure, text via vvb_last_error(); 6 = no device / unsupported size).
+ */
+#ifndef VVB200_CUDA_H
+#define VVB200_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vvb_engine vvb_engine;     /* device-resident STFT plan: tables + stream */
+typedef struct vvb_fft_engine vvb_fft_engine; /* device-resident FFT plan */
+typedef struct { float re, im; } vvb_cpx;
+
+enum { VVB_OUT_COMPLEX = 0, VVB_OUT_POWER = 1, VVB_OUT_MAGNITUDE = 2 };
+enum { VVB_PAD_ZERO = 0, VVB_PAD_REFLECT_CENTER = 1 };
+
+const char* vvb_last_error(void);
+unsigned long long vvb_kernel_launches(void);
+int vvb_device_ready(void);   /* 0 when a usable sm_100-class device is current */
+
+/* ---- memory / stream plumbing (device = the engine's device) */
+int vvb_malloc(void** dptr, size_t bytes);
+int vvb_free(void* dptr);
+int vvb_host_alloc(void** hptr, size_t bytes);   /* pinned */
+int vvb_host_free(void* hptr);
+int vvb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int vvb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int vvb_memcpy2d_h2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream);
+int vvb_memcpy2d_d2h(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream);
+int vvb_memset(void* dst, int value, size_t bytes, void* stream);
+int vvb_stream_create(void** stream);
+int vvb_stream_destroy(void* stream);
+int vvb_stream_sync(void* stream);
+int vvb_event_create(void** ev);
+int vvb_event_destroy(void* ev);
+int vvb_event_record(void* ev, void* stream);
+int vvb_stream_wait_event(void* stream, void* ev);
+
+/* ---- STFT engine.  window: nfft host floats (the analysis == synthesis window). */
+int vvb_engine_create(size_t nfft, size_t hop, const float* window, vvb_engine** out);
+void vvb_engine_destroy(vvb_engine* e);
+int vvb_engine_is_fast(const vvb_engine* e);   /* 1 if nfft has a Stockham kernel (pow2 256..8192) */
+
+/* frames of every signal b < batch: frame f covers x[start .. start+nfft), start = f*hop
+ * (VVB_PAD_ZERO, zeros outside [0,n)) or f*hop - nfft/2 with edge-inclusive reflection
+ * (VVB_PAD_REFLECT_CENTER).  d_out: [batch][frames][out_pitch] of vvb_cpx (COMPLEX) or
+ * float (POWER / MAGNITUDE), bins 0..nfft/2. */
+int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, size_t n, size_t x_pitch, size_t frames,
+                     int pad_mode, int out_kind, void* d_out, size_t out_pitch, void* stream);
+
+/* overlap-add synthesis of d_spec [batch][frames][spec_pitch] into d_y [batch][y_pitch]
+ * (n_out valid samples each).  d_inv_norm: table set built by vvb_norm_tables_build, or
+ * NULL for the raw (un-normalised) sum. */
+int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t batch, size_t frames, size_t spec_pitch,
+                     float* d_y, size_t n_out, size_t y_pitch, const float* d_inv_norm, void* stream);
+
+/* windowed synthesis frames without overlap-add: d_frames [count][nfft] =
+ * Re(IDFT(spec)/nfft) * w  (what vv_dsp_stft_reconstruct adds into out_add). */
+int vvb_stft_inverse_frames(vvb_engine* e, const vvb_cpx* d_spec, size_t count, size_t spec_pitch,
+                            float* d_frames, void* stream);
+
+/* ---- FFT engine (plan API): type 0 C2C, 1 R2C, 2 C2R; dir +1 / -1 */
+int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine** out);
+void vvb_fft_engine_destroy(vvb_fft_engine* e);
+int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, size_t batch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VVB200_CUDA_H */

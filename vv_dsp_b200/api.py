@@ -1,0 +1,304 @@
+"""ctypes mirror of the C API in include/vv_dsp/*.h (see package docstring)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(PKG, "lib", "libvvdsp_b200.so")
+
+WINDOWS = {"boxcar": 0, "hann": 1, "hamming": 2}
+CONVENTIONS = {"valid": 0, "spectrogram": 1, "padded_tail": 2, "center": 3}
+KINDS = {"complex": 0, "power": 1, "magnitude": 2}
+HOST, DEVICE = 0, 1
+STATUS = {0: "VV_DSP_OK", 1: "VV_DSP_ERROR_NULL_POINTER", 2: "VV_DSP_ERROR_INVALID_SIZE",
+          3: "VV_DSP_ERROR_OUT_OF_RANGE", 4: "VV_DSP_ERROR_INTERNAL", 5: "VV_DSP_ERROR_NAN_INF",
+          6: "VV_DSP_ERROR_UNSUPPORTED"}
+FFT_C2C, FFT_R2C, FFT_C2R = 0, 1, 2
+FFT_FORWARD, FFT_BACKWARD = 1, -1
+
+_sz = C.c_size_t
+_vp = C.c_void_p
+
+
+class VvDspError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = int(status)
+        super().__init__(f"{where}: {STATUS.get(int(status), status)}" + (f" ({detail})" if detail else ""))
+
+
+class StftParams(C.Structure):
+    """vv_dsp_stft_params (reference include/vv_dsp/spectral/stft.h:23-27)"""
+    _fields_ = [("fft_size", _sz), ("hop_size", _sz), ("window", C.c_int)]
+
+
+class Library:
+    """A loaded libvvdsp_b200.so with prototypes declared for every exported entry point."""
+
+    # name -> (restype, argtypes); the exported C-ABI of include/vv_dsp/*.h
+    PROTOS = {
+        "vv_dsp_stft_create": (C.c_int, [C.POINTER(StftParams), C.POINTER(_vp)]),
+        "vv_dsp_stft_destroy": (C.c_int, [_vp]),
+        "vv_dsp_stft_process": (C.c_int, [_vp, _vp, _vp]),
+        "vv_dsp_stft_reconstruct": (C.c_int, [_vp, _vp, _vp, _vp]),
+        "vv_dsp_stft_spectrogram": (C.c_int, [_vp, _vp, _sz, _vp, C.POINTER(_sz)]),
+        "vv_dsp_fft_set_backend": (C.c_int, [C.c_int]),
+        "vv_dsp_fft_get_backend": (C.c_int, []),
+        "vv_dsp_fft_is_backend_available": (C.c_int, [C.c_int]),
+        "vv_dsp_fft_set_fftw_flag": (C.c_int, [C.c_int]),
+        "vv_dsp_fft_flush_fftw_cache": (C.c_int, []),
+        "vv_dsp_fft_make_plan": (C.c_int, [_sz, C.c_int, C.c_int, C.POINTER(_vp)]),
+        "vv_dsp_fft_execute": (C.c_int, [_vp, _vp, _vp]),
+        "vv_dsp_fft_destroy": (C.c_int, [_vp]),
+        "vv_dsp_window_boxcar": (C.c_int, [_sz, _vp]),
+        "vv_dsp_window_hann": (C.c_int, [_sz, _vp]),
+        "vv_dsp_window_hamming": (C.c_int, [_sz, _vp]),
+        "vv_dsp_get_num_frames": (_sz, [_sz, _sz, _sz, C.c_int]),
+        "vv_dsp_fetch_frame": (C.c_int, [_vp, _sz, _vp, _sz, _sz, _sz, C.c_int, _vp]),
+        "vv_dsp_overlap_add": (C.c_int, [_vp, _vp, _sz, _sz, _sz, _sz]),
+        "vv_dsp_vectorized_window_apply": (C.c_int, [_vp, _vp, _vp, _sz]),
+        "vv_dsp_stft_num_frames": (_sz, [_vp, _sz, C.c_int]),
+        "vv_dsp_stft_num_bins": (_sz, [_vp]),
+        "vv_dsp_stft_set_stream": (C.c_int, [_vp, _vp]),
+        "vv_dsp_stft_synchronize": (C.c_int, [_vp]),
+        "vv_dsp_stft_batch_forward": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, C.c_int, _vp, C.c_int, _sz,
+                                                C.POINTER(_sz)]),
+        "vv_dsp_stft_batch_inverse": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, _vp, C.c_int, _sz, _sz, C.c_int]),
+        "vv_dsp_stft_istft": (C.c_int, [_vp, _vp, _sz, _vp, _sz]),
+        "vv_dsp_b200_version": (C.c_char_p, []),
+        "vv_dsp_b200_last_error": (C.c_char_p, []),
+        "vv_dsp_b200_kernel_launches": (C.c_ulonglong, []),
+    }
+
+    def __init__(self, path: str | None = None):
+        path = path or DEFAULT_LIB
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} not found: the CUDA library has not been built (python -m vv_dsp_b200.build). "
+                "vv-dsp_b200 has no CPU fallback.")
+        self.path = path
+        self.dll = C.CDLL(path)
+        for name, (res, args) in self.PROTOS.items():
+            fn = getattr(self.dll, name)
+            fn.restype = res
+            fn.argtypes = args
+
+    def __getattr__(self, name):
+        return getattr(self.dll, name)
+
+    def last_error(self) -> str:
+        return (self.dll.vv_dsp_b200_last_error() or b"").decode()
+
+    def kernel_launches(self) -> int:
+        return int(self.dll.vv_dsp_b200_kernel_launches())
+
+    def version(self) -> str:
+        return self.dll.vv_dsp_b200_version().decode()
+
+
+_default = None
+
+
+def default_library() -> Library:
+    global _default
+    if _default is None:
+        _default = Library()
+    return _default
+
+
+def _check(lib, st, where):
+    if st != 0:
+        raise VvDspError(st, where, lib.last_error())
+
+
+def _is_device(a) -> bool:
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return _vp(a.data_ptr())
+    return a.ctypes.data_as(_vp)
+
+
+def _win_id(w):
+    return WINDOWS[w] if isinstance(w, str) else int(w)
+
+
+# ----------------------------------------------------------------------------- free functions
+def window(kind, n, lib: Library | None = None):
+    """vv_dsp_window_{boxcar,hann,hamming}(N, out) -> (status, float32[n])"""
+    lib = lib or default_library()
+    out = np.empty(max(n, 1), np.float32)
+    st = getattr(lib, f"vv_dsp_window_{kind}")(n, _ptr(out))
+    return st, out[:n]
+
+
+def get_num_frames(signal_len, frame_len, hop_len, center=0, lib: Library | None = None) -> int:
+    lib = lib or default_library()
+    return int(lib.vv_dsp_get_num_frames(signal_len, frame_len, hop_len, int(center)))
+
+
+def fetch_frame(signal, frame_len, hop_len, frame_index, center=0, win=None, lib: Library | None = None):
+    lib = lib or default_library()
+    signal = np.ascontiguousarray(signal, np.float32)
+    out = np.zeros(max(frame_len, 1), np.float32)
+    w = np.ascontiguousarray(win, np.float32) if win is not None else None
+    st = lib.vv_dsp_fetch_frame(_ptr(signal), signal.size, _ptr(out), frame_len, hop_len, frame_index, int(center), _ptr(w))
+    return st, out[:frame_len]
+
+
+def overlap_add(frame, output, hop_len, frame_index, lib: Library | None = None) -> int:
+    lib = lib or default_library()
+    frame = np.ascontiguousarray(frame, np.float32)
+    assert output.dtype == np.float32 and output.flags.c_contiguous
+    return lib.vv_dsp_overlap_add(_ptr(frame), _ptr(output), output.size, frame.size, hop_len, frame_index)
+
+
+# ----------------------------------------------------------------------------- STFT handle
+class Stft:
+    """vv_dsp_stft handle: create / process / reconstruct / spectrogram + the batched extension."""
+
+    def __init__(self, fft_size, hop_size, window="hann", lib: Library | None = None):
+        self.lib = lib or default_library()
+        self.nfft, self.hop = int(fft_size), int(hop_size)
+        self.bins = self.nfft // 2 + 1
+        self._h = _vp()
+        p = StftParams(self.nfft, self.hop, _win_id(window))
+        st = self.lib.vv_dsp_stft_create(C.byref(p), C.byref(self._h))
+        _check(self.lib, st, "vv_dsp_stft_create")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.vv_dsp_stft_destroy(self._h)
+            self._h = _vp()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # --- reference per-frame API
+    def process(self, frame):
+        frame = np.ascontiguousarray(frame, np.float32)
+        assert frame.size == self.nfft
+        out = np.empty(self.nfft, np.complex64)
+        _check(self.lib, self.lib.vv_dsp_stft_process(self._h, _ptr(frame), _ptr(out)), "vv_dsp_stft_process")
+        return out
+
+    def reconstruct(self, spec, out_add, norm_add=None):
+        spec = np.ascontiguousarray(spec, np.complex64)
+        assert spec.size == self.nfft and out_add.dtype == np.float32 and out_add.size >= self.nfft
+        _check(self.lib, self.lib.vv_dsp_stft_reconstruct(self._h, _ptr(spec), _ptr(out_add), _ptr(norm_add)),
+               "vv_dsp_stft_reconstruct")
+
+    def spectrogram(self, signal):
+        signal = np.ascontiguousarray(signal, np.float32)
+        frames = self.num_frames(signal.size, "spectrogram")
+        out = np.empty((frames, self.nfft), np.float32)
+        nf = _sz(0)
+        keep = signal if signal.size else np.zeros(1, np.float32)
+        _check(self.lib, self.lib.vv_dsp_stft_spectrogram(self._h, _ptr(keep), signal.size, _ptr(out), C.byref(nf)),
+               "vv_dsp_stft_spectrogram")
+        assert nf.value == frames
+        return out
+
+    # --- batched extension (include/vv_dsp/b200.h)
+    def num_frames(self, n, convention="valid") -> int:
+        return int(self.lib.vv_dsp_stft_num_frames(self._h, n, CONVENTIONS[convention]))
+
+    def set_stream(self, cuda_stream):
+        _check(self.lib, self.lib.vv_dsp_stft_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None),
+               "vv_dsp_stft_set_stream")
+
+    def synchronize(self):
+        _check(self.lib, self.lib.vv_dsp_stft_synchronize(self._h), "vv_dsp_stft_synchronize")
+
+    def batch_forward(self, signals, kind="complex", convention="valid", out=None):
+        """signals: [batch, n] float32, numpy (host) or torch CUDA tensor (device).  Returns
+        [batch, frames, bins] complex64 / float32 in the same kind of container unless `out` is given."""
+        dev_in = _is_device(signals)
+        if not dev_in:
+            signals = np.ascontiguousarray(signals, np.float32)
+        assert signals.ndim == 2
+        batch, n = int(signals.shape[0]), int(signals.shape[1])
+        pitch = int(signals.stride(0)) if dev_in else n
+        frames = self.num_frames(n, convention)
+        if out is None:
+            if dev_in:
+                import torch
+                out = torch.empty((batch, frames, self.bins), device=signals.device,
+                                  dtype=torch.complex64 if kind == "complex" else torch.float32)
+            else:
+                out = np.empty((batch, frames, self.bins), np.complex64 if kind == "complex" else np.float32)
+        nf = _sz(0)
+        st = self.lib.vv_dsp_stft_batch_forward(self._h, _ptr(signals), DEVICE if dev_in else HOST, batch, n, pitch,
+                                                CONVENTIONS[convention], KINDS[kind], _ptr(out),
+                                                DEVICE if _is_device(out) else HOST, 0, C.byref(nf))
+        _check(self.lib, st, "vv_dsp_stft_batch_forward")
+        assert nf.value == frames
+        return out
+
+    def batch_inverse(self, spectra, n_out, normalise=True, out=None):
+        """spectra: [batch, frames, bins] complex64 (numpy or torch CUDA).  Returns [batch, n_out] float32."""
+        dev_in = _is_device(spectra)
+        if not dev_in:
+            spectra = np.ascontiguousarray(spectra, np.complex64)
+        assert spectra.ndim == 3 and spectra.shape[2] == self.bins
+        batch, frames = int(spectra.shape[0]), int(spectra.shape[1])
+        if out is None:
+            if dev_in:
+                import torch
+                out = torch.empty((batch, n_out), device=spectra.device, dtype=torch.float32)
+            else:
+                out = np.empty((batch, n_out), np.float32)
+        keep = spectra if frames else None
+        st = self.lib.vv_dsp_stft_batch_inverse(self._h, _ptr(keep), DEVICE if dev_in else HOST, batch, frames, 0,
+                                                _ptr(out), DEVICE if _is_device(out) else HOST, n_out, 0, int(normalise))
+        _check(self.lib, st, "vv_dsp_stft_batch_inverse")
+        return out
+
+    def istft(self, half_spectra, n_out):
+        half_spectra = np.ascontiguousarray(half_spectra, np.complex64)
+        out = np.empty(n_out, np.float32)
+        st = self.lib.vv_dsp_stft_istft(self._h, _ptr(half_spectra) if half_spectra.size else None,
+                                        half_spectra.shape[0], _ptr(out), n_out)
+        _check(self.lib, st, "vv_dsp_stft_istft")
+        return out
+
+
+# ----------------------------------------------------------------------------- FFT plan
+class FftPlan:
+    """vv_dsp_fft_plan: make_plan / execute / destroy (reference include/vv_dsp/spectral/fft.h:190-252)."""
+
+    def __init__(self, n, ftype=FFT_C2C, direction=FFT_FORWARD, lib: Library | None = None):
+        self.lib = lib or default_library()
+        self.n, self.type, self.dir = int(n), int(ftype), int(direction)
+        self._p = _vp()
+        st = self.lib.vv_dsp_fft_make_plan(self.n, self.type, self.dir, C.byref(self._p))
+        _check(self.lib, st, "vv_dsp_fft_make_plan")
+
+    def execute(self, x):
+        n = self.n
+        if self.type == FFT_C2C:
+            x = np.ascontiguousarray(x, np.complex64); out = np.empty(n, np.complex64)
+        elif self.type == FFT_R2C:
+            x = np.ascontiguousarray(x, np.float32); out = np.empty(n // 2 + 1, np.complex64)
+        else:
+            x = np.ascontiguousarray(x, np.complex64); out = np.empty(n, np.float32)
+        _check(self.lib, self.lib.vv_dsp_fft_execute(self._p, _ptr(x), _ptr(out)), "vv_dsp_fft_execute")
+        return out
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self.lib.vv_dsp_fft_destroy(self._p)
+            self._p = _vp()
+
+    __del__ = close

@@ -1,0 +1,524 @@
+/*
+ * vvb_cuda.cu -- implementation of the thin C-ABI in include/vvb200_cuda.h: device
+ * plans (tables resident in HBM), kernel dispatch, memory / stream plumbing.
+ *
+ * Built by nvcc for sm_100a only (vv_dsp_b200/build.py).  There is no CPU code path:
+ * without a usable CUDA device every entry returns 6 (VV_DSP_ERROR_UNSUPPORTED) or
+ * 4 (VV_DSP_ERROR_INTERNAL) and the host library fails loudly.
+ * (-DVVB_EMU is the test-only emulator build under tests/emu/, see cuda_emu.h.)
+ */
+#include "vvb_direct_kernels.cuh"
+#include "../../../include/vvb200_cuda.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace vvb;
+
+/* ------------------------------------------------------------------ error plumbing */
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+extern "C" const char* vvb_last_error(void) { return g_err; }
+extern "C" unsigned long long vvb_kernel_launches(void) { return g_launches.load(); }
+
+static int fail(int code, const char* what, const char* detail)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, detail ? detail : "");
+    return code;
+}
+
+#ifdef VVB_EMU
+/* ---- emulator runtime: host memory stands in for HBM, streams are no-ops */
+namespace vvb_emu {
+Cta* g_cta = nullptr;
+uint3_emu g_threadIdx, g_blockIdx;
+dim3 g_blockDim, g_gridDim;
+char* g_dyn_smem = nullptr;
+}
+#define CK(expr) do { if ((expr) != 0) return fail(4, #expr, "emu"); } while (0)
+static int rt_num_sms() { return 3; }
+extern "C" int vvb_device_ready(void) { return 0; }
+extern "C" int vvb_malloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : fail(4, "malloc", "oom"); }
+extern "C" int vvb_free(void* p) { free(p); return 0; }
+extern "C" int vvb_host_alloc(void** p, size_t bytes) { return vvb_malloc(p, bytes); }
+extern "C" int vvb_host_free(void* p) { free(p); return 0; }
+extern "C" int vvb_memcpy_h2d(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
+extern "C" int vvb_memcpy_d2h(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
+static int emu_copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h)
+{
+    for (size_t r = 0; r < h; ++r) memcpy((char*)d + r * dp, (const char*)s + r * sp, w);
+    return 0;
+}
+extern "C" int vvb_memcpy2d_h2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, void*) { return emu_copy2d(d, dp, s, sp, w, h); }
+extern "C" int vvb_memcpy2d_d2h(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, void*) { return emu_copy2d(d, dp, s, sp, w, h); }
+extern "C" int vvb_memset(void* d, int v, size_t n, void*) { memset(d, v, n); return 0; }
+extern "C" int vvb_stream_create(void** s) { *s = malloc(1); return 0; }
+extern "C" int vvb_stream_destroy(void* s) { free(s); return 0; }
+extern "C" int vvb_stream_sync(void*) { return 0; }
+extern "C" int vvb_event_create(void** e) { *e = malloc(1); return 0; }
+extern "C" int vvb_event_destroy(void* e) { free(e); return 0; }
+extern "C" int vvb_event_record(void*, void*) { return 0; }
+extern "C" int vvb_stream_wait_event(void*, void*) { return 0; }
+#define VVB_LAUNCH(kern, grid, block, smem, stream, args) \
+    do { g_launches++; vvb_emu::launch(dim3(grid), dim3(block), smem, [&] { kern(args); }); } while (0)
+template <class K> static int rt_blocks_per_sm(K, int, size_t) { return 1; }
+#else
+/* ---- CUDA runtime */
+#define CK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(4, #expr, cudaGetErrorString(e_)); } while (0)
+static int rt_num_sms()
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+extern "C" int vvb_device_ready(void)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(6, "no CUDA device", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    int dev = 0, major = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return fail(6, "device is not sm_100-class", "this library ships sm_100a code only");
+    return 0;
+}
+extern "C" int vvb_malloc(void** p, size_t bytes) { CK(cudaMalloc(p, bytes ? bytes : 1)); return 0; }
+extern "C" int vvb_free(void* p) { if (p) CK(cudaFree(p)); return 0; }
+extern "C" int vvb_host_alloc(void** p, size_t bytes) { CK(cudaMallocHost(p, bytes ? bytes : 1)); return 0; }
+extern "C" int vvb_host_free(void* p) { if (p) CK(cudaFreeHost(p)); return 0; }
+extern "C" int vvb_memcpy_h2d(void* d, const void* s, size_t n, void* st) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, (cudaStream_t)st)); return 0; }
+extern "C" int vvb_memcpy_d2h(void* d, const void* s, size_t n, void* st) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, (cudaStream_t)st)); return 0; }
+extern "C" int vvb_memcpy2d_h2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, void* st)
+{
+    CK(cudaMemcpy2DAsync(d, dp, s, sp, w, h, cudaMemcpyHostToDevice, (cudaStream_t)st)); return 0;
+}
+extern "C" int vvb_memcpy2d_d2h(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, void* st)
+{
+    CK(cudaMemcpy2DAsync(d, dp, s, sp, w, h, cudaMemcpyDeviceToHost, (cudaStream_t)st)); return 0;
+}
+extern "C" int vvb_memset(void* d, int v, size_t n, void* st) { CK(cudaMemsetAsync(d, v, n, (cudaStream_t)st)); return 0; }
+extern "C" int vvb_stream_create(void** s) { cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); *s = st; return 0; }
+extern "C" int vvb_stream_destroy(void* s) { if (s) CK(cudaStreamDestroy((cudaStream_t)s)); return 0; }
+extern "C" int vvb_stream_sync(void* s) { CK(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
+extern "C" int vvb_event_create(void** e) { cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); *e = ev; return 0; }
+extern "C" int vvb_event_destroy(void* e) { if (e) CK(cudaEventDestroy((cudaEvent_t)e)); return 0; }
+extern "C" int vvb_event_record(void* e, void* s) { CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s)); return 0; }
+extern "C" int vvb_stream_wait_event(void* s, void* e) { CK(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0)); return 0; }
+#define VVB_LAUNCH(kern, grid, block, smem, stream, args) \
+    do { g_launches++; kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(args); CK(cudaGetLastError()); } while (0)
+/* opt in to the dynamic shared memory the kernel needs and ask how many CTAs fit per SM */
+template <class K> static int rt_blocks_per_sm(K kern, int threads, size_t smem)
+{
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) return 0;
+    return nb;
+}
+#endif
+
+/* -------------------------------------------------------------------- plan tables */
+/* Everything trigonometric is computed in double on the host and rounded once. */
+template <class C> static void build_tables(std::vector<float>& blob, const float* window)
+{
+    using TB = Tables<C>;
+    constexpr int M = C::M, N = 2 * M;
+    blob.assign(TB::TOTAL, 0.f);
+    for (int i = 0; i < N; ++i) {
+        const float w = window ? window[i] : 1.0f;
+        blob[TB::WIN + i] = w;
+        blob[TB::WSYN + i] = w * (1.0f / (float)M);   /* power-of-two scale: exact */
+    }
+    auto fill = [&](int off, int R, int NS) {
+        for (int r = 1; r < R; ++r)
+            for (int jm = 0; jm < NS; ++jm) {
+                const double ang = -2.0 * M_PI * (double)r * (double)jm / ((double)NS * R);
+                blob[off + 2 * ((r - 1) * NS + jm)] = (float)cos(ang);
+                blob[off + 2 * ((r - 1) * NS + jm) + 1] = (float)sin(ang);
+            }
+    };
+    fill(TB::TW2, C::R2, C::R1);
+    if (C::NP == 3) fill(TB::TW3, C::R3, C::R1 * C::R2);
+    for (int k = 0; k <= M / 2; ++k) {
+        const double ang = 2.0 * M_PI * (double)k / (double)N;
+        blob[TB::POST + 2 * k] = (float)(0.5 * cos(ang));
+        blob[TB::POST + 2 * k + 1] = (float)(0.5 * sin(ang));
+    }
+}
+
+/* the kernel configurations: M complex points = fft_size/2 for the real transforms */
+using Cfg128 = Cfg<128, 16, 16, 8>;
+using Cfg256 = Cfg<256, 16, 16, 16>;
+using Cfg512 = Cfg<512, 32, 32, 16>;
+using Cfg1024 = Cfg<1024, 32, 32, 32>;
+using Cfg2048 = Cfg<2048, 16, 16, 16, 8>;
+using Cfg4096 = Cfg<4096, 16, 16, 16, 16>;
+template <class C> struct Teams { static constexpr int G = (C::T >= 256) ? 2 : 256 / C::T; };
+
+template <class C> static constexpr size_t smem_fwd() { return sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3 + C::POST + 1) + 2 * Teams<C>::G * C::XBUF); }
+template <class C> static size_t smem_inv(int hop, bool ola) { return smem_fwd<C>() + (ola ? sizeof(float) * 2 * (2 * C::M - hop) : 0); }
+template <class C> static constexpr size_t smem_c2c() { return sizeof(float) * (2 * (C::TW2 + C::TW3) + 2 * Teams<C>::G * C::XBUF); }
+
+static bool fast_size(size_t m) { return m == 128 || m == 256 || m == 512 || m == 1024 || m == 2048 || m == 4096; }
+
+struct vvb_engine {
+    size_t nfft = 0, hop = 0;
+    bool fast = false;
+    int sms = 0;
+    float* d_tables = nullptr;       /* fast: Tables<C> blob */
+    float* d_win = nullptr;          /* direct: window */
+    float2* d_wtab = nullptr;        /* direct: (cos,-sin)(2 pi j/n) */
+    float* d_scratch = nullptr;      /* direct: synthesis frames */
+    size_t scratch_bytes = 0;
+};
+
+static void make_wtab(std::vector<float>& t, size_t n)
+{
+    t.resize(2 * n);
+    for (size_t j = 0; j < n; ++j) {
+        const double ang = 2.0 * M_PI * (double)j / (double)n;
+        t[2 * j] = (float)cos(ang);
+        t[2 * j + 1] = (float)-sin(ang);
+    }
+}
+
+static int upload(float** d, const std::vector<float>& h)
+{
+    int st = vvb_malloc((void**)d, h.size() * sizeof(float));
+    if (st) return st;
+    st = vvb_memcpy_h2d(*d, h.data(), h.size() * sizeof(float), nullptr);
+    if (st) return st;
+    return vvb_stream_sync(nullptr);
+}
+
+extern "C" int vvb_engine_create(size_t nfft, size_t hop, const float* window, vvb_engine** out)
+{
+    if (!out || !window) return fail(1, "vvb_engine_create", "null");
+    *out = nullptr;
+    if (nfft == 0 || hop == 0 || hop > nfft) return fail(2, "vvb_engine_create", "size");
+#ifndef VVB_EMU
+    if (int st = vvb_device_ready()) return st;
+#endif
+    vvb_engine* e = new (std::nothrow) vvb_engine();
+    if (!e) return fail(4, "vvb_engine_create", "oom");
+    e->nfft = nfft; e->hop = hop; e->sms = rt_num_sms();
+    e->fast = (nfft % 2 == 0) && fast_size(nfft / 2);
+    int st = 0;
+    std::vector<float> blob;
+    if (e->fast) {
+        switch (nfft / 2) {
+        case 128: build_tables<Cfg128>(blob, window); break;
+        case 256: build_tables<Cfg256>(blob, window); break;
+        case 512: build_tables<Cfg512>(blob, window); break;
+        case 1024: build_tables<Cfg1024>(blob, window); break;
+        case 2048: build_tables<Cfg2048>(blob, window); break;
+        default: build_tables<Cfg4096>(blob, window); break;
+        }
+        st = upload(&e->d_tables, blob);
+    } else {
+        std::vector<float> w(window, window + nfft), t;
+        make_wtab(t, nfft);
+        st = upload(&e->d_win, w);
+        if (!st) st = upload((float**)&e->d_wtab, t);
+    }
+    if (st) { vvb_engine_destroy(e); return st; }
+    *out = e;
+    return 0;
+}
+
+extern "C" void vvb_engine_destroy(vvb_engine* e)
+{
+    if (!e) return;
+    vvb_free(e->d_tables); vvb_free(e->d_win); vvb_free(e->d_wtab); vvb_free(e->d_scratch);
+    delete e;
+}
+
+extern "C" int vvb_engine_is_fast(const vvb_engine* e) { return e && e->fast; }
+
+static int persistent_grid(long long work, int per_sm, int sms)
+{
+    long long cap = (long long)(per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    long long g = work < cap ? work : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+/* ------------------------------------------------------------------ forward launch */
+template <class C, int OUT> static int launch_forward_t(vvb_engine* e, FwdArgs a, void* stream)
+{
+    constexpr int G = Teams<C>::G;
+    a.groups_per_signal = (a.frames + G - 1) / G;
+    static int per_sm = -1;
+    auto kern = stft_forward_kernel<C, G, OUT>;
+    const size_t smem = smem_fwd<C>();
+    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
+    if (per_sm == 0) return fail(4, "stft_forward_kernel", "does not fit on this device");
+    const long long groups = (long long)a.groups_per_signal * (long long)(a.num_groups);   /* num_groups carries batch here */
+    if (groups > 0x7fffffffLL) return fail(2, "vvb_stft_forward", "batch*frames too large for one launch");
+    a.num_groups = (int)groups;
+    if (groups == 0) return 0;
+    VVB_LAUNCH(kern, persistent_grid(groups, per_sm, e->sms), C::T * G, smem, stream, a);
+    return 0;
+}
+template <class C> static int launch_forward(vvb_engine* e, const FwdArgs& a, int kind, void* stream)
+{
+    switch (kind) {
+    case OUT_COMPLEX: return launch_forward_t<C, OUT_COMPLEX>(e, a, stream);
+    case OUT_POWER: return launch_forward_t<C, OUT_POWER>(e, a, stream);
+    case OUT_MAGNITUDE: return launch_forward_t<C, OUT_MAGNITUDE>(e, a, stream);
+    default: return fail(3, "vvb_stft_forward", "bad out_kind");
+    }
+}
+
+extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, size_t n, size_t x_pitch, size_t frames,
+                                int pad_mode, int out_kind, void* d_out, size_t out_pitch, void* stream)
+{
+    if (!e || !d_x || !d_out) return fail(1, "vvb_stft_forward", "null");
+    if (batch == 0 || frames == 0) return 0;
+    if (frames > 0x7fffffffu || batch > 0x7fffffffu) return fail(2, "vvb_stft_forward", "too many frames");
+    if (out_pitch < e->nfft / 2 + 1) return fail(2, "vvb_stft_forward", "out_pitch < bins");
+    if (e->fast) {
+        FwdArgs a;
+        a.x = d_x; a.x_pitch = (long long)x_pitch; a.n = (long long)n;
+        a.frames = (int)frames; a.hop = (int)e->hop; a.pad_mode = pad_mode;
+        a.out = d_out; a.out_pitch = (long long)out_pitch; a.tables = e->d_tables;
+        a.num_groups = (int)batch; a.groups_per_signal = 0;
+        switch (e->nfft / 2) {
+        case 128: return launch_forward<Cfg128>(e, a, out_kind, stream);
+        case 256: return launch_forward<Cfg256>(e, a, out_kind, stream);
+        case 512: return launch_forward<Cfg512>(e, a, out_kind, stream);
+        case 1024: return launch_forward<Cfg1024>(e, a, out_kind, stream);
+        case 2048: return launch_forward<Cfg2048>(e, a, out_kind, stream);
+        default: return launch_forward<Cfg4096>(e, a, out_kind, stream);
+        }
+    }
+    DirFwdArgs a;
+    a.x = d_x; a.x_pitch = (long long)x_pitch; a.n = (long long)n;
+    a.batch = (int)batch; a.frames = (int)frames; a.hop = (int)e->hop; a.nfft = (int)e->nfft;
+    a.pad_mode = pad_mode; a.out_kind = out_kind; a.out = d_out; a.out_pitch = (long long)out_pitch;
+    a.win = e->d_win; a.wtab = e->d_wtab;
+    const long long total = (long long)batch * frames * (e->nfft / 2 + 1);
+    VVB_LAUNCH(stft_forward_direct_kernel, persistent_grid((total + 127) / 128, 16, e->sms), 128, 0, stream, a);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ inverse launch */
+template <class C, bool OLA> static int launch_inverse_t(vvb_engine* e, InvArgs a, long long batch, void* stream)
+{
+    constexpr int G = Teams<C>::G;
+    static int per_sm_cache[2] = {-1, -1};
+    static size_t smem_cache = 0;
+    auto kern = stft_inverse_kernel<C, G, OLA>;
+    const size_t smem = smem_inv<C>(a.hop, OLA);
+    int& per_sm = per_sm_cache[0];
+    if (per_sm < 0 || smem != smem_cache) { per_sm = rt_blocks_per_sm(kern, C::T * G, smem); smem_cache = smem; }
+    if (per_sm == 0) return fail(4, "stft_inverse_kernel", "does not fit on this device");
+    long long items;
+    if (OLA) {
+        /* split every signal into chunks of frames so the persistent grid has >= ~4 items per CTA;
+         * each chunk re-synthesises up to K-1 halo frames, so chunks are kept long (>= 16 rounds) */
+        const long long cap = (long long)per_sm * e->sms;
+        long long want = (4 * cap + batch - 1) / batch;                 /* chunks per signal wanted */
+        long long max_chunks = a.frames / (16 * G);
+        if (max_chunks < 1) max_chunks = 1;
+        if (want > max_chunks) want = max_chunks;
+        if (want < 1) want = 1;
+        long long cf = (a.frames + want - 1) / want;
+        cf = (cf + G - 1) / G * G;                                      /* whole rounds */
+        a.chunk_frames = (int)cf;
+        a.chunks_per_signal = (int)((a.frames + cf - 1) / cf);
+        items = batch * a.chunks_per_signal;
+    } else {
+        items = (a.frames + G - 1) / G;
+    }
+    if (items > 0x7fffffffLL) return fail(2, "vvb_stft_inverse", "too many work items");
+    a.num_items = (int)items;
+    if (items == 0) return 0;
+    VVB_LAUNCH(kern, persistent_grid(items, per_sm, e->sms), C::T * G, smem, stream, a);
+    return 0;
+}
+
+template <bool OLA> static int dispatch_inverse(vvb_engine* e, const InvArgs& a, long long batch, void* stream)
+{
+    switch (e->nfft / 2) {
+    case 128: return launch_inverse_t<Cfg128, OLA>(e, a, batch, stream);
+    case 256: return launch_inverse_t<Cfg256, OLA>(e, a, batch, stream);
+    case 512: return launch_inverse_t<Cfg512, OLA>(e, a, batch, stream);
+    case 1024: return launch_inverse_t<Cfg1024, OLA>(e, a, batch, stream);
+    case 2048: return launch_inverse_t<Cfg2048, OLA>(e, a, batch, stream);
+    default: return launch_inverse_t<Cfg4096, OLA>(e, a, batch, stream);
+    }
+}
+
+static int ensure_scratch(vvb_engine* e, size_t bytes)
+{
+    if (e->scratch_bytes >= bytes) return 0;
+    vvb_free(e->d_scratch); e->d_scratch = nullptr; e->scratch_bytes = 0;
+    int st = vvb_malloc((void**)&e->d_scratch, bytes);
+    if (!st) e->scratch_bytes = bytes;
+    return st;
+}
+
+extern "C" int vvb_stft_inverse_frames(vvb_engine* e, const vvb_cpx* d_spec, size_t count, size_t spec_pitch,
+                                       float* d_frames, void* stream)
+{
+    if (!e || !d_spec || !d_frames) return fail(1, "vvb_stft_inverse_frames", "null");
+    if (count == 0) return 0;
+    if (count > 0x7fffffffu) return fail(2, "vvb_stft_inverse_frames", "too many frames");
+    if (e->fast) {
+        InvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.spec = reinterpret_cast<const float2*>(d_spec); a.spec_pitch = (long long)spec_pitch;
+        a.frames = (int)count; a.hop = (int)e->hop; a.y = d_frames; a.tables = e->d_tables;
+        return dispatch_inverse<false>(e, a, 1, stream);
+    }
+    DirInvArgs a;
+    a.spec = reinterpret_cast<const float2*>(d_spec); a.spec_pitch = (long long)spec_pitch;
+    a.count = (long long)count; a.nfft = (int)e->nfft; a.frames_out = d_frames; a.win = e->d_win; a.wtab = e->d_wtab;
+    const long long total = (long long)count * e->nfft;
+    VVB_LAUNCH(stft_inverse_direct_kernel, persistent_grid((total + 127) / 128, 16, e->sms), 128, 0, stream, a);
+    return 0;
+}
+
+extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t batch, size_t frames, size_t spec_pitch,
+                                float* d_y, size_t n_out, size_t y_pitch, const float* d_inv_norm, void* stream)
+{
+    if (!e || !d_y || (!d_spec && frames)) return fail(1, "vvb_stft_inverse", "null");
+    if (batch == 0 || n_out == 0) return 0;
+    if (frames > 0x7fffffffu) return fail(2, "vvb_stft_inverse", "too many frames");
+    if (frames == 0) {
+        for (size_t b = 0; b < batch; ++b)
+            if (int st = vvb_memset(d_y + b * y_pitch, 0, n_out * sizeof(float), stream)) return st;
+        return 0;
+    }
+    if (e->fast) {
+        InvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.spec = reinterpret_cast<const float2*>(d_spec); a.spec_pitch = (long long)spec_pitch;
+        a.frames = (int)frames; a.hop = (int)e->hop;
+        a.y = d_y; a.y_pitch = (long long)y_pitch; a.n_out = (long long)n_out;
+        a.inv_norm = d_inv_norm; a.tables = e->d_tables;
+        return dispatch_inverse<true>(e, a, (long long)batch, stream);
+    }
+    /* direct path: synthesis frames to HBM scratch, then the stand-alone overlap-add kernel */
+    const size_t count = batch * frames;
+    if (int st = ensure_scratch(e, count * e->nfft * sizeof(float))) return st;
+    DirInvArgs d;
+    d.spec = reinterpret_cast<const float2*>(d_spec); d.spec_pitch = (long long)spec_pitch;
+    d.count = (long long)count; d.nfft = (int)e->nfft; d.frames_out = e->d_scratch; d.win = e->d_win; d.wtab = e->d_wtab;
+    const long long total = (long long)count * e->nfft;
+    VVB_LAUNCH(stft_inverse_direct_kernel, persistent_grid((total + 127) / 128, 16, e->sms), 128, 0, stream, d);
+    OlaArgs o;
+    o.frames_in = e->d_scratch; o.batch = (int)batch; o.frames = (int)frames; o.hop = (int)e->hop; o.nfft = (int)e->nfft;
+    o.y = d_y; o.y_pitch = (long long)y_pitch; o.n_out = (long long)n_out; o.inv_norm = d_inv_norm;
+    const long long tot2 = (long long)batch * n_out;
+    VVB_LAUNCH(overlap_add_kernel, persistent_grid((tot2 + 255) / 256, 8, e->sms), 256, 0, stream, o);
+    return 0;
+}
+
+/* ---------------------------------------------------------------------- FFT engine */
+struct vvb_fft_engine {
+    size_t n = 0;
+    int type = 0, dir = 0, sms = 0;
+    bool fast_c2c = false;
+    float* d_tables = nullptr;       /* C2C fast: Tables<C> blob with M = n */
+    float2* d_wtab = nullptr;        /* direct C2C */
+    vvb_engine* real = nullptr;      /* R2C / C2R: STFT engine with a boxcar window, hop = n */
+};
+
+extern "C" int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine** out)
+{
+    if (!out) return fail(1, "vvb_fft_engine_create", "null");
+    *out = nullptr;
+    if (n == 0) return fail(2, "vvb_fft_engine_create", "n == 0");
+    if (type < 0 || type > 2 || (dir != 1 && dir != -1)) return fail(3, "vvb_fft_engine_create", "enum");
+#ifndef VVB_EMU
+    if (int st = vvb_device_ready()) return st;
+#endif
+    vvb_fft_engine* e = new (std::nothrow) vvb_fft_engine();
+    if (!e) return fail(4, "vvb_fft_engine_create", "oom");
+    e->n = n; e->type = type; e->dir = dir; e->sms = rt_num_sms();
+    int st = 0;
+    if (type == 0) {
+        e->fast_c2c = fast_size(n);
+        std::vector<float> blob;
+        if (e->fast_c2c) {
+            switch (n) {
+            case 128: build_tables<Cfg128>(blob, nullptr); break;
+            case 256: build_tables<Cfg256>(blob, nullptr); break;
+            case 512: build_tables<Cfg512>(blob, nullptr); break;
+            case 1024: build_tables<Cfg1024>(blob, nullptr); break;
+            case 2048: build_tables<Cfg2048>(blob, nullptr); break;
+            default: build_tables<Cfg4096>(blob, nullptr); break;
+            }
+            st = upload(&e->d_tables, blob);
+        } else {
+            make_wtab(blob, n);
+            st = upload((float**)&e->d_wtab, blob);
+        }
+    } else {
+        std::vector<float> ones(n, 1.0f);
+        st = vvb_engine_create(n, n, ones.data(), &e->real);
+    }
+    if (st) { vvb_fft_engine_destroy(e); return st; }
+    *out = e;
+    return 0;
+}
+
+extern "C" void vvb_fft_engine_destroy(vvb_fft_engine* e)
+{
+    if (!e) return;
+    vvb_free(e->d_tables); vvb_free(e->d_wtab); vvb_engine_destroy(e->real);
+    delete e;
+}
+
+template <class C> static int launch_c2c(vvb_fft_engine* e, C2CArgs a, void* stream)
+{
+    constexpr int G = Teams<C>::G;
+    static int per_sm = -1;
+    auto kern = fft_c2c_kernel<C, G>;
+    const size_t smem = smem_c2c<C>();
+    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
+    if (per_sm == 0) return fail(4, "fft_c2c_kernel", "does not fit on this device");
+    const long long groups = (a.batch + G - 1) / G;
+    VVB_LAUNCH(kern, persistent_grid(groups, per_sm, e->sms), C::T * G, smem, stream, a);
+    return 0;
+}
+
+extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, size_t batch, void* stream)
+{
+    if (!e || !d_in || !d_out) return fail(1, "vvb_fft_exec", "null");
+    if (batch == 0) return 0;
+    if (batch > 0x7fffffffu) return fail(2, "vvb_fft_exec", "batch");
+    if (e->type == 0) {
+        if (e->fast_c2c) {
+            C2CArgs a;
+            a.in = (const float2*)d_in; a.out = (float2*)d_out; a.batch = (int)batch; a.inverse = e->dir < 0; a.tables = e->d_tables;
+            switch (e->n) {
+            case 128: return launch_c2c<Cfg128>(e, a, stream);
+            case 256: return launch_c2c<Cfg256>(e, a, stream);
+            case 512: return launch_c2c<Cfg512>(e, a, stream);
+            case 1024: return launch_c2c<Cfg1024>(e, a, stream);
+            case 2048: return launch_c2c<Cfg2048>(e, a, stream);
+            default: return launch_c2c<Cfg4096>(e, a, stream);
+            }
+        }
+        /* the direct kernel reads every input of a transform for every output: out must not alias in */
+        DirC2CArgs a;
+        a.in = (const float2*)d_in; a.out = (float2*)d_out; a.batch = (long long)batch; a.n = (int)e->n;
+        a.inverse = e->dir < 0; a.wtab = e->d_wtab;
+        if (d_in == d_out) return fail(3, "vvb_fft_exec", "direct C2C cannot run in place (host stages a copy)");
+        const long long total = (long long)batch * e->n;
+        VVB_LAUNCH(fft_c2c_direct_kernel, persistent_grid((total + 127) / 128, 16, e->sms), 128, 0, stream, a);
+        return 0;
+    }
+    const size_t bins = e->n / 2 + 1;
+    if (e->type == 1)   /* R2C: one frame per transform, boxcar window, complex half spectrum */
+        return vvb_stft_forward(e->real, (const float*)d_in, batch, e->n, e->n, 1, PAD_ZERO, OUT_COMPLEX, d_out, bins, stream);
+    return vvb_stft_inverse_frames(e->real, (const vvb_cpx*)d_in, batch, bins, (float*)d_out, stream);   /* C2R */
+}

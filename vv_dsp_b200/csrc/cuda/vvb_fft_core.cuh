@@ -1,0 +1,250 @@
+/*
+ * vvb_fft_core.cuh -- register/shared-memory FFT building blocks (sm_100a).
+ *
+ * Replaces the arithmetic of the reference's src/spectral/fft_kiss.c:27-74 (iterative
+ * radix-2 with a float twiddle recurrence) with a Stockham autosort FFT:
+ *   - a "team" of T = M/E threads owns one M-point complex transform, E points per
+ *     thread held in registers;
+ *   - each pass is a radix-R (R = 8/16/32) DFT done entirely in registers with
+ *     compile-time twiddles, followed by one exchange through shared memory;
+ *   - inter-pass twiddles come from tables computed in double on the host (no
+ *     recurrence, so the error does not grow with N like the reference's does).
+ * Real-input transforms of length N = 2M are done as one M-point complex transform
+ * plus a split step (vvb_stft_kernels.cu), i.e. half the flops of the reference's
+ * C2C-on-(x,0) (src/spectral/stft.c:83-90).
+ *
+ * Index algebra of one pass (radix R, Ns = product of the radices already done),
+ * work item j in [0, M/R):
+ *     v[r]  = in[j + r*M/R]                      r = 0..R-1
+ *     v[r] *= exp(-2*pi*i * r*(j % Ns) / (Ns*R))
+ *     v     = DFT_R(v)
+ *     out[(j/Ns)*Ns*R + (j % Ns) + r*Ns] = v[r]
+ * After the last pass `out` is in natural frequency order.
+ */
+#pragma once
+
+#ifdef VVB_EMU
+#include "cuda_emu.h"
+#define VVB_DEV inline __attribute__((always_inline))
+#define VVB_CX constexpr
+#else
+#include <cuda_runtime.h>
+#define VVB_DEV __device__ __forceinline__
+#define VVB_CX __host__ __device__ constexpr
+#endif
+
+namespace vvb {
+
+/* ---------------------------------------------------------------- compile-time trig */
+constexpr double kPi = 3.141592653589793238462643383279502884;
+
+constexpr double ct_sin_small(double x)   /* |x| <= pi/4 */
+{
+    double term = x, sum = x, x2 = x * x;
+    for (int i = 1; i < 12; ++i) { term *= -x2 / ((2 * i) * (2 * i + 1)); sum += term; }
+    return sum;
+}
+constexpr double ct_cos_small(double x)
+{
+    double term = 1.0, sum = 1.0, x2 = x * x;
+    for (int i = 1; i < 12; ++i) { term *= -x2 / ((2 * i - 1) * (2 * i)); sum += term; }
+    return sum;
+}
+/* cos / sin of 2*pi*num/den for 0 <= num < den, octant-reduced so the series stays accurate */
+constexpr double ct_cos2pi(int num, int den)
+{
+    int n8 = (8 * num) / den;                         /* octant 0..7 */
+    double frac = (double)num / den;
+    switch (n8) {
+    case 0: return ct_cos_small(2 * kPi * frac);
+    case 1: case 2: return -ct_sin_small(2 * kPi * (frac - 0.25));
+    case 3: case 4: return -ct_cos_small(2 * kPi * (frac - 0.5));
+    case 5: case 6: return ct_sin_small(2 * kPi * (frac - 0.75));
+    default: return ct_cos_small(2 * kPi * (frac - 1.0));
+    }
+}
+constexpr double ct_sin2pi(int num, int den)
+{
+    int n8 = (8 * num) / den;
+    double frac = (double)num / den;
+    switch (n8) {
+    case 0: return ct_sin_small(2 * kPi * frac);
+    case 1: case 2: return ct_cos_small(2 * kPi * (frac - 0.25));
+    case 3: case 4: return -ct_sin_small(2 * kPi * (frac - 0.5));
+    case 5: case 6: return -ct_cos_small(2 * kPi * (frac - 0.75));
+    default: return ct_sin_small(2 * kPi * (frac - 1.0));
+    }
+}
+
+template <int N, int I> struct TwC {
+    static constexpr float c = (float)ct_cos2pi(I, N);
+    static constexpr float s = (float)ct_sin2pi(I, N);
+};
+
+/* ------------------------------------------------------------------ complex helpers */
+VVB_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+VVB_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+VVB_DEV float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+
+/* x * exp(-2*pi*i*I/N), trivial factors resolved at compile time */
+template <int N, int I> VVB_DEV float2 mul_w(float2 x)
+{
+    if constexpr (I == 0) {
+        return x;
+    } else if constexpr (4 * I == N) {            /* -i */
+        return make_float2(x.y, -x.x);
+    } else if constexpr (2 * I == N) {            /* -1 */
+        return make_float2(-x.x, -x.y);
+    } else if constexpr (8 * I == N) {            /* (1-i)/sqrt2 */
+        constexpr float h = 0.70710678118654752440f;
+        return make_float2((x.x + x.y) * h, (x.y - x.x) * h);
+    } else if constexpr (8 * I == 3 * N) {        /* (-1-i)/sqrt2 */
+        constexpr float h = 0.70710678118654752440f;
+        return make_float2((x.y - x.x) * h, -(x.x + x.y) * h);
+    } else {
+        constexpr float c = TwC<N, I>::c, s = TwC<N, I>::s;   /* w = c - i s */
+        return make_float2(x.x * c + x.y * s, x.y * c - x.x * s);
+    }
+}
+
+/* ------------------------------------------------- in-register DFT, radix-2 DIF tree */
+template <int... Is> struct iseq {};
+template <int N, int... Is> struct make_iseq : make_iseq<N - 1, N - 1, Is...> {};
+template <int... Is> struct make_iseq<0, Is...> { using type = iseq<Is...>; };
+
+template <int N, int O, int I> VVB_DEV void dif_bfly(float2* v)
+{
+    const float2 a = v[O + I], b = v[O + I + N / 2];
+    v[O + I] = cadd(a, b);
+    v[O + I + N / 2] = mul_w<N, I>(csub(a, b));
+}
+template <int N, int O, int... Is> VVB_DEV void dif_stage(float2* v, iseq<Is...>)
+{
+    (dif_bfly<N, O, Is>(v), ...);
+}
+/* DFT of v[O..O+N), result in bit-reversed register order: X[k] sits in v[O + bitrev(k)] */
+template <int N, int O> VVB_DEV void fft_dif(float2* v)
+{
+    if constexpr (N >= 2) {
+        dif_stage<N, O>(v, typename make_iseq<N / 2>::type{});
+        fft_dif<N / 2, O>(v);
+        fft_dif<N / 2, O + N / 2>(v);
+    }
+}
+
+VVB_CX int ct_log2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+VVB_CX int ct_bitrev(int x, int n)
+{
+    int r = 0;
+    for (int b = ct_log2(n); b > 0; --b) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+
+/* ------------------------------------------------------------ team configuration */
+/* M complex points, E per thread, up to three passes with radices R1*R2*R3 == M */
+template <int M_, int E_, int R1_, int R2_, int R3_ = 1> struct Cfg {
+    static constexpr int M = M_, E = E_, T = M_ / E_;
+    static constexpr int R1 = R1_, R2 = R2_, R3 = R3_;
+    static constexpr int NP = (R3_ > 1) ? 3 : 2;
+    static constexpr int XBUF = M_ + M_ / R1_;               /* padded float2 per team buffer */
+    static constexpr int TW2 = (R2_ - 1) * R1_;               /* pass-2 twiddles (float2) */
+    static constexpr int TW3 = (R3_ > 1) ? (R3_ - 1) * R1_ * R2_ : 0;
+    static constexpr int POST = M_ / 2 + 1;                   /* split-step twiddles */
+    static_assert(R1_ * R2_ * R3_ == M_, "radices must multiply to M");
+    static_assert(E_ % R1_ == 0 && E_ % R2_ == 0 && E_ % R3_ == 0, "E must be a multiple of every radix");
+    static_assert(E_ >= 2 && (M_ / 2) % T == 0, "split step needs M/2 pairs divisible over the team");
+    /* padded shared-memory position: one float2 of padding every R1 elements makes the
+     * stride-R1 writes of pass 1 hit 16 distinct bank pairs per half warp */
+    VVB_DEV static int pad(int i) { return i + i / R1_; }
+};
+
+/* team barrier: sub-warp and warp teams use __syncwarp (all teams of a warp run in
+ * lockstep on the same control path), larger teams a named barrier per team */
+template <int T> VVB_DEV void team_sync(int team)
+{
+    if constexpr (T <= 32) {
+        __syncwarp();
+    } else {
+#ifdef VVB_EMU
+        emu_named_barrier(1 + team, T);
+#else
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(T) : "memory");
+#endif
+    }
+}
+
+/* One Stockham pass on the team's registers.
+ *   FIRST: v was filled by the caller (no shared-memory read, Ns == 1, no twiddle)
+ *   LAST : results stay in registers: X[j + r*NS] = v[q*R + bitrev(r)], j = t + T*q
+ * tw: this pass's table, tw[(r-1)*NS + (j % NS)] = exp(-2 pi i r (j%NS) / (NS*R)). */
+template <class C, int R, int NS, bool FIRST, bool LAST>
+VVB_DEV void stockham_pass(float2 (&v)[C::E], float2* xb, const float2* tw, int t, int team)
+{
+    constexpr int NQ = C::E / R;
+    constexpr int STRIDE = C::M / R;
+    if constexpr (!FIRST) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int j = t + C::T * q;
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[q * R + r] = xb[C::pad(j + r * STRIDE)];
+        }
+        team_sync<C::T>(team);     /* everyone has read before anyone overwrites xb */
+        if constexpr (NS > 1) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int jm = (t + C::T * q) % NS;
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[q * R + r] = cmul(v[q * R + r], tw[(r - 1) * NS + jm]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) fft_dif<R, 0>(&v[q * R]);
+    if constexpr (!LAST) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int j = t + C::T * q;
+            const int j0 = (j / NS) * NS * R + (j % NS);
+#pragma unroll
+            for (int r = 0; r < R; ++r) xb[C::pad(j0 + r * NS)] = v[q * R + ct_bitrev(r, R)];
+        }
+        team_sync<C::T>(team);
+    }
+}
+
+/* All passes of an M-point forward DFT.  On entry v holds pass-1 input:
+ *     v[q*R1 + r] = z[j + r*M/R1],  j = t + T*q
+ * On exit it holds the spectrum of the last pass's items:
+ *     Z[j + r*NSL] = v[q*RL + bitrev_RL(r)],  j = t + T*q,  NSL = M/RL  (RL = last radix). */
+template <class C> VVB_DEV void team_fft(float2 (&v)[C::E], float2* xb, const float2* tw2, const float2* tw3, int t, int team)
+{
+    if constexpr (C::NP == 2) {
+        stockham_pass<C, C::R1, 1, true, false>(v, xb, nullptr, t, team);
+        stockham_pass<C, C::R2, C::R1, false, true>(v, xb, tw2, t, team);
+    } else {
+        stockham_pass<C, C::R1, 1, true, false>(v, xb, nullptr, t, team);
+        stockham_pass<C, C::R2, C::R1, false, false>(v, xb, tw2, t, team);
+        stockham_pass<C, C::R3, C::R1 * C::R2, false, true>(v, xb, tw3, t, team);
+    }
+}
+
+template <class C> struct LastPass {
+    static constexpr int R = (C::NP == 2) ? C::R2 : C::R3;
+    static constexpr int NS = C::M / R;
+    static constexpr int NQ = C::E / R;
+};
+
+/* Write the register-resident spectrum to the team buffer in natural order (padded). */
+template <class C> VVB_DEV void team_store_natural(const float2 (&v)[C::E], float2* xb, int t)
+{
+    using L = LastPass<C>;
+#pragma unroll
+    for (int q = 0; q < L::NQ; ++q) {
+        const int j = t + C::T * q;
+#pragma unroll
+        for (int r = 0; r < L::R; ++r) xb[C::pad(j + r * L::NS)] = v[q * L::R + ct_bitrev(r, L::R)];
+    }
+}
+
+}  // namespace vvb

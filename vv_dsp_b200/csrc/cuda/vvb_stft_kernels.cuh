@@ -1,0 +1,420 @@
+/*
+ * vvb_stft_kernels.cuh -- the STFT / ISTFT hot-path kernels (sm_100a).
+ *
+ * stft_forward_kernel  replaces, for a whole batch, the per-frame chain
+ *     frame gather + zero/reflect pad   src/spectral/stft.c:127-130, src/core/framing.c:95-118
+ *     window multiply                   src/core/vv_dsp_vectorized_math_fallback.c:24-26
+ *     real->complex pack + C2C forward  src/spectral/stft.c:85-90, src/spectral/fft_kiss.c:27-67
+ *     magnitude / power                 src/spectral/stft.c:133-140
+ *   in ONE kernel: the window is applied while the samples are loaded into the registers
+ *   of the first FFT pass, the N-point real transform is an N/2-point complex Stockham FFT
+ *   plus a split step, and |X|^2 / |X| / X is formed in the split step and stored once.
+ *
+ * stft_inverse_kernel  replaces
+ *     C2C backward + 1/n                src/spectral/fft_kiss.c:27-74
+ *     synthesis window + OLA + norm     src/spectral/stft.c:103-108
+ *     caller-side normalise             tools/dump_stft_roundtrip.c:50-54
+ *   in ONE kernel: Hermitian half spectrum -> merged N/2-point complex spectrum -> inverse
+ *   Stockham FFT (forward machinery on re/im-swapped data) -> times w/M -> each team parks
+ *   its windowed frame in its own shared-memory slot -> after a CTA barrier every output
+ *   sample is summed ONCE, by one thread, from the slots that cover it, in ascending frame
+ *   order (the reference's accumulation order) -> times 1/sum(w^2) -> one coalesced store.
+ *   No atomics anywhere; partial sums that belong to later frames are carried in shared
+ *   memory from one round of G frames to the next.
+ */
+#pragma once
+#include "vvb_fft_core.cuh"
+#include <stdint.h>
+
+namespace vvb {
+
+enum { OUT_COMPLEX = 0, OUT_POWER = 1, OUT_MAGNITUDE = 2 };
+enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
+
+/* float offsets of the per-plan table blob in global memory (host builds it, vvb_runtime.cu) */
+template <class C> struct Tables {
+    static constexpr int N = 2 * C::M;
+    static constexpr int WIN = 0;                      /* analysis window w[N] */
+    static constexpr int WSYN = WIN + N;               /* synthesis window w[N]/M */
+    static constexpr int TW2 = WSYN + N;               /* float2[C::TW2] */
+    static constexpr int TW3 = TW2 + 2 * C::TW2;       /* float2[C::TW3] */
+    static constexpr int POST = TW3 + 2 * C::TW3;      /* float2[C::POST] = (cos,sin)(2 pi k/N)/2 */
+    static constexpr int TOTAL = POST + 2 * C::POST;
+};
+
+struct FwdArgs {
+    const float* x;          /* [batch][x_pitch] */
+    long long x_pitch, n;
+    int frames, hop, pad_mode;
+    void* out;               /* [batch][frames][out_pitch] float2 or float */
+    long long out_pitch;
+    const float* tables;
+    int num_groups, groups_per_signal;
+};
+
+struct InvArgs {
+    const float2* spec;      /* [batch][frames][spec_pitch] */
+    long long spec_pitch;
+    int frames, hop;
+    float* y;                /* OLA: [batch][y_pitch];  FRAMES: [count][N] */
+    long long y_pitch, n_out;
+    const float* inv_norm;   /* [head L | mid hop | tail L], L = N - hop; or nullptr = raw sum */
+    const float* tables;
+    int num_items, chunks_per_signal, chunk_frames;
+};
+
+/* edge-inclusive reflection of any index into [0, n): ... 1 0 | 0 1 .. n-1 | n-1 n-2 ...
+ * (same map as the reference's reflect_index, src/core/framing.c:21-56) */
+VVB_DEV long long reflect_index(long long idx, long long n)
+{
+    const long long period = 2 * n;
+    long long m = idx % period;
+    if (m < 0) m += period;
+    return m < n ? m : period - 1 - m;
+}
+
+VVB_DEV float fetch_sample(const float* xs, long long n, long long idx, int pad_mode)
+{
+    if (pad_mode == PAD_REFLECT) return n > 0 ? xs[reflect_index(idx, n)] : 0.0f;
+    return (idx < 0 || idx >= n) ? 0.0f : xs[idx];
+}
+
+/* cooperative global -> shared copy of `count` floats */
+VVB_DEV void copy_table(float* dst, const float* src, int count)
+{
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+/* ============================================================== forward (analysis) */
+template <class C, int G, int OUT>
+__global__ void __launch_bounds__(C::T* G) stft_forward_kernel(const FwdArgs a)
+{
+    using TB = Tables<C>;
+    constexpr int M = C::M, N = 2 * M, E = C::E, T = C::T;
+#ifdef VVB_EMU
+    float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float smem[];
+#endif
+    float* s_win = smem;                                              /* N floats */
+    float2* s_tw2 = reinterpret_cast<float2*>(s_win + N);
+    float2* s_tw3 = s_tw2 + C::TW2;
+    float2* s_post = s_tw3 + C::TW3;
+    float2* s_xb = s_post + C::POST + 1;                              /* +1 keeps 16 B alignment */
+    copy_table(s_win, a.tables + TB::WIN, N);
+    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3 + C::POST));
+    __syncthreads();
+
+    const int team = threadIdx.x / T, t = threadIdx.x % T;
+    float2* xb = s_xb + team * C::XBUF;
+    const float2* win2 = reinterpret_cast<const float2*>(s_win);
+
+    for (int group = blockIdx.x; group < a.num_groups; group += gridDim.x) {
+        const int b = group / a.groups_per_signal;
+        const int f = (group % a.groups_per_signal) * G + team;
+        const bool active = f < a.frames;
+        const float* xs = a.x + (long long)b * a.x_pitch;
+        long long start = (long long)f * a.hop;
+        if (a.pad_mode == PAD_REFLECT) start -= M;                   /* nfft/2 */
+
+        /* ---- framing + window, straight into the registers of pass 1 */
+        float2 v[E];
+        {
+            constexpr int R = C::R1, NQ = E / R, STRIDE = M / R;
+            const bool inside = active && start >= 0 && start + N <= a.n;
+            if (inside) {
+                const float* p = xs + start;
+                if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+                    const float2* p2 = reinterpret_cast<const float2*>(p);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int i = t + T * q + r * STRIDE;
+                            const float2 s = __ldg(p2 + i), w = win2[i];
+                            v[q * R + r] = make_float2(s.x * w.x, s.y * w.y);
+                        }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int i = t + T * q + r * STRIDE;
+                            const float2 w = win2[i];
+                            v[q * R + r] = make_float2(__ldg(p + 2 * i) * w.x, __ldg(p + 2 * i + 1) * w.y);
+                        }
+                }
+            } else if (active) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = t + T * q + r * STRIDE;
+                        const float2 w = win2[i];
+                        v[q * R + r] = make_float2(fetch_sample(xs, a.n, start + 2 * i, a.pad_mode) * w.x,
+                                                   fetch_sample(xs, a.n, start + 2 * i + 1, a.pad_mode) * w.y);
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < E; ++i) v[i] = make_float2(0.f, 0.f);
+            }
+        }
+
+        /* ---- M-point complex FFT of z[i] = x[2i] + j x[2i+1] */
+        team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+        team_store_natural<C>(v, xb, t);
+        team_sync<T>(team);
+
+        /* ---- split step: X[k] = (Z[k] + conj Z[M-k])/2 - (j/2) W_N^k (Z[k] - conj Z[M-k]) */
+        const long long row = ((long long)b * a.frames + f) * a.out_pitch;
+        auto emit = [&](int k, float xr, float xi) {
+            if constexpr (OUT == OUT_COMPLEX) reinterpret_cast<float2*>(a.out)[row + k] = make_float2(xr, xi);
+            else if constexpr (OUT == OUT_POWER) reinterpret_cast<float*>(a.out)[row + k] = xr * xr + xi * xi;
+            else reinterpret_cast<float*>(a.out)[row + k] = sqrtf(xr * xr + xi * xi);
+        };
+#pragma unroll
+        for (int i = 0; i < E / 2; ++i) {
+            const int k = t + T * i;                                  /* 0 .. M/2-1 */
+            const float2 A = xb[C::pad(k)];
+            const float2 Bc = xb[C::pad((M - k) & (M - 1))];
+            const float2 hw = s_post[k];                              /* (cos, sin)/2 */
+            const float sr = A.x + Bc.x, si = A.y - Bc.y;             /* A + conj(Bc) */
+            const float dr = A.x - Bc.x, di = A.y + Bc.y;             /* A - conj(Bc) */
+            const float gr = hw.y * dr - hw.x * di, gi = hw.y * di + hw.x * dr;
+            if (active) {
+                emit(k, 0.5f * sr - gr, 0.5f * si - gi);             /* X[k]   */
+                emit(M - k, 0.5f * sr + gr, -(0.5f * si + gi));      /* X[M-k] */
+            }
+        }
+        if (t == 0 && active) {                                       /* k = M/2: X = conj(Z[M/2]) */
+            const float2 A = xb[C::pad(M / 2)];
+            emit(M / 2, A.x, -A.y);
+        }
+        team_sync<T>(team);                                           /* xb is reused next group */
+    }
+}
+
+/* =============================================================== inverse (synthesis) */
+/* Load the half spectrum of one frame, merge to Z (stored re/im swapped so the forward FFT
+ * machinery computes the inverse), run the FFT, multiply by the synthesis window.
+ * On exit: out2[i] = (x[2i], x[2i+1]) * wsyn for this thread's items i = j + r*NS. */
+template <class C>
+VVB_DEV void team_inverse_frame(float2 (&v)[C::E], const float2* X, bool active, float2* xb, const float2* s_tw2,
+                                const float2* s_tw3, const float2* s_post, int t, int team)
+{
+    constexpr int M = C::M, E = C::E, T = C::T;
+    /* ---- merge: Z[k] = (X[k]+conj X[M-k])/2 + (j/2) conj(W_N^k) (X[k]-conj X[M-k]) */
+#pragma unroll
+    for (int i = 0; i < E / 2; ++i) {
+        const int k = t + T * i;                                      /* 0 .. M/2-1 */
+        float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+        if (active) { a = __ldg(X + k); b = __ldg(X + (M - k)); }
+        if (k == 0) { a.y = 0.f; b.y = 0.f; }                         /* Re(IDFT): DC / Nyquist imag drop out */
+        const float2 hw = s_post[k];
+        const float sr = a.x + b.x, si = a.y - b.y;                   /* a + conj(b) */
+        const float dr = a.x - b.x, di = a.y + b.y;                   /* a - conj(b) */
+        const float ur = -hw.y * dr - hw.x * di, ui = -hw.y * di + hw.x * dr;
+        const float zr = 0.5f * sr + ur, zi = 0.5f * si + ui;         /* Z[k]   */
+        const float yr = 0.5f * sr - ur, yi = -(0.5f * si - ui);      /* Z[M-k] */
+        xb[C::pad(k)] = make_float2(zi, zr);                          /* swapped */
+        if (k != 0) xb[C::pad(M - k)] = make_float2(yi, yr);
+    }
+    if (t == 0) {                                                     /* k = M/2: Z = conj(X[M/2]) */
+        float2 a = make_float2(0.f, 0.f);
+        if (active) a = __ldg(X + M / 2);
+        xb[C::pad(M / 2)] = make_float2(-a.y, a.x);
+    }
+    team_sync<T>(team);
+    {   /* pass-1 operands from the natural-order buffer */
+        constexpr int R = C::R1, NQ = E / R, STRIDE = M / R;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[q * R + r] = xb[C::pad(t + T * q + r * STRIDE)];
+    }
+    team_sync<T>(team);
+    team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+}
+
+template <class C, int G, bool OLA>
+__global__ void __launch_bounds__(C::T* G) stft_inverse_kernel(const InvArgs a)
+{
+    using TB = Tables<C>;
+    using L = LastPass<C>;
+    constexpr int M = C::M, N = 2 * M, E = C::E, T = C::T;
+#ifdef VVB_EMU
+    float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float smem[];
+#endif
+    float* s_wsyn = smem;                                             /* N floats */
+    float2* s_tw2 = reinterpret_cast<float2*>(s_wsyn + N);
+    float2* s_tw3 = s_tw2 + C::TW2;
+    float2* s_post = s_tw3 + C::TW3;
+    float2* s_xb = s_post + C::POST + 1;
+    float* s_carry = reinterpret_cast<float*>(s_xb + G * C::XBUF);    /* 2 x (N - hop) floats (OLA) */
+    copy_table(s_wsyn, a.tables + TB::WSYN, N);
+    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3 + C::POST));
+    __syncthreads();
+
+    const int team = threadIdx.x / T, t = threadIdx.x % T;
+    float2* xb = s_xb + team * C::XBUF;
+    const float2* wsyn2 = reinterpret_cast<const float2*>(s_wsyn);
+    const int hop = a.hop;
+
+    if constexpr (!OLA) {
+        /* windowed frames out, no overlap-add: item = group of G frames of the flat frame list */
+        for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+            const int f = item * G + team;
+            const bool active = f < a.frames;
+            float2 v[E];
+            team_inverse_frame<C>(v, a.spec + (long long)f * a.spec_pitch, active, xb, s_tw2, s_tw3, s_post, t, team);
+            if (active) {
+                float2* dst = reinterpret_cast<float2*>(a.y + (long long)f * N);
+#pragma unroll
+                for (int q = 0; q < L::NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < L::R; ++r) {
+                        const int i = t + T * q + r * L::NS;
+                        const float2 z = v[q * L::R + ct_bitrev(r, L::R)], w = wsyn2[i];
+                        dst[i] = make_float2(z.y * w.x, z.x * w.y);   /* (Re z, Im z) after un-swap */
+                    }
+            }
+            team_sync<T>(team);
+        }
+        return;
+    } else {
+        const int edge = N - hop;                                     /* samples a frame shares with later ones */
+        const int K = (N + hop - 1) / hop;                            /* frames covering one sample */
+        const int nblk = (G * hop + edge + hop - 1) / hop;            /* hop-blocks in the accumulation span */
+        for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+            const int b = item / a.chunks_per_signal;
+            const int c = item % a.chunks_per_signal;
+            const int f_begin = c * a.chunk_frames;
+            const int f_end = min(a.frames, f_begin + a.chunk_frames);
+            const bool last = (f_end >= a.frames);
+            const long long out_lo = (long long)f_begin * hop;
+            const long long out_hi = last ? a.n_out : min(a.n_out, (long long)f_end * hop);
+            const int fr0 = f_begin - min(K - 1, f_begin);            /* halo frames re-synthesised */
+            const float2* specb = a.spec + (long long)b * a.frames * a.spec_pitch;
+            float* yb = a.y + (long long)b * a.y_pitch;
+
+            for (int i = threadIdx.x; i < 2 * edge; i += blockDim.x) s_carry[i] = 0.f;
+            int cur = 0;
+            __syncthreads();
+
+            for (long long fb = fr0; fb * hop < out_hi; fb += G) {
+                const long long f = fb + team;
+                const bool active = f < f_end;
+                float2 v[E];
+                team_inverse_frame<C>(v, specb + f * a.spec_pitch, active, xb, s_tw2, s_tw3, s_post, t, team);
+                /* park the windowed frame in this team's slot, natural sample order */
+#pragma unroll
+                for (int q = 0; q < L::NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < L::R; ++r) {
+                        const int i = t + T * q + r * L::NS;
+                        const float2 z = v[q * L::R + ct_bitrev(r, L::R)], w = wsyn2[i];
+                        xb[i] = make_float2(z.y * w.x, z.x * w.y);
+                    }
+                __syncthreads();
+
+                /* conflict-free overlap-add: one thread per output sample, ascending frame order */
+                const float* carry_in = s_carry + cur * edge;
+                float* carry_out = s_carry + (cur ^ 1) * edge;
+                for (int hb = 0; hb < nblk; ++hb) {
+                    const int g_lo = max(0, hb - K + 1), g_hi = min(G - 1, hb);
+                    for (int cidx = threadIdx.x; cidx < hop; cidx += blockDim.x) {
+                        const int s = hb * hop + cidx;
+                        if (s >= G * hop + edge) break;
+                        float acc = (s < edge) ? carry_in[s] : 0.f;
+                        for (int g = g_lo; g <= g_hi; ++g) {
+                            const int p = s - g * hop;
+                            if (p < N) acc += reinterpret_cast<const float*>(s_xb + g * C::XBUF)[p];
+                        }
+                        if (s < G * hop) {
+                            const long long tt = fb * hop + s;
+                            if (tt >= out_lo && tt < out_hi) {
+                                float scale = 1.0f;
+                                if (a.inv_norm) {
+                                    const long long tail0 = (long long)a.frames * hop;
+                                    if (tt >= tail0) scale = (tt - tail0 < edge) ? __ldg(a.inv_norm + edge + hop + (tt - tail0)) : 0.f;
+                                    else if (tt < edge) scale = __ldg(a.inv_norm + tt);
+                                    else scale = __ldg(a.inv_norm + edge + cidx);
+                                }
+                                yb[tt] = acc * scale;
+                            }
+                        } else {
+                            carry_out[s - G * hop] = acc;
+                        }
+                    }
+                }
+                cur ^= 1;
+                __syncthreads();
+            }
+        }
+    }
+}
+
+/* ===================================================== batched complex FFT (plan API) */
+struct C2CArgs {
+    const float2* in;
+    float2* out;
+    int batch;
+    int inverse;             /* 1: backward, scaled 1/M */
+    const float* tables;
+};
+
+template <class C, int G>
+__global__ void __launch_bounds__(C::T* G) fft_c2c_kernel(const C2CArgs a)
+{
+    using TB = Tables<C>;
+    using L = LastPass<C>;
+    constexpr int M = C::M, E = C::E, T = C::T;
+#ifdef VVB_EMU
+    float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float smem[];
+#endif
+    float2* s_tw2 = reinterpret_cast<float2*>(smem);
+    float2* s_tw3 = s_tw2 + C::TW2;
+    float2* s_xb = s_tw3 + C::TW3;
+    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3));
+    __syncthreads();
+    const int team = threadIdx.x / T, t = threadIdx.x % T;
+    float2* xb = s_xb + team * C::XBUF;
+    const int groups = (a.batch + G - 1) / G;
+    const float scale = a.inverse ? 1.0f / (float)M : 1.0f;
+    for (int group = blockIdx.x; group < groups; group += gridDim.x) {
+        const int id = group * G + team;
+        const bool active = id < a.batch;
+        float2 v[E];
+        {
+            constexpr int R = C::R1, NQ = E / R, STRIDE = M / R;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float2 s = make_float2(0.f, 0.f);
+                    if (active) s = __ldg(a.in + (long long)id * M + t + T * q + r * STRIDE);
+                    v[q * R + r] = a.inverse ? make_float2(s.y, s.x) : s;
+                }
+        }
+        /* in == out is allowed (reference fft_kiss.c:112): every load of this transform is done
+         * before its first store because team_fft contains team barriers */
+        team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < L::NQ; ++q)
+#pragma unroll
+                for (int r = 0; r < L::R; ++r) {
+                    const float2 z = v[q * L::R + ct_bitrev(r, L::R)];
+                    a.out[(long long)id * M + t + T * q + r * L::NS] =
+                        a.inverse ? make_float2(z.y * scale, z.x * scale) : z;
+                }
+        }
+        team_sync<T>(team);
+    }
+}
+
+}  // namespace vvb

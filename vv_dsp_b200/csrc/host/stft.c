@@ -1,0 +1,408 @@
+/*
+ * stft.c -- vv_dsp_stft_* handle API and the batched extension (host, C99).
+ *
+ * Per-frame entry points keep the reference's contract (src/spectral/stft.c:30-144,
+ * include/vv_dsp/spectral/stft.h:30-56): host pointers in and out, synchronous, same
+ * validation order and status codes.  All arithmetic happens on the GPU through
+ * include/vvb200_cuda.h; this file only validates, stages and mirrors.
+ *
+ * The batched entry points (include/vv_dsp/b200.h) are the throughput path: one fused
+ * kernel per direction for a whole batch, device-resident or staged through pinned
+ * double buffers so host<->device copies overlap the kernels.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "vv_dsp/b200.h"
+#include "vv_dsp/core.h"
+#include "vv_dsp/window.h"
+#include "vvb200_cuda.h"
+
+#define NORM_CACHE 4
+#define NSLOT 2
+#define STAGE_TARGET_BYTES ((size_t)192 << 20)   /* per slot and direction */
+
+typedef struct stage_slot {
+    void* stream;
+    void* d_in;  size_t in_bytes;
+    void* d_out; size_t out_bytes;
+} stage_slot;
+
+struct vv_dsp_stft {
+    size_t nfft, hop, bins;
+    vv_dsp_stft_window win_type;
+    vv_dsp_real* win;                 /* host copy of the window (bit-identical to the reference's) */
+    vvb_engine* eng;
+    void* own_stream;
+    void* stream;                     /* own_stream or the caller's */
+    /* per-frame staging */
+    float* h_in;   vvb_cpx* h_spec;   float* h_frame;   /* pinned */
+    float* d_in;   vvb_cpx* d_spec;   float* d_frame;
+    /* batched staging (host-space arguments) */
+    stage_slot slot[NSLOT];
+    /* 1/sum(w^2) tables per frame count: [head nfft-hop | mid hop | tail nfft-hop] */
+    struct { size_t frames; float* d_tab; int used; } norm[NORM_CACHE];
+    int norm_next;
+};
+
+static vv_dsp_status map_status(int st)
+{
+    if (st == 0) return VV_DSP_OK;
+    if (st >= 1 && st <= 6 && st != 5) return (vv_dsp_status)st;
+    return VV_DSP_ERROR_INTERNAL;
+}
+
+const char* vv_dsp_b200_version(void) { return "vv-dsp_b200 0.1.0 (sm_100a)"; }
+const char* vv_dsp_b200_last_error(void) { return vvb_last_error(); }
+unsigned long long vv_dsp_b200_kernel_launches(void) { return vvb_kernel_launches(); }
+
+/* ---------------------------------------------------------------- create / destroy */
+static void handle_free(vv_dsp_stft* h)
+{
+    int i;
+    if (!h) return;
+    for (i = 0; i < NSLOT; ++i) {
+        vvb_free(h->slot[i].d_in); vvb_free(h->slot[i].d_out);
+        if (h->slot[i].stream) vvb_stream_destroy(h->slot[i].stream);
+    }
+    for (i = 0; i < NORM_CACHE; ++i) vvb_free(h->norm[i].d_tab);
+    vvb_host_free(h->h_in); vvb_host_free(h->h_spec); vvb_host_free(h->h_frame);
+    vvb_free(h->d_in); vvb_free(h->d_spec); vvb_free(h->d_frame);
+    vvb_engine_destroy(h->eng);
+    if (h->own_stream) vvb_stream_destroy(h->own_stream);
+    free(h->win);
+    free(h);
+}
+
+vv_dsp_status vv_dsp_stft_create(const vv_dsp_stft_params* params, vv_dsp_stft** out)
+{
+    vv_dsp_stft* h;
+    vv_dsp_status ws;
+    int st;
+    if (!out || !params) return VV_DSP_ERROR_NULL_POINTER;
+    *out = NULL;
+    if (params->fft_size == 0 || params->hop_size == 0 || params->hop_size > params->fft_size)
+        return VV_DSP_ERROR_INVALID_SIZE;
+    h = (vv_dsp_stft*)calloc(1, sizeof(*h));
+    if (!h) return VV_DSP_ERROR_INTERNAL;
+    h->nfft = params->fft_size; h->hop = params->hop_size; h->bins = h->nfft / 2 + 1;
+    h->win_type = params->window;
+    h->win = (vv_dsp_real*)malloc(h->nfft * sizeof(vv_dsp_real));
+    if (!h->win) { handle_free(h); return VV_DSP_ERROR_INTERNAL; }
+    switch (params->window) {
+    case VV_DSP_STFT_WIN_BOXCAR: ws = vv_dsp_window_boxcar(h->nfft, h->win); break;
+    case VV_DSP_STFT_WIN_HANN: ws = vv_dsp_window_hann(h->nfft, h->win); break;
+    case VV_DSP_STFT_WIN_HAMMING: ws = vv_dsp_window_hamming(h->nfft, h->win); break;
+    default: ws = VV_DSP_ERROR_OUT_OF_RANGE; break;
+    }
+    if (ws != VV_DSP_OK) { handle_free(h); return ws; }
+    st = vvb_engine_create(h->nfft, h->hop, h->win, &h->eng);
+    if (!st) st = vvb_stream_create(&h->own_stream);
+    h->stream = h->own_stream;
+    if (!st) st = vvb_host_alloc((void**)&h->h_in, h->nfft * sizeof(float));
+    if (!st) st = vvb_host_alloc((void**)&h->h_spec, h->bins * sizeof(vvb_cpx));
+    if (!st) st = vvb_host_alloc((void**)&h->h_frame, h->nfft * sizeof(float));
+    if (!st) st = vvb_malloc((void**)&h->d_in, h->nfft * sizeof(float));
+    if (!st) st = vvb_malloc((void**)&h->d_spec, h->bins * sizeof(vvb_cpx));
+    if (!st) st = vvb_malloc((void**)&h->d_frame, h->nfft * sizeof(float));
+    if (st) { handle_free(h); return st == 6 ? VV_DSP_ERROR_UNSUPPORTED : VV_DSP_ERROR_INTERNAL; }
+    *out = h;
+    return VV_DSP_OK;
+}
+
+vv_dsp_status vv_dsp_stft_destroy(vv_dsp_stft* h)
+{
+    if (!h) return VV_DSP_ERROR_NULL_POINTER;     /* reference stft.c:63 */
+    handle_free(h);
+    return VV_DSP_OK;
+}
+
+/* ------------------------------------------------------------------ per-frame API */
+vv_dsp_status vv_dsp_stft_process(vv_dsp_stft* h, const vv_dsp_real* in, vv_dsp_cpx* out)
+{
+    int st;
+    size_t k;
+    if (!h || !in || !out) return VV_DSP_ERROR_NULL_POINTER;
+    memcpy(h->h_in, in, h->nfft * sizeof(float));
+    st = vvb_memcpy_h2d(h->d_in, h->h_in, h->nfft * sizeof(float), h->stream);
+    if (!st) st = vvb_stft_forward(h->eng, h->d_in, 1, h->nfft, h->nfft, 1, VVB_PAD_ZERO, VVB_OUT_COMPLEX,
+                                   h->d_spec, h->bins, h->stream);
+    if (!st) st = vvb_memcpy_d2h(h->h_spec, h->d_spec, h->bins * sizeof(vvb_cpx), h->stream);
+    if (!st) st = vvb_stream_sync(h->stream);
+    if (st) return map_status(st);
+    /* bins 0..nfft/2 from the device; the rest is the conjugate mirror of a real input's spectrum */
+    for (k = 0; k < h->bins; ++k) { out[k].re = h->h_spec[k].re; out[k].im = h->h_spec[k].im; }
+    for (k = 1; k < h->bins; ++k)
+        if (h->nfft - k > k) { out[h->nfft - k].re = h->h_spec[k].re; out[h->nfft - k].im = -h->h_spec[k].im; }
+    return VV_DSP_OK;
+}
+
+vv_dsp_status vv_dsp_stft_reconstruct(vv_dsp_stft* h, const vv_dsp_cpx* in, vv_dsp_real* out_add, vv_dsp_real* norm_add)
+{
+    int st;
+    size_t k, i;
+    const size_t n = h ? h->nfft : 0;
+    if (!h || !in || !out_add) return VV_DSP_ERROR_NULL_POINTER;
+    /* Re(IDFT(X)) == IDFT of the Hermitian part of X: Xh[k] = (X[k] + conj X[n-k]) / 2 */
+    for (k = 0; k < h->bins; ++k) {
+        const vv_dsp_cpx a = in[k], b = in[(n - k) % n];
+        h->h_spec[k].re = 0.5f * (a.re + b.re);
+        h->h_spec[k].im = 0.5f * (a.im - b.im);
+    }
+    st = vvb_memcpy_h2d(h->d_spec, h->h_spec, h->bins * sizeof(vvb_cpx), h->stream);
+    if (!st) st = vvb_stft_inverse_frames(h->eng, h->d_spec, 1, h->bins, h->d_frame, h->stream);
+    if (!st) st = vvb_memcpy_d2h(h->h_frame, h->d_frame, n * sizeof(float), h->stream);
+    if (!st) st = vvb_stream_sync(h->stream);
+    if (st) return map_status(st);
+    for (i = 0; i < n; ++i) {
+        out_add[i] += h->h_frame[i];
+        if (norm_add) norm_add[i] += h->win[i] * h->win[i];
+    }
+    return VV_DSP_OK;
+}
+
+/* ------------------------------------------------------------------ frame counting */
+size_t vv_dsp_stft_num_bins(const vv_dsp_stft* h) { return h ? h->bins : 0; }
+
+size_t vv_dsp_stft_num_frames(const vv_dsp_stft* h, size_t n, vv_dsp_frame_convention convention)
+{
+    if (!h) return 0;
+    switch (convention) {
+    case VV_DSP_FRAMES_VALID: return n < h->nfft ? 0 : 1 + (n - h->nfft) / h->hop;
+    case VV_DSP_FRAMES_SPECTROGRAM: return n < h->nfft ? 1 : 1 + (n - h->nfft + h->hop) / h->hop;
+    case VV_DSP_FRAMES_PADDED_TAIL: return n / h->hop;   /* starts with start + nfft <= n + nfft - hop */
+    case VV_DSP_FRAMES_CENTER: return (n + h->hop - 1) / h->hop;
+    default: return 0;
+    }
+}
+
+vv_dsp_status vv_dsp_stft_set_stream(vv_dsp_stft* h, void* cuda_stream)
+{
+    if (!h) return VV_DSP_ERROR_NULL_POINTER;
+    h->stream = cuda_stream ? cuda_stream : h->own_stream;
+    return VV_DSP_OK;
+}
+
+vv_dsp_status vv_dsp_stft_synchronize(vv_dsp_stft* h)
+{
+    if (!h) return VV_DSP_ERROR_NULL_POINTER;
+    return map_status(vvb_stream_sync(h->stream));
+}
+
+/* ---------------------------------------------------------------- staging helpers */
+static int slot_reserve(stage_slot* s, size_t in_bytes, size_t out_bytes)
+{
+    int st = 0;
+    if (!s->stream) st = vvb_stream_create(&s->stream);
+    if (!st && in_bytes > s->in_bytes) {
+        vvb_free(s->d_in); s->d_in = NULL; s->in_bytes = 0;
+        st = vvb_malloc(&s->d_in, in_bytes);
+        if (!st) s->in_bytes = in_bytes;
+    }
+    if (!st && out_bytes > s->out_bytes) {
+        vvb_free(s->d_out); s->d_out = NULL; s->out_bytes = 0;
+        st = vvb_malloc(&s->d_out, out_bytes);
+        if (!st) s->out_bytes = out_bytes;
+    }
+    return st;
+}
+
+static size_t chunk_signals(size_t batch, size_t bytes_per_signal)
+{
+    size_t c = bytes_per_signal ? STAGE_TARGET_BYTES / bytes_per_signal : batch;
+    if (c < 1) c = 1;
+    if (c > batch) c = batch;
+    return c;
+}
+
+/* ------------------------------------------------------------------ batched forward */
+vv_dsp_status vv_dsp_stft_batch_forward(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space,
+                                        size_t batch, size_t n, size_t signal_pitch,
+                                        vv_dsp_frame_convention convention, vv_dsp_spec_kind kind, void* out,
+                                        vv_dsp_mem_space out_space, size_t spec_pitch, size_t* out_frames)
+{
+    size_t frames, esize, done;
+    int pad, st = 0, c = 0;
+    if (!h || !signals || !out) return VV_DSP_ERROR_NULL_POINTER;
+    if ((unsigned)convention > 3u || (unsigned)kind > 2u || (unsigned)signals_space > 1u || (unsigned)out_space > 1u)
+        return VV_DSP_ERROR_OUT_OF_RANGE;
+    if (signal_pitch == 0) signal_pitch = n;
+    if (spec_pitch == 0) spec_pitch = h->bins;
+    if (signal_pitch < n || spec_pitch < h->bins) return VV_DSP_ERROR_INVALID_SIZE;
+    frames = vv_dsp_stft_num_frames(h, n, convention);
+    if (out_frames) *out_frames = frames;
+    if (batch == 0 || frames == 0) return VV_DSP_OK;
+    pad = (convention == VV_DSP_FRAMES_CENTER) ? VVB_PAD_REFLECT_CENTER : VVB_PAD_ZERO;
+    esize = (kind == VV_DSP_SPEC_COMPLEX) ? sizeof(vvb_cpx) : sizeof(float);
+
+    if (signals_space == VV_DSP_MEM_DEVICE && out_space == VV_DSP_MEM_DEVICE)
+        return map_status(vvb_stft_forward(h->eng, signals, batch, n, signal_pitch, frames, pad, (int)kind, out,
+                                           spec_pitch, h->stream));
+
+    /* at least one side lives in host memory: stream chunks of signals through two slots */
+    {
+        const size_t in_per = (signals_space == VV_DSP_MEM_HOST) ? (n ? n : 1) * sizeof(float) : 0;
+        const size_t out_per = (out_space == VV_DSP_MEM_HOST) ? frames * h->bins * esize : 0;
+        const size_t cs = chunk_signals(batch, in_per > out_per ? in_per : out_per);
+        st = vvb_stream_sync(h->stream);            /* device-side operands may still be in flight */
+        for (done = 0; done < batch && !st; done += cs, ++c) {
+            stage_slot* s = &h->slot[c % NSLOT];
+            const size_t nb = (batch - done < cs) ? batch - done : cs;
+            const float* d_x;
+            char* d_o;
+            size_t xp, op;
+            st = slot_reserve(s, in_per * cs, out_per * cs);
+            if (!st) st = vvb_stream_sync(s->stream);                  /* slot free again */
+            if (st) break;
+            if (signals_space == VV_DSP_MEM_HOST) {
+                if (n)
+                    st = vvb_memcpy2d_h2d(s->d_in, n * sizeof(float), signals + done * signal_pitch,
+                                          signal_pitch * sizeof(float), n * sizeof(float), nb, s->stream);
+                d_x = (const float*)s->d_in; xp = n;
+            } else { d_x = signals + done * signal_pitch; xp = signal_pitch; }
+            if (out_space == VV_DSP_MEM_HOST) { d_o = (char*)s->d_out; op = h->bins; }
+            else { d_o = (char*)out + done * frames * spec_pitch * esize; op = spec_pitch; }
+            if (!st) st = vvb_stft_forward(h->eng, d_x, nb, n, xp, frames, pad, (int)kind, d_o, op, s->stream);
+            if (!st && out_space == VV_DSP_MEM_HOST)
+                st = vvb_memcpy2d_d2h((char*)out + done * frames * spec_pitch * esize, spec_pitch * esize, s->d_out,
+                                      h->bins * esize, h->bins * esize, nb * frames, s->stream);
+        }
+        for (c = 0; c < NSLOT; ++c)
+            if (h->slot[c].stream) { int s2 = vvb_stream_sync(h->slot[c].stream); if (!st) st = s2; }
+    }
+    return map_status(st);
+}
+
+/* --------------------------------------------------- 1/sum(w^2) tables for the ISTFT */
+/* norm(t) = sum over frames f covering t, ASCENDING f, of w[t - f*hop]^2 in float32 -- the
+ * order the reference accumulates norm_add in (src/spectral/stft.c:107 driven by
+ * tools/dump_stft_roundtrip.c:44-47); entry = norm > 1e-12 ? 1/norm : 0 (dump tool :50-52). */
+static float inv_norm_at(const vv_dsp_stft* h, size_t frames, size_t t)
+{
+    const size_t nfft = h->nfft, hop = h->hop;
+    size_t f_lo = (t < nfft) ? 0 : (t - nfft) / hop + 1;
+    size_t f_hi = t / hop, f;
+    float acc = 0.0f;
+    if (frames == 0) return 0.0f;
+    if (f_hi > frames - 1) f_hi = frames - 1;
+    for (f = f_lo; f <= f_hi && f_hi != (size_t)-1; ++f) {
+        const float w = h->win[t - f * hop];
+        acc += w * w;
+    }
+    return acc > 1e-12f ? 1.0f / acc : 0.0f;
+}
+
+static int norm_tables(vv_dsp_stft* h, size_t frames, const float** d_tab)
+{
+    const size_t edge = h->nfft - h->hop, total = 2 * edge + h->hop;
+    size_t i;
+    int k, st;
+    float* host;
+    for (k = 0; k < NORM_CACHE; ++k)
+        if (h->norm[k].used && h->norm[k].frames == frames) { *d_tab = h->norm[k].d_tab; return 0; }
+    host = (float*)malloc(total * sizeof(float));
+    if (!host) return 4;
+    for (i = 0; i < edge; ++i) host[i] = inv_norm_at(h, frames, i);                       /* head: t = i */
+    for (i = 0; i < h->hop; ++i) {                                                       /* mid: all K frames present */
+        /* any t >= edge with t % hop == i and t < frames*hop; computed as if frames were unlimited */
+        const size_t t = ((edge + h->hop - 1) / h->hop) * h->hop + i;
+        host[edge + i] = inv_norm_at(h, (size_t)-2, t);
+    }
+    for (i = 0; i < edge; ++i) host[edge + h->hop + i] = inv_norm_at(h, frames, frames * h->hop + i);  /* tail */
+    k = h->norm_next; h->norm_next = (h->norm_next + 1) % NORM_CACHE;
+    st = vvb_stream_sync(h->stream);                 /* the evicted table may still be in use */
+    for (i = 0; i < NSLOT && !st; ++i) if (h->slot[i].stream) st = vvb_stream_sync(h->slot[i].stream);
+    vvb_free(h->norm[k].d_tab); h->norm[k].d_tab = NULL; h->norm[k].used = 0;
+    if (!st) st = vvb_malloc((void**)&h->norm[k].d_tab, total * sizeof(float));
+    if (!st) st = vvb_memcpy_h2d(h->norm[k].d_tab, host, total * sizeof(float), h->stream);
+    if (!st) st = vvb_stream_sync(h->stream);
+    free(host);
+    if (st) return st;
+    h->norm[k].frames = frames; h->norm[k].used = 1;
+    *d_tab = h->norm[k].d_tab;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ batched inverse */
+vv_dsp_status vv_dsp_stft_batch_inverse(vv_dsp_stft* h, const vv_dsp_cpx* spectra, vv_dsp_mem_space spectra_space,
+                                        size_t batch, size_t frames, size_t spec_pitch, vv_dsp_real* out,
+                                        vv_dsp_mem_space out_space, size_t n_out, size_t out_pitch, int normalise)
+{
+    const float* d_tab = NULL;
+    size_t done;
+    int st = 0, c = 0;
+    if (!h || !out || (!spectra && frames)) return VV_DSP_ERROR_NULL_POINTER;
+    if ((unsigned)spectra_space > 1u || (unsigned)out_space > 1u) return VV_DSP_ERROR_OUT_OF_RANGE;
+    if (spec_pitch == 0) spec_pitch = h->bins;
+    if (out_pitch == 0) out_pitch = n_out;
+    if (spec_pitch < h->bins || out_pitch < n_out) return VV_DSP_ERROR_INVALID_SIZE;
+    if (batch == 0 || n_out == 0) return VV_DSP_OK;
+    if (normalise) { st = norm_tables(h, frames, &d_tab); if (st) return map_status(st); }
+
+    if (spectra_space == VV_DSP_MEM_DEVICE && out_space == VV_DSP_MEM_DEVICE)
+        return map_status(vvb_stft_inverse(h->eng, (const vvb_cpx*)spectra, batch, frames, spec_pitch, out, n_out,
+                                           out_pitch, d_tab, h->stream));
+    {
+        const size_t in_per = (spectra_space == VV_DSP_MEM_HOST) ? frames * h->bins * sizeof(vvb_cpx) : 0;
+        const size_t out_per = (out_space == VV_DSP_MEM_HOST) ? n_out * sizeof(float) : 0;
+        const size_t cs = chunk_signals(batch, in_per > out_per ? in_per : out_per);
+        st = vvb_stream_sync(h->stream);
+        for (done = 0; done < batch && !st; done += cs, ++c) {
+            stage_slot* s = &h->slot[c % NSLOT];
+            const size_t nb = (batch - done < cs) ? batch - done : cs;
+            const vvb_cpx* d_s;
+            float* d_y;
+            size_t sp, yp;
+            st = slot_reserve(s, in_per * cs, out_per * cs);
+            if (!st) st = vvb_stream_sync(s->stream);
+            if (st) break;
+            if (spectra_space == VV_DSP_MEM_HOST) {
+                if (frames)
+                    st = vvb_memcpy2d_h2d(s->d_in, h->bins * sizeof(vvb_cpx), spectra + done * frames * spec_pitch,
+                                          spec_pitch * sizeof(vvb_cpx), h->bins * sizeof(vvb_cpx), nb * frames, s->stream);
+                d_s = (const vvb_cpx*)s->d_in; sp = h->bins;
+            } else { d_s = (const vvb_cpx*)spectra + done * frames * spec_pitch; sp = spec_pitch; }
+            if (out_space == VV_DSP_MEM_HOST) { d_y = (float*)s->d_out; yp = n_out; }
+            else { d_y = out + done * out_pitch; yp = out_pitch; }
+            if (!st) st = vvb_stft_inverse(h->eng, d_s, nb, frames, sp, d_y, n_out, yp, d_tab, s->stream);
+            if (!st && out_space == VV_DSP_MEM_HOST)
+                st = vvb_memcpy2d_d2h(out + done * out_pitch, out_pitch * sizeof(float), s->d_out, n_out * sizeof(float),
+                                      n_out * sizeof(float), nb, s->stream);
+        }
+        for (c = 0; c < NSLOT; ++c)
+            if (h->slot[c].stream) { int s2 = vvb_stream_sync(h->slot[c].stream); if (!st) st = s2; }
+    }
+    return map_status(st);
+}
+
+vv_dsp_status vv_dsp_stft_istft(vv_dsp_stft* h, const vv_dsp_cpx* half_spectra, size_t frames, vv_dsp_real* out, size_t n_out)
+{
+    return vv_dsp_stft_batch_inverse(h, half_spectra, VV_DSP_MEM_HOST, 1, frames, 0, out, VV_DSP_MEM_HOST, n_out, 0, 1);
+}
+
+/* ---------------------------------------------------- whole-signal magnitude (reference API) */
+vv_dsp_status vv_dsp_stft_spectrogram(vv_dsp_stft* h, const vv_dsp_real* signal, size_t n, vv_dsp_real* out_mag,
+                                      size_t* out_frames)
+{
+    size_t frames, f, k;
+    float* half;
+    vv_dsp_status st;
+    static const float zero = 0.0f;
+    if (!h || !signal || !out_mag || !out_frames) return VV_DSP_ERROR_NULL_POINTER;
+    frames = vv_dsp_stft_num_frames(h, n, VV_DSP_FRAMES_SPECTROGRAM);
+    *out_frames = frames;
+    half = (float*)malloc(frames * h->bins * sizeof(float));
+    if (!half) return VV_DSP_ERROR_INTERNAL;
+    st = vv_dsp_stft_batch_forward(h, n ? signal : &zero, VV_DSP_MEM_HOST, 1, n, n ? n : 1, VV_DSP_FRAMES_SPECTROGRAM,
+                                   VV_DSP_SPEC_MAGNITUDE, half, VV_DSP_MEM_HOST, 0, NULL);
+    if (st == VV_DSP_OK) {
+        /* the reference writes all fft_size bins per frame (stft.c:133-140); |X[n-k]| = |X[k]| */
+        for (f = 0; f < frames; ++f) {
+            const float* src = half + f * h->bins;
+            float* dst = out_mag + f * h->nfft;
+            for (k = 0; k < h->bins; ++k) dst[k] = src[k];
+            for (k = 1; k < h->bins; ++k) if (h->nfft - k > k) dst[h->nfft - k] = src[k];
+        }
+    }
+    free(half);
+    return st;
+}
