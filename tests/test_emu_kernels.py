@@ -1,0 +1,72 @@
+"""CPU tests (-m "not gpu"): the kernel SOURCES and the host library, executed under the
+test-only fibre emulator (tests/emu), against the oracle.  This is not a product path --
+it exists because the build container has no GPU; the same checks run on the B200 in
+test_gpu_parity.py through the nvcc-built library."""
+import os
+import sys
+
+import pytest
+
+import parity_cases as pc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    sys.path.insert(0, os.path.join(HERE, "emu"))
+    import build_emu
+    from vv_dsp_b200 import Library
+    return Library(build_emu.build())
+
+
+def test_status_codes(emu):
+    pc.check_status_codes(emu)
+    pc.check_live_handle_null_args(emu)
+
+
+def test_reference_known_answers(emu):
+    pc.check_reference_known_answers(emu)
+
+
+@pytest.mark.parametrize("nfft,hop,win", [(2048, 512, "hann"), (256, 64, "hamming"), (64, 32, "hann"), (12, 5, "boxcar")])
+def test_per_frame_api(emu, oracle, nfft, hop, win):
+    pc.check_per_frame_api(emu, oracle, nfft, hop, win)
+
+
+@pytest.mark.parametrize("nfft,hop,n", [(256, 64, 2000), (512, 128, 3000), (1024, 256, 5000), (2048, 512, 9000),
+                                        (4096, 1024, 14000), (8192, 2048, 30000), (2048, 300, 7000), (100, 30, 900)])
+def test_batch_forward_and_inverse(emu, oracle, nfft, hop, n):
+    pc.check_batch_forward(emu, oracle, nfft, hop, "hann", n)
+    pc.check_batch_inverse(emu, oracle, nfft, hop, "hann", n)
+
+
+def test_short_and_ragged_inputs(emu, oracle):
+    # signal shorter than a frame, shorter than half a frame (multiple reflections), exactly one frame
+    for n in (1, 100, 700, 2048, 2049):
+        pc.check_batch_forward(emu, oracle, 2048, 512, "hann", n, batch=1)
+    pc.check_batch_forward(emu, oracle, 256, 64, "hamming", 3001, batch=3)
+    pc.check_batch_inverse(emu, oracle, 256, 256, "boxcar", 2000)
+
+
+def test_spectrogram(emu, oracle):
+    pc.check_spectrogram(emu, oracle, 512, 128, "hann", 3000)
+    pc.check_spectrogram(emu, oracle, 64, 16, "hamming", 40)     # n < nfft: one zero-padded frame
+
+
+def test_fft_plans(emu, oracle):
+    pc.check_fft_plans(emu, oracle, [1, 2, 3, 8, 16, 100, 128, 256, 1024, 2048])
+
+
+def test_golden_slices(emu, golden):
+    pc.check_golden_slices(emu, golden)
+
+
+def test_config1_voicebank(emu, golden):
+    pc.check_config1_voicebank(emu, golden)
+
+
+def test_accuracy_vs_truth(emu, oracle):
+    for nfft in (256, 2048, 8192):
+        mine, theirs = pc.check_accuracy_vs_truth(emu, oracle, nfft)
+        assert mine < theirs

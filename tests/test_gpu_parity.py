@@ -1,0 +1,186 @@
+"""GPU tests (-m gpu): the product library (nvcc, sm_100a) through its C-ABI against the
+oracle on identical seeded inputs, the committed golden slices of the real reference, and --
+at BASELINE's full sizes -- size-independent properties (round trip, linearity, Parseval).
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from _util import ROUNDTRIP_REL_L2, noise, rel_l2, spectra_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from vv_dsp_b200 import default_library
+    lib = default_library()           # raises if the CUDA library is missing: no fallback
+    return lib
+
+
+def test_library_loaded_and_launches(lib, oracle):
+    before = lib.kernel_launches()
+    pc.check_per_frame_api(lib, oracle, 2048, 512, "hann")
+    assert lib.kernel_launches() > before            # the CUDA kernels really ran
+    assert "sm_100a" in lib.version()
+
+
+def test_status_codes(lib):
+    pc.check_status_codes(lib)
+    pc.check_live_handle_null_args(lib)
+
+
+def test_reference_known_answers(lib):
+    pc.check_reference_known_answers(lib)
+
+
+@pytest.mark.parametrize("nfft,hop,win", [(2048, 512, "hann"), (1024, 256, "hamming"), (256, 64, "boxcar"),
+                                          (4096, 1024, "hann"), (64, 32, "hann"), (12, 5, "boxcar"), (200, 50, "hann")])
+def test_per_frame_api(lib, oracle, nfft, hop, win):
+    pc.check_per_frame_api(lib, oracle, nfft, hop, win)
+
+
+@pytest.mark.parametrize("nfft,hop,n", [(256, 64, 20000), (512, 128, 20000), (1024, 256, 30000), (2048, 512, 60000),
+                                        (4096, 1024, 60000), (8192, 2048, 90000), (2048, 300, 30000),
+                                        (2048, 2048, 20000), (100, 30, 3000), (64, 16, 3000)])
+def test_batch_forward_and_inverse(lib, oracle, nfft, hop, n):
+    pc.check_batch_forward(lib, oracle, nfft, hop, "hann", n, batch=3)
+    pc.check_batch_inverse(lib, oracle, nfft, hop, "hann", n, batch=3)
+
+
+@pytest.mark.parametrize("win", ["boxcar", "hamming"])
+def test_other_windows(lib, oracle, win):
+    pc.check_batch_forward(lib, oracle, 1024, 256, win, 20000)
+    pc.check_batch_inverse(lib, oracle, 1024, 256, win, 20000)
+
+
+def test_short_and_ragged_inputs(lib, oracle):
+    for n in (1, 100, 700, 2048, 2049, 2559, 2560):
+        pc.check_batch_forward(lib, oracle, 2048, 512, "hann", n, batch=1)
+    pc.check_batch_forward(lib, oracle, 256, 64, "hamming", 3001, batch=5)
+    pc.check_batch_inverse(lib, oracle, 256, 256, "boxcar", 2000)
+    pc.check_batch_inverse(lib, oracle, 2048, 512, "hann", 2048 + 512 * 3 + 5, batch=1)
+
+
+def test_many_signals_chunking(lib, oracle):
+    """more work items than resident CTAs, several chunks per signal in the ISTFT"""
+    nfft, hop, n, B = 1024, 256, 200000, 7
+    x = np.stack([noise(300 + i, n) for i in range(B)])
+    from vv_dsp_b200 import Stft
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        s = h.batch_forward(x, "complex", "valid")
+        ref = oracle.batch_forward(x, nfft, hop, threads=4)
+        ok, frac = spectra_close(s, ref)
+        assert ok, frac
+        y = h.batch_inverse(ref, n, True)
+        refy = np.stack([oracle.istft(ref[i], nfft, hop, n) for i in range(B)])
+        assert rel_l2(y[:, nfft:-nfft], refy[:, nfft:-nfft]) < 5e-5
+        assert rel_l2(h.batch_inverse(s, n, True)[:, nfft:-nfft], x[:, nfft:-nfft]) < ROUNDTRIP_REL_L2
+
+
+def test_device_resident_torch_tensors(lib, oracle):
+    import torch
+    from vv_dsp_b200 import Stft
+    nfft, hop, n, B = 2048, 512, 48000, 4
+    x = np.stack([noise(400 + i, n) for i in range(B)])
+    xd = torch.from_numpy(x).cuda()
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        sd = h.batch_forward(xd, "complex", "valid")
+        pd = h.batch_forward(xd, "power", "valid")
+        yd = h.batch_inverse(sd, n, True)
+        torch.cuda.synchronize()
+        ref = oracle.batch_forward(x, nfft, hop, threads=4)
+        ok, frac = spectra_close(sd.cpu().numpy(), ref)
+        assert ok, frac
+        ok, frac = spectra_close(pd.cpu().numpy(), oracle.batch_power(x, nfft, hop, threads=4), rtol=1e-4, atol=1e-4)
+        assert ok, frac
+        assert rel_l2(yd.cpu().numpy()[:, nfft:-nfft], x[:, nfft:-nfft]) < ROUNDTRIP_REL_L2
+        # host-staged and device-resident paths give identical bits
+        assert np.array_equal(h.batch_forward(x, "complex", "valid"), sd.cpu().numpy())
+
+
+def test_spectrogram(lib, oracle):
+    pc.check_spectrogram(lib, oracle, 2048, 512, "hann", 30000)
+    pc.check_spectrogram(lib, oracle, 64, 16, "hamming", 40)
+
+
+def test_fft_plans(lib, oracle):
+    pc.check_fft_plans(lib, oracle, [1, 2, 3, 4, 8, 16, 32, 64, 100, 128, 200, 256, 512, 1024, 2048, 4096, 8192])
+
+
+def test_golden_slices_of_the_real_reference(lib, golden):
+    pc.check_golden_slices(lib, golden)
+
+
+def test_config1_voicebank(lib, golden):
+    err = pc.check_config1_voicebank(lib, golden)
+    print(f"config1 interior round-trip rel-L2 = {err:.3e}")
+
+
+@pytest.mark.parametrize("nfft", [256, 1024, 2048, 4096, 8192])
+def test_accuracy_vs_float64_truth(lib, oracle, nfft):
+    mine, theirs = pc.check_accuracy_vs_truth(lib, oracle, nfft)
+    print(f"nfft={nfft}: max err/max|X| vs float64: library {mine:.2e}, oracle {theirs:.2e}")
+    assert mine < theirs
+
+
+def test_full_size_properties_config2_3():
+    """BASELINE configs 2/3 at FULL size (1024 x 480000, nfft=2048 hop=512), device-resident:
+    frame count, Parseval per frame, linearity, and the STFT->ISTFT round trip."""
+    import torch
+    from vv_dsp_b200 import Stft
+    B, n, nfft, hop = 1024, 480000, 2048, 512
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.rand((B, n), device="cuda", generator=g) * 2 - 1
+    with Stft(nfft, hop, "hann") as h:
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        assert h.num_frames(n) == 934
+        spec = h.batch_forward(x, "complex", "valid")
+        assert tuple(spec.shape) == (B, 934, 1025)
+        power = h.batch_forward(x, "power", "valid")
+        y = h.batch_inverse(spec, n, True)
+        torch.cuda.synchronize()
+        # round trip on the interior, every signal
+        num = torch.linalg.vector_norm((y - x)[:, nfft:-nfft].double(), dim=1)
+        den = torch.linalg.vector_norm(x[:, nfft:-nfft].double(), dim=1)
+        assert float((num / den).max()) <= ROUNDTRIP_REL_L2
+        # uncovered tail is exactly zero, first sample (w[0] = 0 -> norm 0) is zero
+        cov = 933 * hop + nfft
+        assert float(y[:, cov:].abs().max()) == 0.0 and float(y[:, 0].abs().max()) == 0.0
+        # power == |spec|^2
+        p2 = spec.real ** 2 + spec.imag ** 2
+        assert float(((power - p2).abs() / (p2.abs().amax(dim=-1, keepdim=True) + 1e-30)).max()) < 1e-6
+        # Parseval per frame against the windowed frame energy (checked on a subset of signals)
+        w = torch.hann_window(nfft, periodic=False, device="cuda")
+        fr = x[:8].unfold(1, nfft, hop) * w
+        e_time = (fr.double() ** 2).sum(-1)
+        pw = power[:8].double()
+        e_freq = (pw[..., 0] + pw[..., -1] + 2 * pw[..., 1:-1].sum(-1)) / nfft
+        assert float(((e_time - e_freq).abs() / e_time).max()) < 1e-5
+        # linearity: STFT(a x1 + b x2) == a STFT(x1) + b STFT(x2)
+        x1, x2 = x[:4], x[4:8]
+        lhs = h.batch_forward(0.5 * x1 - 1.5 * x2, "complex", "valid")
+        rhs = 0.5 * spec[:4] - 1.5 * spec[4:8]
+        torch.cuda.synchronize()
+        assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 2e-6
+        del spec, power, y, p2
+
+
+def test_full_size_spot_check_against_oracle(oracle):
+    """same full-size batch: 3 signals spot-checked bin by bin against the oracle"""
+    import torch
+    from vv_dsp_b200 import Stft
+    B, n, nfft, hop = 64, 480000, 2048, 512
+    x = np.stack([noise(5000 + i, n) for i in range(B)])
+    with Stft(nfft, hop, "hann") as h:
+        s = h.batch_forward(x, "complex", "valid")
+        y = h.batch_inverse(s, n, True)
+    for i in (0, 31, 63):
+        ref = oracle.stft(x[i], nfft, hop)
+        ok, frac = spectra_close(s[i], ref)
+        assert ok, (i, frac)
+        refy = oracle.istft(ref, nfft, hop, n)
+        assert rel_l2(y[i][nfft:-nfft], refy[nfft:-nfft]) < 2e-5
