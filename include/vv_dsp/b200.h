@@ -68,7 +68,8 @@ typedef enum vv_dsp_spec_kind {
 size_t vv_dsp_stft_num_frames(const vv_dsp_stft* h, size_t n, vv_dsp_frame_convention convention);
 size_t vv_dsp_stft_num_bins(const vv_dsp_stft* h);
 
-/* Bind the handle to a caller-owned cudaStream_t (NULL = the handle's own stream). */
+/* Bind the handle to a caller-owned cudaStream_t.  NULL = the handle's own (non-blocking) stream;
+ * to address CUDA's default streams pass cudaStreamLegacy ((void*)1) or cudaStreamPerThread ((void*)2). */
 vv_dsp_status vv_dsp_stft_set_stream(vv_dsp_stft* h, void* cuda_stream);
 /* Block until everything enqueued on the handle's stream has finished. */
 vv_dsp_status vv_dsp_stft_synchronize(vv_dsp_stft* h);

@@ -72,7 +72,9 @@ def check_batch_inverse(lib, oracle, nfft, hop, win, n, batch=2):
         cov = (frames - 1) * hop + nfft if frames else 0
         assert np.all(y[:, cov:] == 0) and np.all(raw[:, cov:] == 0)               # no frame covers: exactly 0
         lo, hi = nfft, n - nfft
-        if hi > lo:
+        # normalised comparisons only where the divide is well conditioned (Hann/Hamming at hop > nfft/2
+        # leave window-sums near zero; the raw overlap-add above is still compared everywhere)
+        if hi > lo and (2 * hop <= nfft or win == "boxcar"):
             assert rel_l2(y[:, lo:hi], refy[:, lo:hi]) <= 5e-5
             # the library's own STFT -> ISTFT round trip must meet the north-star bound
             own = h.batch_inverse(h.batch_forward(x, "complex", "valid"), n, True)
@@ -82,7 +84,7 @@ def check_batch_inverse(lib, oracle, nfft, hop, win, n, batch=2):
             one = h.istft(spec[0], n)
             assert np.array_equal(one, y[0])
         # truncated / extended output lengths (vv_dsp_overlap_add's drop rule, framing.c:139-145)
-        if frames:
+        if frames and (2 * hop <= nfft or win == "boxcar"):
             short = h.batch_inverse(spec, n // 2, True)
             refshort = oracle.istft(spec[0], nfft, hop, n // 2, win)
             m = slice(nfft, max(nfft, n // 2 - nfft))

@@ -215,8 +215,14 @@ class Stft:
         return int(self.lib.vv_dsp_stft_num_frames(self._h, n, CONVENTIONS[convention]))
 
     def set_stream(self, cuda_stream):
-        _check(self.lib, self.lib.vv_dsp_stft_set_stream(self._h, _vp(cuda_stream) if cuda_stream else None),
-               "vv_dsp_stft_set_stream")
+        """cuda_stream: a cudaStream_t as an integer.  None = the handle's own stream; 0 (the legacy default
+        stream, what torch reports for its default stream) is passed as cudaStreamLegacy (0x1), because the C
+        API reserves NULL for "the handle's own stream"."""
+        if cuda_stream is None:
+            arg = None
+        else:
+            arg = _vp(int(cuda_stream) or 1)
+        _check(self.lib, self.lib.vv_dsp_stft_set_stream(self._h, arg), "vv_dsp_stft_set_stream")
 
     def synchronize(self):
         _check(self.lib, self.lib.vv_dsp_stft_synchronize(self._h), "vv_dsp_stft_synchronize")
