@@ -49,6 +49,16 @@ def test_short_and_ragged_inputs(emu, oracle):
     pc.check_batch_inverse(emu, oracle, 256, 256, "boxcar", 2000)
 
 
+def test_marching_istft_partitions(emu, oracle):
+    """fft_size 2048 warp-marching ISTFT: warp ranges that start mid-signal (halo re-synthesis) and span
+    signal boundaries; all three instantiated hops; truncated and extended output lengths"""
+    for hop in (256, 512, 1024):
+        pc.check_batch_inverse(emu, oracle, 2048, hop, "hann", 2048 + hop * 10 + 100, batch=3)
+        pc.check_batch_inverse(emu, oracle, 2048, hop, "hamming", 2048 + hop * 37 + 1, batch=5)
+    pc.check_batch_inverse(emu, oracle, 2048, 512, "hann", 2048, batch=2)          # one frame per signal
+    pc.check_batch_inverse(emu, oracle, 2048, 512, "hann", 2048 + 511, batch=1)
+
+
 def test_spectrogram(emu, oracle):
     pc.check_spectrogram(emu, oracle, 512, 128, "hann", 3000)
     pc.check_spectrogram(emu, oracle, 64, 16, "hamming", 40)     # n < nfft: one zero-padded frame

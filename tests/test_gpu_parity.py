@@ -64,6 +64,15 @@ def test_short_and_ragged_inputs(lib, oracle):
     pc.check_batch_inverse(lib, oracle, 2048, 512, "hann", 2048 + 512 * 3 + 5, batch=1)
 
 
+def test_marching_istft_partitions(lib, oracle):
+    for hop in (256, 512, 1024):
+        pc.check_batch_inverse(lib, oracle, 2048, hop, "hann", 2048 + hop * 10 + 100, batch=3)
+        pc.check_batch_inverse(lib, oracle, 2048, hop, "hamming", 2048 + hop * 37 + 1, batch=5)
+        pc.check_batch_inverse(lib, oracle, 2048, hop, "hann", 300000, batch=9)
+    pc.check_batch_inverse(lib, oracle, 2048, 512, "hann", 2048, batch=2)
+    pc.check_batch_inverse(lib, oracle, 2048, 512, "hann", 2048 + 511, batch=1)
+
+
 def test_many_signals_chunking(lib, oracle):
     """more work items than resident CTAs, several chunks per signal in the ISTFT"""
     nfft, hop, n, B = 1024, 256, 200000, 7

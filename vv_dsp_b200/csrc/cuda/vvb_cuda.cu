@@ -355,6 +355,24 @@ template <bool OLA> static int dispatch_inverse(vvb_engine* e, const InvArgs& a,
     }
 }
 
+/* warp-marching ISTFT (fft_size 2048, hop = 64*S): register-resident overlap-add */
+template <int S> static int launch_march(vvb_engine* e, InvArgs a, long long batch, void* stream)
+{
+    using C = Cfg1024;
+    constexpr int W = 4;
+    static int per_sm = -1;
+    auto kern = istft_march_kernel<C, S, W>;
+    const size_t smem = sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::POST + 1) + 2 * W * C::XBUF);
+    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, 32 * W, smem);
+    if (per_sm == 0) return fail(4, "istft_march_kernel", "does not fit on this device");
+    if (batch > 0x7fffffffLL) return fail(2, "vvb_stft_inverse", "batch");
+    a.num_items = (int)batch;                                   /* the kernel partitions batch*frames itself */
+    const long long total = batch * a.frames;
+    const long long want = (total + 16 * W - 1) / (16 * W);     /* at least ~16 frames per warp */
+    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), 32 * W, smem, stream, a);
+    return 0;
+}
+
 static int ensure_scratch(vvb_engine* e, size_t bytes)
 {
     if (e->scratch_bytes >= bytes) return 0;
@@ -403,6 +421,11 @@ extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t bat
         a.frames = (int)frames; a.hop = (int)e->hop;
         a.y = d_y; a.y_pitch = (long long)y_pitch; a.n_out = (long long)n_out;
         a.inv_norm = d_inv_norm; a.tables = e->d_tables;
+        if (e->nfft == 2048 && !getenv("VVB_NO_MARCH")) {
+            if (e->hop == 256) return launch_march<4>(e, a, (long long)batch, stream);
+            if (e->hop == 512) return launch_march<8>(e, a, (long long)batch, stream);
+            if (e->hop == 1024) return launch_march<16>(e, a, (long long)batch, stream);
+        }
         return dispatch_inverse<true>(e, a, (long long)batch, stream);
     }
     /* direct path: synthesis frames to HBM scratch, then the stand-alone overlap-add kernel */

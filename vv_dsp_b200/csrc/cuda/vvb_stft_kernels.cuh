@@ -356,6 +356,110 @@ __global__ void __launch_bounds__(C::T* G) stft_inverse_kernel(const InvArgs a)
     }
 }
 
+/* ================================================= inverse, warp-marching specialisation */
+/* For one-warp teams (T == 32, i.e. fft_size 2048) and hop = 64*S: a warp walks consecutive
+ * frames of one signal and keeps the overlap-add accumulator IN REGISTERS.  Thread t owns the
+ * sample pairs (2i, 2i+1), i = t + 32 r, of every frame; advancing one frame shifts positions by
+ * hop = 2*32*S samples = S register slots of the SAME thread, so the accumulator is a register
+ * ring rotated by S slots per frame (compile-time indices: the frame loop is unrolled 32/S
+ * times).  After frame f is added, the first S slots hold finished samples [f*hop, (f+1)*hop):
+ * they are scaled by 1/sum(w^2) and stored with coalesced 64-bit stores, then cleared.
+ * No shared-memory slots, no carry buffers, no CTA barriers, no atomics; frames are added in
+ * ascending order exactly like the reference accumulates out_add (src/spectral/stft.c:103-108).
+ * Work is split into equal ranges of the flattened (signal, frame) sequence, one range per
+ * warp; a range that starts mid-signal first re-synthesises the 32/S - 1 frames before it. */
+template <class C, int S, int W>
+__global__ void __launch_bounds__(32 * W, 3) istft_march_kernel(const InvArgs a)
+{
+    static_assert(C::T == 32 && C::E == 32 && C::NP == 2, "one-warp teams only");
+    using TB = Tables<C>;
+    constexpr int M = C::M, N = 2 * M, E = C::E, PERIOD = 32 / S, HOP = 64 * S, EDGE = N - HOP;
+#ifdef VVB_EMU
+    float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float smem[];
+#endif
+    float* s_wsyn = smem;
+    float2* s_tw2 = reinterpret_cast<float2*>(s_wsyn + N);
+    float2* s_post = s_tw2 + C::TW2;
+    float2* s_xb = s_post + C::POST + 1;
+    copy_table(s_wsyn, a.tables + TB::WSYN, N);
+    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * C::TW2);
+    copy_table(reinterpret_cast<float*>(s_post), a.tables + TB::POST, 2 * C::POST);
+    __syncthreads();
+
+    const int warp = threadIdx.x / 32, t = threadIdx.x % 32;
+    float2* xb = s_xb + warp * C::XBUF;
+    const float2* wsyn2 = reinterpret_cast<const float2*>(s_wsyn);
+    const long long F = a.frames;
+    const long long total = (long long)a.num_items * F;               /* num_items carries the batch */
+    const long long nwarps = (long long)gridDim.x * W;
+    const long long quota = (total + nwarps - 1) / nwarps;
+    long long g0 = ((long long)blockIdx.x * W + warp) * quota;
+    const long long g1 = min(total, g0 + quota);
+
+    while (g0 < g1) {
+        const long long b = g0 / F;
+        const int f_begin = (int)(g0 % F);
+        const int f_end = (int)min(F, (long long)f_begin + (g1 - g0));
+        const bool last = (f_end == (int)F);
+        const int emit_end = last ? f_end + PERIOD - 1 : f_end;        /* hop-blocks [f_begin, emit_end) are ours */
+        const int fr0 = f_begin - min(PERIOD - 1, f_begin);            /* halo frames re-synthesised */
+        const float2* specb = a.spec + b * F * a.spec_pitch;
+        float* yb = a.y + b * a.y_pitch;
+        const bool y_vec = (reinterpret_cast<uintptr_t>(yb) & 7) == 0;
+        g0 += f_end - f_begin;
+
+        float2 acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = make_float2(0.f, 0.f);
+
+        for (int fb = fr0; fb < emit_end; fb += PERIOD) {
+#pragma unroll
+            for (int u = 0; u < PERIOD; ++u) {
+                const int frame = fb + u;
+                if (frame < f_end) {                                   /* warp-uniform */
+                    float2 v[E];
+                    team_inverse_frame<C>(v, specb + (long long)frame * a.spec_pitch, true, xb, s_tw2, nullptr, s_post, t, warp);
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const float2 z = v[ct_bitrev(r, 32)], w = wsyn2[t + 32 * r];
+                        float2& s = acc[(r + u * S) % 32];
+                        s.x = fmaf(z.y, w.x, s.x);                    /* Re z * w  (z is stored swapped) */
+                        s.y = fmaf(z.x, w.y, s.y);
+                    }
+                    __syncwarp();                                      /* xb is rewritten by the next frame */
+                }
+                if (frame >= f_begin && frame < emit_end) {
+                    /* 1/sum(w^2) for this hop-block: head / steady-state / tail table (warp-uniform choice) */
+                    const float* tab = nullptr;
+                    if (a.inv_norm) {
+                        if (frame >= F) tab = a.inv_norm + EDGE + HOP + (long long)(frame - F) * HOP;
+                        else if (frame < PERIOD - 1) tab = a.inv_norm + (long long)frame * HOP;
+                        else tab = a.inv_norm + EDGE;
+                    }
+                    const long long base = (long long)frame * HOP;
+#pragma unroll
+                    for (int r = 0; r < S; ++r) {
+                        const int c = 2 * (t + 32 * r);
+                        float2 o = acc[(r + u * S) % 32];
+                        if (tab) { const float2 sc = __ldg(reinterpret_cast<const float2*>(tab) + t + 32 * r); o.x *= sc.x; o.y *= sc.y; }
+                        const long long tt = base + c;
+                        if (y_vec && tt + 1 < a.n_out) *reinterpret_cast<float2*>(yb + tt) = o;
+                        else { if (tt < a.n_out) yb[tt] = o.x; if (tt + 1 < a.n_out) yb[tt + 1] = o.y; }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < S; ++r) acc[(r + u * S) % 32] = make_float2(0.f, 0.f);
+            }
+        }
+        if (last) {                                                    /* nothing covers [cov, n_out): zeros */
+            const long long cov = (F - 1) * HOP + N;
+            for (long long tt = cov + t; tt < a.n_out; tt += 32) yb[tt] = 0.f;
+        }
+    }
+}
+
 /* ===================================================== batched complex FFT (plan API) */
 struct C2CArgs {
     const float2* in;
