@@ -125,7 +125,7 @@ template <class K> static int rt_blocks_per_sm(K kern, int threads, size_t smem)
 
 /* -------------------------------------------------------------------- plan tables */
 /* Everything trigonometric is computed in double on the host and rounded once. */
-template <class C> static void build_tables(std::vector<float>& blob, const float* window)
+template <class C> static void build_tables(std::vector<float>& blob, const float* window, size_t hop = 0)
 {
     using TB = Tables<C>;
     constexpr int M = C::M, N = 2 * M;
@@ -149,6 +149,24 @@ template <class C> static void build_tables(std::vector<float>& blob, const floa
         const double ang = 2.0 * M_PI * (double)k / (double)N;
         blob[TB::POST + 2 * k] = (float)(0.5 * cos(ang));
         blob[TB::POST + 2 * k + 1] = (float)(0.5 * sin(ang));
+    }
+    /* steady-state window-sum sum_w2[c] = sum of w[c + i*hop]^2 over the frames covering a position,
+     * accumulated in ASCENDING frame order (descending i) in float32 like the reference's norm_add
+     * (src/spectral/stft.c:107), and the synthesis window with 1/sum_w2 folded in (guard 1e-12 as in
+     * tools/dump_stft_roundtrip.c:50-52) */
+    if (hop > 0 && hop <= (size_t)N) {
+        for (size_t c = 0; c < hop; ++c) {
+            float acc = 0.0f;
+            for (long long i = ((long long)N - 1 - (long long)c) / (long long)hop; i >= 0; --i) {
+                const float w = blob[TB::WIN + c + (size_t)i * hop];
+                acc += w * w;
+            }
+            blob[TB::MIDNORM + c] = acc;
+        }
+        for (int p = 0; p < N; ++p) {
+            const float nrm = blob[TB::MIDNORM + (size_t)p % hop];
+            blob[TB::WSYN_NORM + p] = nrm > 1e-12f ? blob[TB::WSYN + p] * (1.0f / nrm) : 0.0f;
+        }
     }
 }
 
@@ -213,12 +231,12 @@ extern "C" int vvb_engine_create(size_t nfft, size_t hop, const float* window, v
     std::vector<float> blob;
     if (e->fast) {
         switch (nfft / 2) {
-        case 128: build_tables<Cfg128>(blob, window); break;
-        case 256: build_tables<Cfg256>(blob, window); break;
-        case 512: build_tables<Cfg512>(blob, window); break;
-        case 1024: build_tables<Cfg1024>(blob, window); break;
-        case 2048: build_tables<Cfg2048>(blob, window); break;
-        default: build_tables<Cfg4096>(blob, window); break;
+        case 128: build_tables<Cfg128>(blob, window, hop); break;
+        case 256: build_tables<Cfg256>(blob, window, hop); break;
+        case 512: build_tables<Cfg512>(blob, window, hop); break;
+        case 1024: build_tables<Cfg1024>(blob, window, hop); break;
+        case 2048: build_tables<Cfg2048>(blob, window, hop); break;
+        default: build_tables<Cfg4096>(blob, window, hop); break;
         }
         st = upload(&e->d_tables, blob);
     } else {
@@ -275,6 +293,37 @@ template <class C> static int launch_forward(vvb_engine* e, const FwdArgs& a, in
     }
 }
 
+/* warp-marching STFT (fft_size 2048, hop = 64*S, zero padding): TMA-fed ring of hop-blocks per warp */
+template <int S, int W, int OUT> static int launch_fwd_march_w(vvb_engine* e, FwdArgs a, void* stream)
+{
+    using C = Cfg1024;
+    static int per_sm = -1;
+    auto kern = stft_march_kernel<C, S, W, OUT>;
+    const size_t smem = sizeof(float) * 2 * (C::TW2 + C::POST + 1 + W * C::XBUF + W * (32 / S + 1) * 32 * S) + 8 * W;
+    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, 32 * W, smem);
+    if (per_sm == 0) return fail(4, "stft_march_kernel", "does not fit on this device");
+    const long long total = (long long)a.num_groups * a.frames;  /* num_groups carries the batch */
+    const long long want = (total + 16 * W - 1) / (16 * W);
+    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), 32 * W, smem, stream, a);
+    return 0;
+}
+template <int S, int OUT> static int launch_fwd_march_s(vvb_engine* e, const FwdArgs& a, void* stream)
+{
+    static int w = -1;
+    if (w < 0) { const char* s = getenv("VVB_FWD_MARCH_W"); w = s ? atoi(s) : 8; }
+    if (w == 10) return launch_fwd_march_w<S, 10, OUT>(e, a, stream);
+    return launch_fwd_march_w<S, 8, OUT>(e, a, stream);
+}
+template <int S> static int launch_fwd_march(vvb_engine* e, const FwdArgs& a, int kind, void* stream)
+{
+    switch (kind) {
+    case OUT_COMPLEX: return launch_fwd_march_s<S, OUT_COMPLEX>(e, a, stream);
+    case OUT_POWER: return launch_fwd_march_s<S, OUT_POWER>(e, a, stream);
+    case OUT_MAGNITUDE: return launch_fwd_march_s<S, OUT_MAGNITUDE>(e, a, stream);
+    default: return fail(3, "vvb_stft_forward", "bad out_kind");
+    }
+}
+
 extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, size_t n, size_t x_pitch, size_t frames,
                                 int pad_mode, int out_kind, void* d_out, size_t out_pitch, void* stream)
 {
@@ -288,6 +337,11 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
         a.frames = (int)frames; a.hop = (int)e->hop; a.pad_mode = pad_mode;
         a.out = d_out; a.out_pitch = (long long)out_pitch; a.tables = e->d_tables;
         a.num_groups = (int)batch; a.groups_per_signal = 0;
+        if (e->nfft == 2048 && pad_mode == PAD_ZERO && !getenv("VVB_NO_MARCH")) {
+            if (e->hop == 256) return launch_fwd_march<4>(e, a, out_kind, stream);
+            if (e->hop == 512) return launch_fwd_march<8>(e, a, out_kind, stream);
+            if (e->hop == 1024) return launch_fwd_march<16>(e, a, out_kind, stream);
+        }
         switch (e->nfft / 2) {
         case 128: return launch_forward<Cfg128>(e, a, out_kind, stream);
         case 256: return launch_forward<Cfg256>(e, a, out_kind, stream);
@@ -355,14 +409,14 @@ template <bool OLA> static int dispatch_inverse(vvb_engine* e, const InvArgs& a,
     }
 }
 
-/* warp-marching ISTFT (fft_size 2048, hop = 64*S): register-resident overlap-add */
-template <int S> static int launch_march(vvb_engine* e, InvArgs a, long long batch, void* stream)
+/* warp-marching ISTFT (fft_size 2048, hop = 64*S): register-resident overlap-add.
+ * One CTA of W warps per SM; W trades warps in flight against registers per thread. */
+template <int S, int W> static int launch_march_w(vvb_engine* e, InvArgs a, long long batch, void* stream)
 {
     using C = Cfg1024;
-    constexpr int W = 4;
     static int per_sm = -1;
     auto kern = istft_march_kernel<C, S, W>;
-    const size_t smem = sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::POST + 1) + 2 * W * C::XBUF);
+    const size_t smem = sizeof(float) * (2 * C::M + 2 * C::TW2 + 2 * W * (C::XBUF + C::M + 2));
     if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, 32 * W, smem);
     if (per_sm == 0) return fail(4, "istft_march_kernel", "does not fit on this device");
     if (batch > 0x7fffffffLL) return fail(2, "vvb_stft_inverse", "batch");
@@ -371,6 +425,14 @@ template <int S> static int launch_march(vvb_engine* e, InvArgs a, long long bat
     const long long want = (total + 16 * W - 1) / (16 * W);     /* at least ~16 frames per warp */
     VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), 32 * W, smem, stream, a);
     return 0;
+}
+template <int S> static int launch_march(vvb_engine* e, const InvArgs& a, long long batch, void* stream)
+{
+    static int w = -1;
+    if (w < 0) { const char* s = getenv("VVB_MARCH_W"); w = s ? atoi(s) : 8; }   /* 8 warps: 226 regs, no spills (12 warps spill and are 1.5x slower) */
+    if (w == 8) return launch_march_w<S, 8>(e, a, batch, stream);
+    if (w == 10) return launch_march_w<S, 10>(e, a, batch, stream);
+    return launch_march_w<S, 12>(e, a, batch, stream);
 }
 
 static int ensure_scratch(vvb_engine* e, size_t bytes)
@@ -421,7 +483,8 @@ extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t bat
         a.frames = (int)frames; a.hop = (int)e->hop;
         a.y = d_y; a.y_pitch = (long long)y_pitch; a.n_out = (long long)n_out;
         a.inv_norm = d_inv_norm; a.tables = e->d_tables;
-        if (e->nfft == 2048 && !getenv("VVB_NO_MARCH")) {
+        const bool y_aligned = ((uintptr_t)d_y % 8 == 0) && (y_pitch % 2 == 0);   /* 64-bit stores */
+        if (e->nfft == 2048 && y_aligned && !getenv("VVB_NO_MARCH")) {
             if (e->hop == 256) return launch_march<4>(e, a, (long long)batch, stream);
             if (e->hop == 512) return launch_march<8>(e, a, (long long)batch, stream);
             if (e->hop == 1024) return launch_march<16>(e, a, (long long)batch, stream);

@@ -116,6 +116,14 @@ template <int N, int I> VVB_DEV float2 mul_w(float2 x)
  * W = 1 and W = -i need 4 adds.  A 32-point DFT is 388 FP instructions (456 in the
  * decimation-in-frequency form this replaced).  Input and output are in natural order; the
  * bit reversal of the recursion is only a renaming of registers. */
+template <int N, int K> struct DitTw {       /* all evaluated by the host compiler: plain immediates in SASS */
+    static constexpr double cd = ct_cos2pi(K, N), sd = ct_sin2pi(K, N);
+    static constexpr bool cos_form = (cd < 0 ? -cd : cd) >= (sd < 0 ? -sd : sd);
+    static constexpr float c = (float)cd, sn = (float)sd;
+    static constexpr float tn = cos_form ? (float)(sd / cd) : 0.f;      /* tan */
+    static constexpr float ct = cos_form ? 0.f : (float)(cd / sd);      /* cot */
+};
+
 template <int N, int K> VVB_DEV void dit_combine(float2 a, float2 b, float2& lo, float2& hi)
 {
     if constexpr (K == 0) {
@@ -124,15 +132,14 @@ template <int N, int K> VVB_DEV void dit_combine(float2 a, float2 b, float2& lo,
         lo = make_float2(a.x + b.y, a.y - b.x);
         hi = make_float2(a.x - b.y, a.y + b.x);
     } else {
-        constexpr double cd = ct_cos2pi(K, N), sd = ct_sin2pi(K, N);
-        constexpr bool cos_form = (cd < 0 ? -cd : cd) >= (sd < 0 ? -sd : sd);
-        if constexpr (cos_form) {
-            constexpr float tn = (float)(sd / cd), c = (float)cd;
+        using TW = DitTw<N, K>;
+        if constexpr (TW::cos_form) {
+            constexpr float tn = TW::tn, c = TW::c;
             const float pr = fmaf(tn, b.y, b.x), pi = fmaf(-tn, b.x, b.y);     /* b (1 - i tn) */
             lo = make_float2(fmaf(c, pr, a.x), fmaf(c, pi, a.y));
             hi = make_float2(fmaf(-c, pr, a.x), fmaf(-c, pi, a.y));
         } else {
-            constexpr float ct = (float)(cd / sd), sn = (float)sd;
+            constexpr float ct = TW::ct, sn = TW::sn;
             const float pr = fmaf(ct, b.x, b.y), pi = fmaf(ct, b.y, -b.x);     /* b (ct - i) */
             lo = make_float2(fmaf(sn, pr, a.x), fmaf(sn, pi, a.y));
             hi = make_float2(fmaf(-sn, pr, a.x), fmaf(-sn, pi, a.y));
@@ -211,8 +218,12 @@ template <int T> VVB_DEV void team_sync(int team)
  *   FIRST: v was filled by the caller (no shared-memory read, Ns == 1, no twiddle)
  *   LAST : results stay in registers: X[j + r*NS] = v[q*R + bitrev(r)], j = t + T*q
  * tw: this pass's table, tw[(r-1)*NS + (j % NS)] = exp(-2 pi i r (j%NS) / (NS*R)). */
-template <class C, int R, int NS, bool FIRST, bool LAST>
-VVB_DEV void stockham_pass(float2 (&v)[C::E], float2* xb, const float2* tw, int t, int team)
+struct NoHook { VVB_DEV void operator()() const {} };
+
+/* after_read: called once the team has finished READING xb in this pass (xb is free from then on
+ * if the pass is the last one) -- used to start the next frame's asynchronous prefetch into xb. */
+template <class C, int R, int NS, bool FIRST, bool LAST, class Hook = NoHook>
+VVB_DEV void stockham_pass(float2 (&v)[C::E], float2* xb, const float2* tw, int t, int team, Hook after_read = Hook())
 {
     constexpr int NQ = C::E / R;
     constexpr int STRIDE = C::M / R;
@@ -224,6 +235,7 @@ VVB_DEV void stockham_pass(float2 (&v)[C::E], float2* xb, const float2* tw, int 
             for (int r = 0; r < R; ++r) v[q * R + r] = xb[C::pad(j + r * STRIDE)];
         }
         team_sync<C::T>(team);     /* everyone has read before anyone overwrites xb */
+        after_read();
         if constexpr (NS > 1) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
@@ -251,16 +263,91 @@ VVB_DEV void stockham_pass(float2 (&v)[C::E], float2* xb, const float2* tw, int 
  *     v[q*R1 + r] = z[j + r*M/R1],  j = t + T*q
  * On exit it holds the spectrum of the last pass's items:
  *     Z[j + r*NSL] = v[q*RL + bitrev_RL(r)],  j = t + T*q,  NSL = M/RL  (RL = last radix). */
-template <class C> VVB_DEV void team_fft(float2 (&v)[C::E], float2* xb, const float2* tw2, const float2* tw3, int t, int team)
+template <class C, class Hook = NoHook>
+VVB_DEV void team_fft(float2 (&v)[C::E], float2* xb, const float2* tw2, const float2* tw3, int t, int team, Hook after_last_read = Hook())
 {
     if constexpr (C::NP == 2) {
         stockham_pass<C, C::R1, 1, true, false>(v, xb, nullptr, t, team);
-        stockham_pass<C, C::R2, C::R1, false, true>(v, xb, tw2, t, team);
+        stockham_pass<C, C::R2, C::R1, false, true>(v, xb, tw2, t, team, after_last_read);
     } else {
         stockham_pass<C, C::R1, 1, true, false>(v, xb, nullptr, t, team);
         stockham_pass<C, C::R2, C::R1, false, false>(v, xb, tw2, t, team);
-        stockham_pass<C, C::R3, C::R1 * C::R2, false, true>(v, xb, tw3, t, team);
+        stockham_pass<C, C::R3, C::R1 * C::R2, false, true>(v, xb, tw3, t, team, after_last_read);
     }
+}
+
+/* 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, completion via groups */
+VVB_DEV void cp_async8(float2* smem_dst, const float2* gsrc)
+{
+#ifdef VVB_EMU
+    *smem_dst = *gsrc;
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+VVB_DEV void cp_async_commit()
+{
+#ifndef VVB_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+VVB_DEV void cp_async_wait_all()
+{
+#ifndef VVB_EMU
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+/* ---- TMA 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) completing on an mbarrier.
+ * src, dst and bytes must be multiples of 16.  Issued by ONE thread. */
+VVB_DEV void mbar_init(unsigned long long* bar, unsigned count)
+{
+#ifdef VVB_EMU
+    *bar = 0;
+#else
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+VVB_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+#ifndef VVB_EMU
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+#endif
+}
+VVB_DEV void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar)
+{
+#ifdef VVB_EMU
+    memcpy(smem_dst, gsrc, bytes);
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+#endif
+}
+VVB_DEV void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+#ifndef VVB_EMU
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
+#endif
+}
+/* order earlier generic-proxy accesses of shared memory before later async-proxy (TMA) writes */
+VVB_DEV void fence_proxy_async()
+{
+#ifndef VVB_EMU
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
 }
 
 template <class C> struct LastPass {

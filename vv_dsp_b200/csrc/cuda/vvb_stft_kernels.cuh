@@ -39,7 +39,9 @@ template <class C> struct Tables {
     static constexpr int TW2 = WSYN + N;               /* float2[C::TW2] */
     static constexpr int TW3 = TW2 + 2 * C::TW2;       /* float2[C::TW3] */
     static constexpr int POST = TW3 + 2 * C::TW3;      /* float2[C::POST] = (cos,sin)(2 pi k/N)/2 */
-    static constexpr int TOTAL = POST + 2 * C::POST;
+    static constexpr int WSYN_NORM = POST + 2 * C::POST + 1;   /* w[p]/M * 1/sum_w2[p % hop]: normalisation folded in */
+    static constexpr int MIDNORM = WSYN_NORM + N;      /* sum_w2[c], c < hop (steady state, all frames present) */
+    static constexpr int TOTAL = MIDNORM + N;
 };
 
 struct FwdArgs {
@@ -191,6 +193,139 @@ __global__ void __launch_bounds__(C::T* G) stft_forward_kernel(const FwdArgs a)
             emit(M / 2, A.x, -A.y);
         }
         team_sync<T>(team);                                           /* xb is reused next group */
+    }
+}
+
+/* ================================================= forward, warp-marching specialisation */
+/* One-warp teams (fft_size 2048), hop = 64*S, zero padding.  A warp walks consecutive frames of one
+ * signal.  Consecutive frames share N - hop samples, so the warp keeps a ring of N/hop + 1 hop-blocks
+ * in shared memory and, per frame, fetches only the ONE new hop-block -- with a TMA 1-D bulk copy
+ * (cp.async.bulk, completion on an mbarrier) issued one frame ahead by a single lane.  Every input
+ * sample therefore leaves L2 once per warp-range instead of N/hop times, and its latency is
+ * covered by a whole frame of FFT work.  The window lives in registers (it depends only on the lane
+ * and the register slot), the split step and |X|^2 are fused as in stft_forward_kernel.  There are no
+ * CTA-wide barriers after the tables are loaded. */
+template <class C, int OUT>
+VVB_DEV void split_and_store(const float2* xb, const float2* s_post, int t, void* out, long long row)
+{
+    constexpr int M = C::M, E = C::E, T = C::T;
+    auto emit = [&](int k, float xr, float xi) {
+        if constexpr (OUT == OUT_COMPLEX) reinterpret_cast<float2*>(out)[row + k] = make_float2(xr, xi);
+        else if constexpr (OUT == OUT_POWER) reinterpret_cast<float*>(out)[row + k] = xr * xr + xi * xi;
+        else reinterpret_cast<float*>(out)[row + k] = sqrtf(xr * xr + xi * xi);
+    };
+#pragma unroll
+    for (int i = 0; i < E / 2; ++i) {
+        const int k = t + T * i;                                      /* 0 .. M/2-1 */
+        const float2 A = xb[C::pad(k)];
+        const float2 Bc = xb[C::pad((M - k) & (M - 1))];
+        const float2 hw = s_post[k];                                  /* (cos, sin)/2 */
+        const float sr = A.x + Bc.x, si = A.y - Bc.y;                 /* A + conj(Bc) */
+        const float dr = A.x - Bc.x, di = A.y + Bc.y;                 /* A - conj(Bc) */
+        const float gr = hw.y * dr - hw.x * di, gi = hw.y * di + hw.x * dr;
+        emit(k, 0.5f * sr - gr, 0.5f * si - gi);                     /* X[k]   */
+        emit(M - k, 0.5f * sr + gr, -(0.5f * si + gi));              /* X[M-k] */
+    }
+    if (t == 0) {                                                     /* k = M/2: X = conj(Z[M/2]) */
+        const float2 A = xb[C::pad(M / 2)];
+        emit(M / 2, A.x, -A.y);
+    }
+}
+
+template <class C, int S, int W, int OUT>
+__global__ void __launch_bounds__(32 * W, 1) stft_march_kernel(const FwdArgs a)
+{
+    static_assert(C::T == 32 && C::E == 32 && C::NP == 2, "one-warp teams only");
+    using TB = Tables<C>;
+    constexpr int M = C::M, N = 2 * M, E = C::E, NB = 32 / S, HOP = 64 * S, HB = HOP / 2;   /* HB float2 per hop-block */
+    constexpr int RING = NB + 1;
+#ifdef VVB_EMU
+    float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float smem[];
+#endif
+    float2* s_tw2 = reinterpret_cast<float2*>(smem);
+    float2* s_post = s_tw2 + C::TW2;
+    float2* s_xb = s_post + C::POST + 1;
+    float2* s_ring = s_xb + W * C::XBUF;                              /* W x RING x HB float2, 16-byte aligned */
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ring + W * RING * HB);
+    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * C::TW2);
+    copy_table(reinterpret_cast<float*>(s_post), a.tables + TB::POST, 2 * C::POST);
+    const int warp = threadIdx.x / 32, t = threadIdx.x % 32;
+    if (t == 0) mbar_init(&s_bar[warp], 1);
+    __syncthreads();
+
+    float2* xb = s_xb + warp * C::XBUF;
+    float2* ring = s_ring + warp * RING * HB;
+    unsigned long long* bar = &s_bar[warp];
+    unsigned parity = 0;
+
+    float2 win[32];                                                   /* window of this thread's sample pairs */
+#pragma unroll
+    for (int r = 0; r < 32; ++r) win[r] = __ldg(reinterpret_cast<const float2*>(a.tables + TB::WIN) + t + 32 * r);
+
+    const int F = a.frames;
+    const long long total = (long long)a.num_groups * F;              /* num_groups carries the batch */
+    const long long nwarps = (long long)gridDim.x * W;
+    const long long quota = (total + nwarps - 1) / nwarps;
+    long long g0 = ((long long)blockIdx.x * W + warp) * quota;
+    const long long g1 = min(total, g0 + quota);
+
+    while (g0 < g1) {
+        const int b = (int)(g0 / F);
+        const int f_begin = (int)(g0 - (long long)b * F);
+        const int f_end = (int)min((long long)F, (long long)f_begin + (g1 - g0));
+        const float* xs = a.x + (long long)b * a.x_pitch;
+        const bool bulk_ok = (reinterpret_cast<uintptr_t>(xs) & 15) == 0;
+        g0 += f_end - f_begin;
+
+        /* bring hop-block j (samples [j*HOP, (j+1)*HOP), zeros past n) into its ring slot; returns true
+         * if a TMA copy was issued (completion must then be awaited on the mbarrier) */
+        auto load_block = [&](int j) -> bool {
+            float2* dst = ring + (j % RING) * HB;
+            const long long s0 = (long long)j * HOP;
+            if (bulk_ok && s0 + HOP <= a.n) {
+                if (t == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(bar, HOP * 4);
+                    bulk_load(dst, xs + s0, HOP * 4, bar);
+                }
+                return true;
+            }
+#pragma unroll
+            for (int r = 0; r < S; ++r) {
+                const long long i0 = s0 + 2 * (t + 32 * r);
+                dst[t + 32 * r] = make_float2(i0 < a.n ? __ldg(xs + i0) : 0.f, i0 + 1 < a.n ? __ldg(xs + i0 + 1) : 0.f);
+            }
+            return false;
+        };
+
+        /* prologue: the N/hop blocks of the first frame, one after another */
+        for (int q = 0; q < NB; ++q) {
+            __syncwarp();
+            if (load_block(f_begin + q)) { mbar_wait(bar, parity); parity ^= 1; }
+        }
+        bool pending = false;
+
+#pragma unroll 1
+        for (int frame = f_begin; frame < f_end; ++frame) {
+            if (pending) { mbar_wait(bar, parity); parity ^= 1; }      /* block frame+NB-1 has landed */
+            __syncwarp();                                              /* ... and manual fills are visible */
+            /* fetch the next frame's new block now: it goes to the slot of block frame-1, which nobody
+             * reads any more, and has this whole frame's FFT to arrive */
+            pending = (frame + 1 < f_end) ? load_block(frame + NB) : false;
+            float2 v[E];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const float2 s = ring[((frame + r / S) % RING) * HB + t + 32 * (r % S)];
+                v[r] = make_float2(s.x * win[r].x, s.y * win[r].y);
+            }
+            team_fft<C>(v, xb, s_tw2, nullptr, t, warp);
+            team_store_natural<C>(v, xb, t);
+            __syncwarp();
+            split_and_store<C, OUT>(xb, s_post, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+            __syncwarp();                                              /* xb is reused by the next frame */
+        }
     }
 }
 
@@ -368,12 +503,36 @@ __global__ void __launch_bounds__(C::T* G) stft_inverse_kernel(const InvArgs a)
  * ascending order exactly like the reference accumulates out_add (src/spectral/stft.c:103-108).
  * Work is split into equal ranges of the flattened (signal, frame) sequence, one range per
  * warp; a range that starts mid-signal first re-synthesises the 32/S - 1 frames before it. */
+/* merge step of the marching ISTFT for one bin k = t + 32 R of this thread (R compile time):
+ *     Z[k] = (X[k] + conj X[M-k])/2 + (j/2) conj(W_N^k) (X[k] - conj X[M-k]),  W_N^k = W_N^t * W_64^R
+ * read from the staged half spectrum in xb, result stored re/im swapped for the forward-FFT trick */
+template <class C, int R> VVB_DEV void march_merge_one(float2 (&v)[C::E], const float2* st, int t, float2 hw_t)
+{
+    constexpr int M = C::M;
+    float2 x = st[t + 32 * R];                                        /* st: staged X[0..M], natural order */
+    float2 y = st[M - t - 32 * R];
+    if constexpr (R == 0) {
+        if (t == 0) { x.y = 0.f; y.y = 0.f; }                          /* Re(IDFT): DC / Nyquist imag drop out */
+    }
+    constexpr float cr = TwC<64, R>::c, sr = TwC<64, R>::s;
+    const float hc = hw_t.x * cr - hw_t.y * sr, hs = hw_t.y * cr + hw_t.x * sr;   /* (cos,sin)(2 pi k/N)/2 */
+    const float sre = x.x + y.x, sim = x.y - y.y;                     /* x + conj(y) */
+    const float dre = x.x - y.x, dim = x.y + y.y;                     /* x - conj(y) */
+    const float ur = -hs * dre - hc * dim, ui = -hs * dim + hc * dre;
+    v[R] = make_float2(0.5f * sim + ui, 0.5f * sre + ur);             /* (Im Z, Re Z) */
+}
+template <class C, int... Rs> VVB_DEV void march_merge(float2 (&v)[C::E], const float2* st, int t, float2 hw_t, iseq<Rs...>)
+{
+    (march_merge_one<C, Rs>(v, st, t, hw_t), ...);
+}
+
 template <class C, int S, int W>
-__global__ void __launch_bounds__(32 * W, 3) istft_march_kernel(const InvArgs a)
+__global__ void __launch_bounds__(32 * W, 1) istft_march_kernel(const InvArgs a)
 {
     static_assert(C::T == 32 && C::E == 32 && C::NP == 2, "one-warp teams only");
     using TB = Tables<C>;
     constexpr int M = C::M, N = 2 * M, E = C::E, PERIOD = 32 / S, HOP = 64 * S, EDGE = N - HOP;
+    constexpr int STG = M + 2;                                        /* staged half spectrum X[0..M] (+1 pad) */
 #ifdef VVB_EMU
     float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
 #else
@@ -381,17 +540,24 @@ __global__ void __launch_bounds__(32 * W, 3) istft_march_kernel(const InvArgs a)
 #endif
     float* s_wsyn = smem;
     float2* s_tw2 = reinterpret_cast<float2*>(s_wsyn + N);
-    float2* s_post = s_tw2 + C::TW2;
-    float2* s_xb = s_post + C::POST + 1;
-    copy_table(s_wsyn, a.tables + TB::WSYN, N);
+    float2* s_xb = s_tw2 + C::TW2;
+    float2* s_stage = s_xb + W * C::XBUF;
+    /* normalised synthesis: the steady-state 1/sum(w^2) is already folded into the window table, so the
+     * main path has no per-sample table load or multiply; only the first/last 32/S-1 hop-blocks of a
+     * signal (fewer frames overlap there) are rescaled, below */
+    const bool normalise = a.inv_norm != nullptr;
+    copy_table(s_wsyn, a.tables + (normalise ? TB::WSYN_NORM : TB::WSYN), N);
     copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * C::TW2);
-    copy_table(reinterpret_cast<float*>(s_post), a.tables + TB::POST, 2 * C::POST);
     __syncthreads();
 
     const int warp = threadIdx.x / 32, t = threadIdx.x % 32;
-    float2* xb = s_xb + warp * C::XBUF;
+    float2* xb = s_xb + warp * C::XBUF;                               /* FFT exchange buffer of this warp */
+    float2* stage = s_stage + warp * STG;                             /* next frame's spectrum lands here */
     const float2* wsyn2 = reinterpret_cast<const float2*>(s_wsyn);
-    const long long F = a.frames;
+    /* split-step twiddle of this lane: (cos, sin)(2 pi t / N) / 2; the bins k = t + 32 r of a thread
+     * differ from it by the compile-time rotation 2 pi r / 64 */
+    const float2 hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);
+    const int F = a.frames;
     const long long total = (long long)a.num_items * F;               /* num_items carries the batch */
     const long long nwarps = (long long)gridDim.x * W;
     const long long quota = (total + nwarps - 1) / nwarps;
@@ -399,62 +565,84 @@ __global__ void __launch_bounds__(32 * W, 3) istft_march_kernel(const InvArgs a)
     const long long g1 = min(total, g0 + quota);
 
     while (g0 < g1) {
-        const long long b = g0 / F;
-        const int f_begin = (int)(g0 % F);
-        const int f_end = (int)min(F, (long long)f_begin + (g1 - g0));
-        const bool last = (f_end == (int)F);
-        const int emit_end = last ? f_end + PERIOD - 1 : f_end;        /* hop-blocks [f_begin, emit_end) are ours */
+        const int b = (int)(g0 / F);
+        const int f_begin = (int)(g0 - (long long)b * F);
+        const int f_end = (int)min((long long)F, (long long)f_begin + (g1 - g0));
+        const int emit_end = (f_end == F) ? f_end + PERIOD - 1 : f_end;   /* hop-blocks [f_begin, emit_end) are ours */
         const int fr0 = f_begin - min(PERIOD - 1, f_begin);            /* halo frames re-synthesised */
-        const float2* specb = a.spec + b * F * a.spec_pitch;
-        float* yb = a.y + b * a.y_pitch;
-        const bool y_vec = (reinterpret_cast<uintptr_t>(yb) & 7) == 0;
+        const float2* specb = a.spec + (long long)b * F * a.spec_pitch;
+        float* yb = a.y + (long long)b * a.y_pitch;
         g0 += f_end - f_begin;
+
+        /* asynchronous copy (LDGSTS) of one frame's half spectrum into the warp's staging buffer; issued
+         * right after the previous frame's merge has consumed the buffer, so it is in flight for a whole
+         * frame time */
+        auto prefetch = [&](int frame) {
+            if (frame < f_end) {
+                const float2* X = specb + (long long)frame * a.spec_pitch;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) cp_async8(&stage[t + 32 * r], X + t + 32 * r);
+                if (t == 0) cp_async8(&stage[M], X + M);
+            }
+            cp_async_commit();
+        };
 
         float2 acc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = make_float2(0.f, 0.f);
+        prefetch(fr0);
 
-        for (int fb = fr0; fb < emit_end; fb += PERIOD) {
+#pragma unroll 1
+        for (int frame = fr0; frame < emit_end; ++frame) {
+            if (frame < f_end) {                                       /* warp-uniform */
+                float2 v[E];
+                cp_async_wait_all();
+                __syncwarp();
+                /* merge straight into the pass-1 registers (see march_merge_one) */
+                march_merge<C>(v, stage, t, hw_t, typename make_iseq<32>::type{});
+                __syncwarp();                                          /* all reads of the staged X are done */
+                prefetch(frame + 1);
+                team_fft<C>(v, xb, s_tw2, nullptr, t, warp);
 #pragma unroll
-            for (int u = 0; u < PERIOD; ++u) {
-                const int frame = fb + u;
-                if (frame < f_end) {                                   /* warp-uniform */
-                    float2 v[E];
-                    team_inverse_frame<C>(v, specb + (long long)frame * a.spec_pitch, true, xb, s_tw2, nullptr, s_post, t, warp);
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        const float2 z = v[ct_bitrev(r, 32)], w = wsyn2[t + 32 * r];
-                        float2& s = acc[(r + u * S) % 32];
-                        s.x = fmaf(z.y, w.x, s.x);                    /* Re z * w  (z is stored swapped) */
-                        s.y = fmaf(z.x, w.y, s.y);
-                    }
-                    __syncwarp();                                      /* xb is rewritten by the next frame */
+                for (int r = 0; r < 32; ++r) {
+                    const float2 z = v[r], w = wsyn2[t + 32 * r];
+                    acc[r].x = fmaf(z.y, w.x, acc[r].x);              /* Re z * w  (z is stored swapped) */
+                    acc[r].y = fmaf(z.x, w.y, acc[r].y);
                 }
-                if (frame >= f_begin && frame < emit_end) {
-                    /* 1/sum(w^2) for this hop-block: head / steady-state / tail table (warp-uniform choice) */
-                    const float* tab = nullptr;
-                    if (a.inv_norm) {
-                        if (frame >= F) tab = a.inv_norm + EDGE + HOP + (long long)(frame - F) * HOP;
-                        else if (frame < PERIOD - 1) tab = a.inv_norm + (long long)frame * HOP;
-                        else tab = a.inv_norm + EDGE;
-                    }
-                    const long long base = (long long)frame * HOP;
+            }
+            if (frame >= f_begin) {
+                const long long base = (long long)frame * HOP;
+                if (normalise && (frame < PERIOD - 1 || frame >= F)) {
+                    /* edge block: fewer than 32/S frames overlap; undo the folded steady-state factor and
+                     * apply this block's own 1/sum(w^2) (head or tail table of InvArgs::inv_norm) */
+                    const float* edge = (frame >= F) ? a.inv_norm + EDGE + HOP + (long long)(frame - F) * HOP
+                                                     : a.inv_norm + (long long)frame * HOP;
+                    const float* mid = a.tables + TB::MIDNORM;
 #pragma unroll
                     for (int r = 0; r < S; ++r) {
                         const int c = 2 * (t + 32 * r);
-                        float2 o = acc[(r + u * S) % 32];
-                        if (tab) { const float2 sc = __ldg(reinterpret_cast<const float2*>(tab) + t + 32 * r); o.x *= sc.x; o.y *= sc.y; }
-                        const long long tt = base + c;
-                        if (y_vec && tt + 1 < a.n_out) *reinterpret_cast<float2*>(yb + tt) = o;
-                        else { if (tt < a.n_out) yb[tt] = o.x; if (tt + 1 < a.n_out) yb[tt + 1] = o.y; }
+                        acc[r].x *= __ldg(edge + c) * __ldg(mid + c);
+                        acc[r].y *= __ldg(edge + c + 1) * __ldg(mid + c + 1);
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < S; ++r) acc[(r + u * S) % 32] = make_float2(0.f, 0.f);
+                for (int r = 0; r < S; ++r) {
+                    const long long tt = base + 2 * (t + 32 * r);
+                    if (tt + 1 < a.n_out) *reinterpret_cast<float2*>(yb + tt) = acc[r];
+                    else if (tt < a.n_out) yb[tt] = acc[r].x;
+                }
             }
+            /* advance one hop: slot r now means what slot r+S meant (register moves; a 32/S-fold
+             * unrolled frame loop would not fit the instruction cache) */
+#pragma unroll
+            for (int r = 0; r < 32 - S; ++r) acc[r] = acc[r + S];
+#pragma unroll
+            for (int r = 32 - S; r < 32; ++r) acc[r] = make_float2(0.f, 0.f);
         }
-        if (last) {                                                    /* nothing covers [cov, n_out): zeros */
-            const long long cov = (F - 1) * HOP + N;
+        cp_async_wait_all();                                           /* nothing in flight across pieces */
+        __syncwarp();
+        if (f_end == F) {                                              /* nothing covers [cov, n_out): zeros */
+            const long long cov = (long long)(F - 1) * HOP + N;
             for (long long tt = cov + t; tt < a.n_out; tt += 32) yb[tt] = 0.f;
         }
     }
