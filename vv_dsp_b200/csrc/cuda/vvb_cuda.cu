@@ -116,9 +116,18 @@ extern "C" int vvb_stream_wait_event(void* s, void* e) { CK(cudaStreamWaitEvent(
 /* opt in to the dynamic shared memory the kernel needs and ask how many CTAs fit per SM */
 template <class K> static int rt_blocks_per_sm(K kern, int threads, size_t smem)
 {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    cudaError_t e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) return 0;
+    cudaError_t e2 = (e1 == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) : e1;
+    if (e2 != cudaSuccess || nb == 0) {
+        cudaFuncAttributes fa;
+        memset(&fa, 0, sizeof(fa));
+        cudaFuncGetAttributes(&fa, kern);
+        fprintf(stderr, "vvb: kernel does not fit: %s (threads %d, dyn smem %zu, regs %d, static smem %zu, maxThreadsPerBlock %d)\n",
+                cudaGetErrorString(e2), threads, smem, fa.numRegs, fa.sharedSizeBytes, fa.maxThreadsPerBlock);
+        cudaGetLastError();
+        return 0;
+    }
     return nb;
 }
 #endif
@@ -311,7 +320,7 @@ template <int S, int OUT> static int launch_fwd_march_s(vvb_engine* e, const Fwd
 {
     static int w = -1;
     if (w < 0) { const char* s = getenv("VVB_FWD_MARCH_W"); w = s ? atoi(s) : 8; }
-    if (w == 10) return launch_fwd_march_w<S, 10, OUT>(e, a, stream);
+    (void)w;
     return launch_fwd_march_w<S, 8, OUT>(e, a, stream);
 }
 template <int S> static int launch_fwd_march(vvb_engine* e, const FwdArgs& a, int kind, void* stream)
@@ -430,9 +439,10 @@ template <int S> static int launch_march(vvb_engine* e, const InvArgs& a, long l
 {
     static int w = -1;
     if (w < 0) { const char* s = getenv("VVB_MARCH_W"); w = s ? atoi(s) : 8; }   /* 8 warps: 226 regs, no spills (12 warps spill and are 1.5x slower) */
-    if (w == 8) return launch_march_w<S, 8>(e, a, batch, stream);
-    if (w == 10) return launch_march_w<S, 10>(e, a, batch, stream);
-    return launch_march_w<S, 12>(e, a, batch, stream);
+    /* registers are partitioned per SM sub-partition (16 K each): 8 warps = 2 per sub-partition may use
+     * 255 registers, 9..12 warps put 3 on one and cap at 168, which spills (measured 1.5x slower) */
+    if (w == 12) return launch_march_w<S, 12>(e, a, batch, stream);
+    return launch_march_w<S, 8>(e, a, batch, stream);
 }
 
 static int ensure_scratch(vvb_engine* e, size_t bytes)

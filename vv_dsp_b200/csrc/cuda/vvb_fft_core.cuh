@@ -27,10 +27,12 @@
 #include "cuda_emu.h"
 #define VVB_DEV inline __attribute__((always_inline))
 #define VVB_CX constexpr
+#define VVB_MAXNREG(n)
 #else
 #include <cuda_runtime.h>
 #define VVB_DEV __device__ __forceinline__
 #define VVB_CX __host__ __device__ constexpr
+#define VVB_MAXNREG(n) __maxnreg__(n)      /* explicit per-thread register cap (one CTA of W warps per SM) */
 #endif
 
 namespace vvb {

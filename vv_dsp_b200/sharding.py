@@ -1,0 +1,115 @@
+"""Multi-GPU partitioning of the STFT path.  One process per GPU,
+torch.distributed for the plumbing (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+
+* Batched independent signals: `shard_batch` -- contiguous ranges of the batch per rank, no
+  communication at all.
+* One long stream: `stream_stft` / `stream_istft` -- rank d owns frames [F*d/G, F*(d+1)/G) and
+  the samples [f0*hop, f1*hop) (the last rank up to n).  Analysis needs the first nfft-hop
+  samples of the right neighbour (one point-to-point "halo" message, 12 KB at nfft=4096/hop=1024).
+  Synthesis runs the fused, normalised ISTFT kernel on the local frames, then sends the trailing
+  nfft-hop partial sums to the right neighbour, which adds them to its head and renormalises
+  those nfft-hop samples with the global window-sum; everything else is already final.
+
+The functions take a `vv_dsp_b200.Stft` handle; tensors may be CUDA tensors (device-resident
+path) or CPU tensors (host-staged path).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(batch: int, world: int, rank: int) -> tuple[int, int]:
+    """contiguous [start, stop) of the batch dimension owned by `rank`"""
+    return batch * rank // world, batch * (rank + 1) // world
+
+
+def frame_range(frames: int, world: int, rank: int) -> tuple[int, int]:
+    return frames * rank // world, frames * (rank + 1) // world
+
+
+def owned_samples(n: int, nfft: int, hop: int, world: int, rank: int) -> tuple[int, int]:
+    """[s0, s1) of the stream that `rank` owns: its frames' hop-blocks; the last rank also the rest"""
+    frames = 0 if n < nfft else 1 + (n - nfft) // hop
+    f0, f1 = frame_range(frames, world, rank)
+    return f0 * hop, (n if rank == world - 1 else f1 * hop)
+
+
+def window_sum(w2: torch.Tensor, nfft: int, hop: int, frames: int, t0: int, count: int) -> torch.Tensor:
+    """sum over frames f in [0, frames) covering position t of w2[t - f*hop], t = t0 .. t0+count-1,
+    accumulated in ascending frame order in float32 (the reference's norm_add order)."""
+    t = torch.arange(t0, t0 + count, device=w2.device, dtype=torch.int64)
+    acc = torch.zeros(count, device=w2.device, dtype=torch.float32)
+    k = (nfft + hop - 1) // hop
+    for i in range(k - 1, -1, -1):                      # descending i == ascending frame index
+        f = torch.div(t, hop, rounding_mode="floor") - i
+        p = t - f * hop
+        ok = (f >= 0) & (f < frames) & (p < nfft)
+        acc = acc + torch.where(ok, w2[p.clamp(0, nfft - 1)], torch.zeros((), device=w2.device))
+    return acc
+
+
+def _as_lib(x: torch.Tensor):
+    return x if x.is_cuda else x.numpy()
+
+
+def _from_lib(y, like: torch.Tensor) -> torch.Tensor:
+    return y if isinstance(y, torch.Tensor) else torch.from_numpy(y)
+
+
+def _exchange(send_to: int | None, send_buf: torch.Tensor | None, recv_from: int | None, recv_buf: torch.Tensor | None, group=None):
+    ops = []
+    if send_to is not None:
+        ops.append(dist.P2POp(dist.isend, send_buf, send_to, group))
+    if recv_from is not None:
+        ops.append(dist.P2POp(dist.irecv, recv_buf, recv_from, group))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+
+def stream_stft(h, x_owned: torch.Tensor, n: int, kind: str = "complex", group=None) -> torch.Tensor:
+    """STFT (valid frames) of one stream of n samples sharded by frame range.  `x_owned` is this
+    rank's slice `owned_samples(...)`.  Returns this rank's frames [f1-f0, bins]."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nfft, hop = h.nfft, h.hop
+    frames = 0 if n < nfft else 1 + (n - nfft) // hop
+    f0, f1 = frame_range(frames, world, rank)
+    halo = nfft - hop
+    assert world == 1 or frames // world >= (nfft + hop - 1) // hop, "shards must be longer than one frame"
+    recv = torch.empty(halo, dtype=torch.float32, device=x_owned.device) if rank < world - 1 else None
+    send = x_owned[:halo].contiguous() if rank > 0 else None
+    if halo and world > 1:
+        _exchange(rank - 1 if rank > 0 else None, send, rank + 1 if rank < world - 1 else None, recv, group)
+    local = torch.cat([x_owned, recv]) if (recv is not None and halo) else x_owned
+    spec = _from_lib(h.batch_forward(_as_lib(local[None, :].contiguous()), kind, "valid"), local)[0]
+    assert spec.shape[0] == f1 - f0, (spec.shape, f0, f1)
+    return spec
+
+
+def stream_istft(h, spec_local: torch.Tensor, n: int, window: torch.Tensor, group=None) -> torch.Tensor:
+    """ISTFT with window-sum normalisation of a frame-range-sharded stream; `window` is the handle's
+    window (float32[nfft], same device as spec_local).  Returns this rank's owned samples."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nfft, hop = h.nfft, h.hop
+    frames = 0 if n < nfft else 1 + (n - nfft) // hop
+    f0, f1 = frame_range(frames, world, rank)
+    s0, s1 = owned_samples(n, nfft, hop, world, rank)
+    fl, edge = f1 - f0, nfft - hop
+    span = (fl - 1) * hop + nfft if fl else 0
+    n_local = max(span, s1 - s0)
+    y = _from_lib(h.batch_inverse(_as_lib(spec_local[None].contiguous()), n_local, True), spec_local)[0]
+    if world > 1 and edge:
+        w2 = (window * window).to(torch.float32)
+        send = recv = None
+        if rank < world - 1:                              # raw partial sums of the tail beyond my range
+            send = (y[fl * hop: fl * hop + edge] * window_sum(w2, nfft, hop, fl, fl * hop, edge)).contiguous()
+        if rank > 0:
+            recv = torch.empty(edge, dtype=torch.float32, device=y.device)
+        _exchange(rank + 1 if rank < world - 1 else None, send, rank - 1 if rank > 0 else None, recv, group)
+        if rank > 0:                                      # head: undo the local normalisation, add, renormalise globally
+            raw = y[:edge] * window_sum(w2, nfft, hop, fl, 0, edge) + recv
+            norm = window_sum(w2, nfft, hop, frames, s0, edge)
+            y[:edge] = torch.where(norm > 1e-12, raw / norm, torch.zeros_like(raw))
+    return y[: s1 - s0].contiguous()
