@@ -193,3 +193,20 @@ def test_full_size_spot_check_against_oracle(oracle):
         assert ok, (i, frac)
         refy = oracle.istft(ref, nfft, hop, n)
         assert rel_l2(y[i][nfft:-nfft], refy[nfft:-nfft]) < 2e-5
+
+
+def test_stream_sharding_nccl():
+    """config-4 style frame-range sharding over NCCL; needs >= 2 GPUs (skipped on a 1-GPU box)"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = min(torch.cuda.device_count(), 4)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(here, "nccl_stream_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "nccl stream sharding ok" in r.stdout
