@@ -302,34 +302,46 @@ template <class C> static int launch_forward(vvb_engine* e, const FwdArgs& a, in
     }
 }
 
-/* warp-marching STFT (fft_size 2048, hop = 64*S, zero padding): TMA-fed ring of hop-blocks per warp */
-template <int S, int W, int OUT> static int launch_fwd_march_w(vvb_engine* e, FwdArgs a, void* stream)
+/* team-marching kernels (whole-warp teams: fft_size 2048 / 4096 / 8192, hop = 2*T*S dividing fft_size).
+ * G teams per CTA and CTAs per SM chosen per configuration: registers are partitioned per SM sub-partition
+ * (16 K each), so 8 warps per SM may use 255 registers per thread but 9..12 warps cap at 168. */
+template <class C> struct March;
+template <> struct March<Cfg1024> { static constexpr int G = 8, MINB = 1; };   /* 256 thr, 232 regs, 1 CTA/SM */
+template <> struct March<Cfg2048> { static constexpr int G = 2, MINB = 2; };   /* 256 thr, 2 CTAs/SM */
+template <> struct March<Cfg4096> { static constexpr int G = 2, MINB = 1; };   /* 512 thr, 1 CTA/SM */
+
+template <class C, int S, int OUT> static int launch_fwd_march_t(vvb_engine* e, FwdArgs a, void* stream)
 {
-    using C = Cfg1024;
+    constexpr int G = March<C>::G, MINB = March<C>::MINB;
     static int per_sm = -1;
-    auto kern = stft_march_kernel<C, S, W, OUT>;
-    const size_t smem = sizeof(float) * 2 * (C::TW2 + C::POST + 1 + W * C::XBUF + W * (32 / S + 1) * 32 * S) + 8 * W;
-    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, 32 * W, smem);
+    auto kern = stft_march_kernel<C, S, G, MINB, OUT>;
+    const size_t smem = sizeof(float) * 2 * (C::TW2 + C::TW3 + C::POST + 1 + G * C::XBUF + G * (C::E / S + 1) * C::T * S) + 8 * G;
+    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
     if (per_sm == 0) return fail(4, "stft_march_kernel", "does not fit on this device");
     const long long total = (long long)a.num_groups * a.frames;  /* num_groups carries the batch */
-    const long long want = (total + 16 * W - 1) / (16 * W);
-    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), 32 * W, smem, stream, a);
+    const long long want = (total + 16 * G - 1) / (16 * G);      /* at least ~16 frames per team */
+    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), C::T * G, smem, stream, a);
     return 0;
 }
-template <int S, int OUT> static int launch_fwd_march_s(vvb_engine* e, const FwdArgs& a, void* stream)
-{
-    static int w = -1;
-    if (w < 0) { const char* s = getenv("VVB_FWD_MARCH_W"); w = s ? atoi(s) : 8; }
-    (void)w;
-    return launch_fwd_march_w<S, 8, OUT>(e, a, stream);
-}
-template <int S> static int launch_fwd_march(vvb_engine* e, const FwdArgs& a, int kind, void* stream)
+template <class C, int S> static int launch_fwd_march_s(vvb_engine* e, const FwdArgs& a, int kind, void* stream)
 {
     switch (kind) {
-    case OUT_COMPLEX: return launch_fwd_march_s<S, OUT_COMPLEX>(e, a, stream);
-    case OUT_POWER: return launch_fwd_march_s<S, OUT_POWER>(e, a, stream);
-    case OUT_MAGNITUDE: return launch_fwd_march_s<S, OUT_MAGNITUDE>(e, a, stream);
+    case OUT_COMPLEX: return launch_fwd_march_t<C, S, OUT_COMPLEX>(e, a, stream);
+    case OUT_POWER: return launch_fwd_march_t<C, S, OUT_POWER>(e, a, stream);
+    case OUT_MAGNITUDE: return launch_fwd_march_t<C, S, OUT_MAGNITUDE>(e, a, stream);
     default: return fail(3, "vvb_stft_forward", "bad out_kind");
+    }
+}
+/* returns -1 when this (fft_size, hop) has no marching kernel */
+template <class C> static int launch_fwd_march(vvb_engine* e, const FwdArgs& a, int kind, void* stream)
+{
+    const size_t unit = 2 * (size_t)C::T;                        /* samples per register slot of a team */
+    if (e->hop % unit) return -1;
+    switch (e->hop / unit) {
+    case C::E / 8: return launch_fwd_march_s<C, C::E / 8>(e, a, kind, stream);
+    case C::E / 4: return launch_fwd_march_s<C, C::E / 4>(e, a, kind, stream);
+    case C::E / 2: return launch_fwd_march_s<C, C::E / 2>(e, a, kind, stream);
+    default: return -1;
     }
 }
 
@@ -346,10 +358,12 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
         a.frames = (int)frames; a.hop = (int)e->hop; a.pad_mode = pad_mode;
         a.out = d_out; a.out_pitch = (long long)out_pitch; a.tables = e->d_tables;
         a.num_groups = (int)batch; a.groups_per_signal = 0;
-        if (e->nfft == 2048 && pad_mode == PAD_ZERO && !getenv("VVB_NO_MARCH")) {
-            if (e->hop == 256) return launch_fwd_march<4>(e, a, out_kind, stream);
-            if (e->hop == 512) return launch_fwd_march<8>(e, a, out_kind, stream);
-            if (e->hop == 1024) return launch_fwd_march<16>(e, a, out_kind, stream);
+        if (pad_mode == PAD_ZERO && !getenv("VVB_NO_MARCH")) {
+            int r = -1;
+            if (e->nfft == 2048) r = launch_fwd_march<Cfg1024>(e, a, out_kind, stream);
+            else if (e->nfft == 4096) r = launch_fwd_march<Cfg2048>(e, a, out_kind, stream);
+            else if (e->nfft == 8192) r = launch_fwd_march<Cfg4096>(e, a, out_kind, stream);
+            if (r >= 0) return r;
         }
         switch (e->nfft / 2) {
         case 128: return launch_forward<Cfg128>(e, a, out_kind, stream);
@@ -418,31 +432,32 @@ template <bool OLA> static int dispatch_inverse(vvb_engine* e, const InvArgs& a,
     }
 }
 
-/* warp-marching ISTFT (fft_size 2048, hop = 64*S): register-resident overlap-add.
- * One CTA of W warps per SM; W trades warps in flight against registers per thread. */
-template <int S, int W> static int launch_march_w(vvb_engine* e, InvArgs a, long long batch, void* stream)
+/* team-marching ISTFT: register-resident overlap-add (see istft_march_kernel) */
+template <class C, int S> static int launch_inv_march_s(vvb_engine* e, InvArgs a, long long batch, void* stream)
 {
-    using C = Cfg1024;
+    constexpr int G = March<C>::G, MINB = March<C>::MINB;
     static int per_sm = -1;
-    auto kern = istft_march_kernel<C, S, W>;
-    const size_t smem = sizeof(float) * (2 * C::M + 2 * C::TW2 + 2 * W * (C::XBUF + C::M + 2));
-    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, 32 * W, smem);
+    auto kern = istft_march_kernel<C, S, G, MINB>;
+    const size_t smem = sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3) + 2 * G * (C::XBUF + C::M + 2));
+    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
     if (per_sm == 0) return fail(4, "istft_march_kernel", "does not fit on this device");
     if (batch > 0x7fffffffLL) return fail(2, "vvb_stft_inverse", "batch");
     a.num_items = (int)batch;                                   /* the kernel partitions batch*frames itself */
     const long long total = batch * a.frames;
-    const long long want = (total + 16 * W - 1) / (16 * W);     /* at least ~16 frames per warp */
-    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), 32 * W, smem, stream, a);
+    const long long want = (total + 16 * G - 1) / (16 * G);
+    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), C::T * G, smem, stream, a);
     return 0;
 }
-template <int S> static int launch_march(vvb_engine* e, const InvArgs& a, long long batch, void* stream)
+template <class C> static int launch_inv_march(vvb_engine* e, const InvArgs& a, long long batch, void* stream)
 {
-    static int w = -1;
-    if (w < 0) { const char* s = getenv("VVB_MARCH_W"); w = s ? atoi(s) : 8; }   /* 8 warps: 226 regs, no spills (12 warps spill and are 1.5x slower) */
-    /* registers are partitioned per SM sub-partition (16 K each): 8 warps = 2 per sub-partition may use
-     * 255 registers, 9..12 warps put 3 on one and cap at 168, which spills (measured 1.5x slower) */
-    if (w == 12) return launch_march_w<S, 12>(e, a, batch, stream);
-    return launch_march_w<S, 8>(e, a, batch, stream);
+    const size_t unit = 2 * (size_t)C::T;
+    if (e->hop % unit) return -1;
+    switch (e->hop / unit) {
+    case C::E / 8: return launch_inv_march_s<C, C::E / 8>(e, a, batch, stream);
+    case C::E / 4: return launch_inv_march_s<C, C::E / 4>(e, a, batch, stream);
+    case C::E / 2: return launch_inv_march_s<C, C::E / 2>(e, a, batch, stream);
+    default: return -1;
+    }
 }
 
 static int ensure_scratch(vvb_engine* e, size_t bytes)
@@ -494,10 +509,12 @@ extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t bat
         a.y = d_y; a.y_pitch = (long long)y_pitch; a.n_out = (long long)n_out;
         a.inv_norm = d_inv_norm; a.tables = e->d_tables;
         const bool y_aligned = ((uintptr_t)d_y % 8 == 0) && (y_pitch % 2 == 0);   /* 64-bit stores */
-        if (e->nfft == 2048 && y_aligned && !getenv("VVB_NO_MARCH")) {
-            if (e->hop == 256) return launch_march<4>(e, a, (long long)batch, stream);
-            if (e->hop == 512) return launch_march<8>(e, a, (long long)batch, stream);
-            if (e->hop == 1024) return launch_march<16>(e, a, (long long)batch, stream);
+        if (y_aligned && !getenv("VVB_NO_MARCH")) {
+            int r = -1;
+            if (e->nfft == 2048) r = launch_inv_march<Cfg1024>(e, a, (long long)batch, stream);
+            else if (e->nfft == 4096) r = launch_inv_march<Cfg2048>(e, a, (long long)batch, stream);
+            else if (e->nfft == 8192) r = launch_inv_march<Cfg4096>(e, a, (long long)batch, stream);
+            if (r >= 0) return r;
         }
         return dispatch_inverse<true>(e, a, (long long)batch, stream);
     }

@@ -232,43 +232,43 @@ VVB_DEV void split_and_store(const float2* xb, const float2* s_post, int t, void
     }
 }
 
-template <class C, int S, int W, int OUT>
-__global__ void __launch_bounds__(32 * W, 1) stft_march_kernel(const FwdArgs a)
+template <class C, int S, int G, int MINB, int OUT>
+__global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs a)
 {
-    static_assert(C::T == 32 && C::E == 32 && C::NP == 2, "one-warp teams only");
+    static_assert(C::T >= 32 && C::R1 == C::E && C::E % S == 0, "whole-warp teams, pass-1 radix == points per thread");
     using TB = Tables<C>;
-    constexpr int M = C::M, N = 2 * M, E = C::E, NB = 32 / S, HOP = 64 * S, HB = HOP / 2;   /* HB float2 per hop-block */
-    constexpr int RING = NB + 1;
+    constexpr int M = C::M, E = C::E, T = C::T;
+    constexpr int NB = E / S, HB = T * S, HOP = 2 * HB, RING = NB + 1;    /* HB float2 per hop-block */
 #ifdef VVB_EMU
     float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
 #else
     extern __shared__ __align__(16) float smem[];
 #endif
     float2* s_tw2 = reinterpret_cast<float2*>(smem);
-    float2* s_post = s_tw2 + C::TW2;
+    float2* s_tw3 = s_tw2 + C::TW2;
+    float2* s_post = s_tw3 + C::TW3;
     float2* s_xb = s_post + C::POST + 1;
-    float2* s_ring = s_xb + W * C::XBUF;                              /* W x RING x HB float2, 16-byte aligned */
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ring + W * RING * HB);
-    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * C::TW2);
-    copy_table(reinterpret_cast<float*>(s_post), a.tables + TB::POST, 2 * C::POST);
-    const int warp = threadIdx.x / 32, t = threadIdx.x % 32;
-    if (t == 0) mbar_init(&s_bar[warp], 1);
+    float2* s_ring = s_xb + G * C::XBUF;                              /* G x RING x HB float2, 16-byte aligned */
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ring + G * RING * HB);
+    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3 + C::POST));
+    const int team = threadIdx.x / T, t = threadIdx.x % T;
+    if (t == 0) mbar_init(&s_bar[team], 1);
     __syncthreads();
 
-    float2* xb = s_xb + warp * C::XBUF;
-    float2* ring = s_ring + warp * RING * HB;
-    unsigned long long* bar = &s_bar[warp];
+    float2* xb = s_xb + team * C::XBUF;
+    float2* ring = s_ring + team * RING * HB;
+    unsigned long long* bar = &s_bar[team];
     unsigned parity = 0;
 
-    float2 win[32];                                                   /* window of this thread's sample pairs */
+    float2 win[E];                                                    /* window of this thread's sample pairs */
 #pragma unroll
-    for (int r = 0; r < 32; ++r) win[r] = __ldg(reinterpret_cast<const float2*>(a.tables + TB::WIN) + t + 32 * r);
+    for (int r = 0; r < E; ++r) win[r] = __ldg(reinterpret_cast<const float2*>(a.tables + TB::WIN) + t + T * r);
 
     const int F = a.frames;
     const long long total = (long long)a.num_groups * F;              /* num_groups carries the batch */
-    const long long nwarps = (long long)gridDim.x * W;
-    const long long quota = (total + nwarps - 1) / nwarps;
-    long long g0 = ((long long)blockIdx.x * W + warp) * quota;
+    const long long nteams = (long long)gridDim.x * G;
+    const long long quota = (total + nteams - 1) / nteams;
+    long long g0 = ((long long)blockIdx.x * G + team) * quota;
     const long long g1 = min(total, g0 + quota);
 
     while (g0 < g1) {
@@ -294,15 +294,15 @@ __global__ void __launch_bounds__(32 * W, 1) stft_march_kernel(const FwdArgs a)
             }
 #pragma unroll
             for (int r = 0; r < S; ++r) {
-                const long long i0 = s0 + 2 * (t + 32 * r);
-                dst[t + 32 * r] = make_float2(i0 < a.n ? __ldg(xs + i0) : 0.f, i0 + 1 < a.n ? __ldg(xs + i0 + 1) : 0.f);
+                const long long i0 = s0 + 2 * (t + T * r);
+                dst[t + T * r] = make_float2(i0 < a.n ? __ldg(xs + i0) : 0.f, i0 + 1 < a.n ? __ldg(xs + i0 + 1) : 0.f);
             }
             return false;
         };
 
         /* prologue: the N/hop blocks of the first frame, one after another */
         for (int q = 0; q < NB; ++q) {
-            __syncwarp();
+            team_sync<T>(team);
             if (load_block(f_begin + q)) { mbar_wait(bar, parity); parity ^= 1; }
         }
         bool pending = false;
@@ -310,21 +310,21 @@ __global__ void __launch_bounds__(32 * W, 1) stft_march_kernel(const FwdArgs a)
 #pragma unroll 1
         for (int frame = f_begin; frame < f_end; ++frame) {
             if (pending) { mbar_wait(bar, parity); parity ^= 1; }      /* block frame+NB-1 has landed */
-            __syncwarp();                                              /* ... and manual fills are visible */
+            team_sync<T>(team);                                        /* ... and manual fills are visible */
             /* fetch the next frame's new block now: it goes to the slot of block frame-1, which nobody
              * reads any more, and has this whole frame's FFT to arrive */
             pending = (frame + 1 < f_end) ? load_block(frame + NB) : false;
             float2 v[E];
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const float2 s = ring[((frame + r / S) % RING) * HB + t + 32 * (r % S)];
+            for (int r = 0; r < E; ++r) {
+                const float2 s = ring[((frame + r / S) % RING) * HB + t + T * (r % S)];
                 v[r] = make_float2(s.x * win[r].x, s.y * win[r].y);
             }
-            team_fft<C>(v, xb, s_tw2, nullptr, t, warp);
+            team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
             team_store_natural<C>(v, xb, t);
-            __syncwarp();
+            team_sync<T>(team);
             split_and_store<C, OUT>(xb, s_post, t, a.out, ((long long)b * F + frame) * a.out_pitch);
-            __syncwarp();                                              /* xb is reused by the next frame */
+            team_sync<T>(team);                                        /* xb is reused by the next frame */
         }
     }
 }
@@ -503,18 +503,18 @@ __global__ void __launch_bounds__(C::T* G) stft_inverse_kernel(const InvArgs a)
  * ascending order exactly like the reference accumulates out_add (src/spectral/stft.c:103-108).
  * Work is split into equal ranges of the flattened (signal, frame) sequence, one range per
  * warp; a range that starts mid-signal first re-synthesises the 32/S - 1 frames before it. */
-/* merge step of the marching ISTFT for one bin k = t + 32 R of this thread (R compile time):
- *     Z[k] = (X[k] + conj X[M-k])/2 + (j/2) conj(W_N^k) (X[k] - conj X[M-k]),  W_N^k = W_N^t * W_64^R
- * read from the staged half spectrum in xb, result stored re/im swapped for the forward-FFT trick */
+/* merge step of the marching ISTFT for one bin k = t + T*R of this thread (R compile time):
+ *     Z[k] = (X[k] + conj X[M-k])/2 + (j/2) conj(W_N^k) (X[k] - conj X[M-k]),  W_N^k = W_N^t * W_{2E}^R
+ * read from the staged half spectrum, result stored re/im swapped for the forward-FFT trick */
 template <class C, int R> VVB_DEV void march_merge_one(float2 (&v)[C::E], const float2* st, int t, float2 hw_t)
 {
-    constexpr int M = C::M;
-    float2 x = st[t + 32 * R];                                        /* st: staged X[0..M], natural order */
-    float2 y = st[M - t - 32 * R];
+    constexpr int M = C::M, T = C::T;
+    float2 x = st[t + T * R];                                         /* st: staged X[0..M], natural order */
+    float2 y = st[M - t - T * R];
     if constexpr (R == 0) {
         if (t == 0) { x.y = 0.f; y.y = 0.f; }                          /* Re(IDFT): DC / Nyquist imag drop out */
     }
-    constexpr float cr = TwC<64, R>::c, sr = TwC<64, R>::s;
+    constexpr float cr = TwC<2 * C::E, R>::c, sr = TwC<2 * C::E, R>::s;
     const float hc = hw_t.x * cr - hw_t.y * sr, hs = hw_t.y * cr + hw_t.x * sr;   /* (cos,sin)(2 pi k/N)/2 */
     const float sre = x.x + y.x, sim = x.y - y.y;                     /* x + conj(y) */
     const float dre = x.x - y.x, dim = x.y + y.y;                     /* x - conj(y) */
@@ -526,12 +526,14 @@ template <class C, int... Rs> VVB_DEV void march_merge(float2 (&v)[C::E], const 
     (march_merge_one<C, Rs>(v, st, t, hw_t), ...);
 }
 
-template <class C, int S, int W>
-__global__ void __launch_bounds__(32 * W, 1) istft_march_kernel(const InvArgs a)
+template <class C, int S, int G, int MINB>
+__global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArgs a)
 {
-    static_assert(C::T == 32 && C::E == 32 && C::NP == 2, "one-warp teams only");
+    static_assert(C::T >= 32 && C::R1 == C::E && C::E % S == 0, "whole-warp teams, pass-1 radix == points per thread");
     using TB = Tables<C>;
-    constexpr int M = C::M, N = 2 * M, E = C::E, PERIOD = 32 / S, HOP = 64 * S, EDGE = N - HOP;
+    using L = LastPass<C>;
+    constexpr int M = C::M, N = 2 * M, E = C::E, T = C::T;
+    constexpr int PERIOD = E / S, HOP = 2 * T * S, EDGE = N - HOP;    /* PERIOD frames overlap one sample */
     constexpr int STG = M + 2;                                        /* staged half spectrum X[0..M] (+1 pad) */
 #ifdef VVB_EMU
     float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
@@ -540,28 +542,29 @@ __global__ void __launch_bounds__(32 * W, 1) istft_march_kernel(const InvArgs a)
 #endif
     float* s_wsyn = smem;
     float2* s_tw2 = reinterpret_cast<float2*>(s_wsyn + N);
-    float2* s_xb = s_tw2 + C::TW2;
-    float2* s_stage = s_xb + W * C::XBUF;
+    float2* s_tw3 = s_tw2 + C::TW2;
+    float2* s_xb = s_tw3 + C::TW3;
+    float2* s_stage = s_xb + G * C::XBUF;
     /* normalised synthesis: the steady-state 1/sum(w^2) is already folded into the window table, so the
-     * main path has no per-sample table load or multiply; only the first/last 32/S-1 hop-blocks of a
+     * main path has no per-sample table load or multiply; only the first/last PERIOD-1 hop-blocks of a
      * signal (fewer frames overlap there) are rescaled, below */
     const bool normalise = a.inv_norm != nullptr;
     copy_table(s_wsyn, a.tables + (normalise ? TB::WSYN_NORM : TB::WSYN), N);
-    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * C::TW2);
+    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3));
     __syncthreads();
 
-    const int warp = threadIdx.x / 32, t = threadIdx.x % 32;
-    float2* xb = s_xb + warp * C::XBUF;                               /* FFT exchange buffer of this warp */
-    float2* stage = s_stage + warp * STG;                             /* next frame's spectrum lands here */
+    const int team = threadIdx.x / T, t = threadIdx.x % T;
+    float2* xb = s_xb + team * C::XBUF;                               /* FFT exchange buffer of this team */
+    float2* stage = s_stage + team * STG;                             /* next frame's spectrum lands here */
     const float2* wsyn2 = reinterpret_cast<const float2*>(s_wsyn);
-    /* split-step twiddle of this lane: (cos, sin)(2 pi t / N) / 2; the bins k = t + 32 r of a thread
-     * differ from it by the compile-time rotation 2 pi r / 64 */
-    const float2 hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);
+    /* split-step twiddle of this thread: (cos, sin)(2 pi t / N) / 2; its bins k = t + T r differ from it
+     * by the compile-time rotation 2 pi r / (2E) */
+    const float2 hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);   /* t < T <= M/2 */
     const int F = a.frames;
     const long long total = (long long)a.num_items * F;               /* num_items carries the batch */
-    const long long nwarps = (long long)gridDim.x * W;
-    const long long quota = (total + nwarps - 1) / nwarps;
-    long long g0 = ((long long)blockIdx.x * W + warp) * quota;
+    const long long nteams = (long long)gridDim.x * G;
+    const long long quota = (total + nteams - 1) / nteams;
+    long long g0 = ((long long)blockIdx.x * G + team) * quota;
     const long long g1 = min(total, g0 + quota);
 
     while (g0 < g1) {
@@ -574,76 +577,80 @@ __global__ void __launch_bounds__(32 * W, 1) istft_march_kernel(const InvArgs a)
         float* yb = a.y + (long long)b * a.y_pitch;
         g0 += f_end - f_begin;
 
-        /* asynchronous copy (LDGSTS) of one frame's half spectrum into the warp's staging buffer; issued
+        /* asynchronous copy (LDGSTS) of one frame's half spectrum into the team's staging buffer; issued
          * right after the previous frame's merge has consumed the buffer, so it is in flight for a whole
          * frame time */
         auto prefetch = [&](int frame) {
             if (frame < f_end) {
                 const float2* X = specb + (long long)frame * a.spec_pitch;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) cp_async8(&stage[t + 32 * r], X + t + 32 * r);
+                for (int r = 0; r < E; ++r) cp_async8(&stage[t + T * r], X + t + T * r);
                 if (t == 0) cp_async8(&stage[M], X + M);
             }
             cp_async_commit();
         };
 
-        float2 acc[32];
+        float2 acc[E];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < E; ++i) acc[i] = make_float2(0.f, 0.f);
         prefetch(fr0);
 
 #pragma unroll 1
         for (int frame = fr0; frame < emit_end; ++frame) {
-            if (frame < f_end) {                                       /* warp-uniform */
+            if (frame < f_end) {                                       /* team-uniform */
                 float2 v[E];
                 cp_async_wait_all();
-                __syncwarp();
+                team_sync<T>(team);
                 /* merge straight into the pass-1 registers (see march_merge_one) */
-                march_merge<C>(v, stage, t, hw_t, typename make_iseq<32>::type{});
-                __syncwarp();                                          /* all reads of the staged X are done */
+                march_merge<C>(v, stage, t, hw_t, typename make_iseq<E>::type{});
+                team_sync<T>(team);                                    /* all reads of the staged X are done */
                 prefetch(frame + 1);
-                team_fft<C>(v, xb, s_tw2, nullptr, t, warp);
+                team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+                /* v[q*RL + r] is sample pair i = t + T*(q + NQ*r): accumulate into that slot */
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    const float2 z = v[r], w = wsyn2[t + 32 * r];
-                    acc[r].x = fmaf(z.y, w.x, acc[r].x);              /* Re z * w  (z is stored swapped) */
-                    acc[r].y = fmaf(z.x, w.y, acc[r].y);
-                }
+                for (int q = 0; q < L::NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < L::R; ++r) {
+                        const int sl = q + L::NQ * r;
+                        const float2 z = v[q * L::R + r], w = wsyn2[t + T * sl];
+                        acc[sl].x = fmaf(z.y, w.x, acc[sl].x);        /* Re z * w  (z is stored swapped) */
+                        acc[sl].y = fmaf(z.x, w.y, acc[sl].y);
+                    }
             }
             if (frame >= f_begin) {
                 const long long base = (long long)frame * HOP;
                 if (normalise && (frame < PERIOD - 1 || frame >= F)) {
-                    /* edge block: fewer than 32/S frames overlap; undo the folded steady-state factor and
+                    /* edge block: fewer than PERIOD frames overlap; undo the folded steady-state factor and
                      * apply this block's own 1/sum(w^2) (head or tail table of InvArgs::inv_norm) */
                     const float* edge = (frame >= F) ? a.inv_norm + EDGE + HOP + (long long)(frame - F) * HOP
                                                      : a.inv_norm + (long long)frame * HOP;
                     const float* mid = a.tables + TB::MIDNORM;
 #pragma unroll
                     for (int r = 0; r < S; ++r) {
-                        const int c = 2 * (t + 32 * r);
+                        const int c = 2 * (t + T * r);
                         acc[r].x *= __ldg(edge + c) * __ldg(mid + c);
                         acc[r].y *= __ldg(edge + c + 1) * __ldg(mid + c + 1);
                     }
                 }
 #pragma unroll
                 for (int r = 0; r < S; ++r) {
-                    const long long tt = base + 2 * (t + 32 * r);
+                    const long long tt = base + 2 * (t + T * r);
                     if (tt + 1 < a.n_out) *reinterpret_cast<float2*>(yb + tt) = acc[r];
                     else if (tt < a.n_out) yb[tt] = acc[r].x;
                 }
             }
-            /* advance one hop: slot r now means what slot r+S meant (register moves; a 32/S-fold
-             * unrolled frame loop would not fit the instruction cache) */
+            /* advance one hop: slot r now means what slot r+S meant (register moves; an unrolled ring
+             * of PERIOD frame bodies would not fit the instruction cache) */
 #pragma unroll
-            for (int r = 0; r < 32 - S; ++r) acc[r] = acc[r + S];
+            for (int r = 0; r < E - S; ++r) acc[r] = acc[r + S];
 #pragma unroll
-            for (int r = 32 - S; r < 32; ++r) acc[r] = make_float2(0.f, 0.f);
+            for (int r = E - S; r < E; ++r) acc[r] = make_float2(0.f, 0.f);
         }
         cp_async_wait_all();                                           /* nothing in flight across pieces */
-        __syncwarp();
+        team_sync<T>(team);
         if (f_end == F) {                                              /* nothing covers [cov, n_out): zeros */
             const long long cov = (long long)(F - 1) * HOP + N;
-            for (long long tt = cov + t; tt < a.n_out; tt += 32) yb[tt] = 0.f;
+            for (long long tt = cov + t; tt < a.n_out; tt += T) yb[tt] = 0.f;
         }
     }
 }
