@@ -182,7 +182,9 @@ template <class C> static void build_tables(std::vector<float>& blob, const floa
 /* the kernel configurations: M complex points = fft_size/2 for the real transforms */
 using Cfg128 = Cfg<128, 16, 16, 8>;
 using Cfg256 = Cfg<256, 16, 16, 16>;
+using Cfg256m = Cfg<256, 8, 8, 8, 4>;       /* T = 32: whole-warp team for the marching ISTFT (own table blob) */
 using Cfg512 = Cfg<512, 32, 32, 16>;
+using Cfg512m = Cfg<512, 16, 16, 16, 2>;    /* T = 32 */
 using Cfg1024 = Cfg<1024, 32, 32, 32>;
 using Cfg2048 = Cfg<2048, 16, 16, 16, 8>;
 using Cfg4096 = Cfg<4096, 16, 16, 16, 16>;
@@ -199,6 +201,7 @@ struct vvb_engine {
     bool fast = false;
     int sms = 0;
     float* d_tables = nullptr;       /* fast: Tables<C> blob */
+    float* d_tables_m = nullptr;     /* fft_size 512 / 1024: blob of the whole-warp config used by the marching ISTFT */
     float* d_win = nullptr;          /* direct: window */
     float2* d_wtab = nullptr;        /* direct: (cos,-sin)(2 pi j/n) */
     float* d_scratch = nullptr;      /* direct: synthesis frames */
@@ -248,6 +251,10 @@ extern "C" int vvb_engine_create(size_t nfft, size_t hop, const float* window, v
         default: build_tables<Cfg4096>(blob, window, hop); break;
         }
         st = upload(&e->d_tables, blob);
+        if (!st && (nfft == 512 || nfft == 1024)) {
+            if (nfft == 512) build_tables<Cfg256m>(blob, window, hop); else build_tables<Cfg512m>(blob, window, hop);
+            st = upload(&e->d_tables_m, blob);
+        }
     } else {
         std::vector<float> w(window, window + nfft), t;
         make_wtab(t, nfft);
@@ -262,7 +269,7 @@ extern "C" int vvb_engine_create(size_t nfft, size_t hop, const float* window, v
 extern "C" void vvb_engine_destroy(vvb_engine* e)
 {
     if (!e) return;
-    vvb_free(e->d_tables); vvb_free(e->d_win); vvb_free(e->d_wtab); vvb_free(e->d_scratch);
+    vvb_free(e->d_tables); vvb_free(e->d_tables_m); vvb_free(e->d_win); vvb_free(e->d_wtab); vvb_free(e->d_scratch);
     delete e;
 }
 
@@ -306,6 +313,8 @@ template <class C> static int launch_forward(vvb_engine* e, const FwdArgs& a, in
  * G teams per CTA and CTAs per SM chosen per configuration: registers are partitioned per SM sub-partition
  * (16 K each), so 8 warps per SM may use 255 registers per thread but 9..12 warps cap at 168. */
 template <class C> struct March;
+template <> struct March<Cfg256m> { static constexpr int G = 8, MINB = 3; };    /* 256 thr, <= 80 regs */
+template <> struct March<Cfg512m> { static constexpr int G = 8, MINB = 2; };    /* 256 thr, <= 128 regs */
 template <> struct March<Cfg1024> { static constexpr int G = 8, MINB = 1; };   /* 256 thr, 232 regs, 1 CTA/SM */
 template <> struct March<Cfg2048> { static constexpr int G = 2, MINB = 2; };   /* 256 thr, 2 CTAs/SM */
 template <> struct March<Cfg4096> { static constexpr int G = 2, MINB = 1; };   /* 512 thr, 1 CTA/SM */
@@ -360,6 +369,7 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
         a.num_groups = (int)batch; a.groups_per_signal = 0;
         if (pad_mode == PAD_ZERO && !getenv("VVB_NO_MARCH")) {
             int r = -1;
+            /* (at fft_size 512 / 1024 the 2-pass generic forward kernel is faster than a 3-pass marching one) */
             if (e->nfft == 2048) r = launch_fwd_march<Cfg1024>(e, a, out_kind, stream);
             else if (e->nfft == 4096) r = launch_fwd_march<Cfg2048>(e, a, out_kind, stream);
             else if (e->nfft == 8192) r = launch_fwd_march<Cfg4096>(e, a, out_kind, stream);
@@ -511,7 +521,11 @@ extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t bat
         const bool y_aligned = ((uintptr_t)d_y % 8 == 0) && (y_pitch % 2 == 0);   /* 64-bit stores */
         if (y_aligned && !getenv("VVB_NO_MARCH")) {
             int r = -1;
-            if (e->nfft == 2048) r = launch_inv_march<Cfg1024>(e, a, (long long)batch, stream);
+            InvArgs am = a;
+            am.tables = e->d_tables_m;
+            if (e->nfft == 512) r = launch_inv_march<Cfg256m>(e, am, (long long)batch, stream);
+            else if (e->nfft == 1024) r = launch_inv_march<Cfg512m>(e, am, (long long)batch, stream);
+            else if (e->nfft == 2048) r = launch_inv_march<Cfg1024>(e, a, (long long)batch, stream);
             else if (e->nfft == 4096) r = launch_inv_march<Cfg2048>(e, a, (long long)batch, stream);
             else if (e->nfft == 8192) r = launch_inv_march<Cfg4096>(e, a, (long long)batch, stream);
             if (r >= 0) return r;
