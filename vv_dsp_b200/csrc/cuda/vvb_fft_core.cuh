@@ -84,9 +84,21 @@ template <int N, int I> struct TwC {
 };
 
 /* ------------------------------------------------------------------ complex helpers */
-VVB_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-VVB_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-VVB_DEV float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+/* Complex numbers live in aligned register pairs and all arithmetic uses Blackwell's packed FP32
+ * instructions (FFMA2 / FADD2 / FMUL2: two IEEE fp32 operations per issue slot).  The lane swaps,
+ * scalar broadcasts and per-half negations written below as make_float2(...) fold into the
+ * instructions' operand selectors (.LO_HI, .F32, -, .NP) -- verified in SASS -- so a complex add is
+ * one instruction and a complex multiply two. */
+VVB_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+VVB_DEV float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+VVB_DEV float2 cmul(float2 a, float2 w)            /* a * w */
+{
+    const float2 t = __fmul2_rn(make_float2(a.y, a.x), make_float2(w.y, w.y));       /* (a.y w.y, a.x w.y) */
+    return __ffma2_rn(a, make_float2(w.x, w.x), make_float2(-t.x, t.y));
+}
+VVB_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+VVB_DEV float2 cswap(float2 a) { return make_float2(a.y, a.x); }
+VVB_DEV float2 splat(float s) { return make_float2(s, s); }
 
 /* x * exp(-2*pi*i*I/N), trivial factors resolved at compile time */
 template <int N, int I> VVB_DEV float2 mul_w(float2 x)
@@ -112,11 +124,11 @@ template <int N, int I> VVB_DEV float2 mul_w(float2 x)
 /* ------------------------------------------- in-register DFT, radix-2 DIT, FMA-folded */
 /* Decimation in time: X[k] = E[k] + W^k O[k], X[k+N/2] = E[k] - W^k O[k].  With the twiddle a
  * compile-time constant W = c - i s, the product is folded into the butterfly so a general
- * butterfly is 6 FMAs instead of 4 mul/fma + 4 add:
- *     |c| >= |s|:  b' = b * (1 - i s/c)       (2 FMA)    X = a +- c b'   (4 FMA)
- *     |c| <  |s|:  b' = b * (c/s - i)         (2 FMA)    X = a +- s b'   (4 FMA)
- * W = 1 and W = -i need 4 adds.  A 32-point DFT is 388 FP instructions (456 in the
- * decimation-in-frequency form this replaced).  Input and output are in natural order; the
+ * butterfly is 6 FMAs = 3 packed FFMA2 instead of 4 mul/fma + 4 add:
+ *     |c| >= |s|:  b' = b * (1 - i s/c)       (1 FFMA2)    X = a +- c b'   (2 FFMA2)
+ *     |c| <  |s|:  b' = b * (c/s - i)         (1 FFMA2)    X = a +- s b'   (2 FFMA2)
+ * W = 1 and W = -i need 2 FADD2.  A 32-point DFT is 194 packed instructions (388 scalar ones in
+ * the same DIT form, 456 in the decimation-in-frequency form that came first).  Input and output are in natural order; the
  * bit reversal of the recursion is only a renaming of registers. */
 template <int N, int K> struct DitTw {       /* all evaluated by the host compiler: plain immediates in SASS */
     static constexpr double cd = ct_cos2pi(K, N), sd = ct_sin2pi(K, N);
@@ -129,22 +141,22 @@ template <int N, int K> struct DitTw {       /* all evaluated by the host compil
 template <int N, int K> VVB_DEV void dit_combine(float2 a, float2 b, float2& lo, float2& hi)
 {
     if constexpr (K == 0) {
-        lo = cadd(a, b); hi = csub(a, b);
+        lo = cadd(a, b); hi = csub(a, b);                                       /* 2 x FADD2 */
     } else if constexpr (4 * K == N) {            /* W = -i: W b = (b.y, -b.x) */
-        lo = make_float2(a.x + b.y, a.y - b.x);
-        hi = make_float2(a.x - b.y, a.y + b.x);
+        lo = __fadd2_rn(a, make_float2(b.y, -b.x));
+        hi = __fadd2_rn(a, make_float2(-b.y, b.x));
     } else {
-        using TW = DitTw<N, K>;
+        using TW = DitTw<N, K>;                   /* 3 x FFMA2 */
         if constexpr (TW::cos_form) {
             constexpr float tn = TW::tn, c = TW::c;
-            const float pr = fmaf(tn, b.y, b.x), pi = fmaf(-tn, b.x, b.y);     /* b (1 - i tn) */
-            lo = make_float2(fmaf(c, pr, a.x), fmaf(c, pi, a.y));
-            hi = make_float2(fmaf(-c, pr, a.x), fmaf(-c, pi, a.y));
+            const float2 p = __ffma2_rn(make_float2(tn, -tn), make_float2(b.y, b.x), b);     /* b (1 - i tn) */
+            lo = __ffma2_rn(splat(c), p, a);
+            hi = __ffma2_rn(splat(-c), p, a);
         } else {
             constexpr float ct = TW::ct, sn = TW::sn;
-            const float pr = fmaf(ct, b.x, b.y), pi = fmaf(ct, b.y, -b.x);     /* b (ct - i) */
-            lo = make_float2(fmaf(sn, pr, a.x), fmaf(sn, pi, a.y));
-            hi = make_float2(fmaf(-sn, pr, a.x), fmaf(-sn, pi, a.y));
+            const float2 p = __ffma2_rn(splat(ct), b, make_float2(b.y, -b.x));               /* b (ct - i) */
+            lo = __ffma2_rn(splat(sn), p, a);
+            hi = __ffma2_rn(splat(-sn), p, a);
         }
     }
 }
@@ -350,6 +362,50 @@ VVB_DEV void fence_proxy_async()
 #ifndef VVB_EMU
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
+}
+
+/* ---- inter-pass twiddles W_M^{r*t} computed instead of loaded (one-warp 32 x 32 transforms).
+ * The 31 twiddles of a thread are powers of W_M^t; five of them (r = 1, 2, 4, 8, 16) are kept in
+ * registers and every other power is the product of the bases of its set bits (at most 4 complex
+ * multiplies deep, so the rounding error stays ~2e-7).  With packed FP32 math this costs fewer issue
+ * slots than it saves: 31 LDS.64 (62 shared-memory wavefronts) per transform disappear, and the
+ * kernels are bound by exactly those wavefronts. */
+struct TwBase { float2 w[5]; };
+
+template <int R, int BIT = 0, bool STARTED = false> VVB_DEV float2 tw_power(const TwBase& b, float2 acc = make_float2(1.f, 0.f))
+{
+    if constexpr ((R >> BIT) == 0) {
+        return acc;
+    } else if constexpr (((R >> BIT) & 1) == 0) {
+        return tw_power<R, BIT + 1, STARTED>(b, acc);
+    } else if constexpr (!STARTED) {
+        return tw_power<R, BIT + 1, true>(b, b.w[BIT]);
+    } else {
+        return tw_power<R, BIT + 1, true>(b, cmul(acc, b.w[BIT]));
+    }
+}
+template <int... Rs> VVB_DEV void apply_tw_powers(float2* v, const TwBase& b, iseq<Rs...>)
+{
+    ((v[Rs + 1] = cmul(v[Rs + 1], tw_power<Rs + 1>(b))), ...);
+}
+
+/* team_fft for Cfg<1024,32,32,32> with register twiddles; tw2 is only read once, for the bases */
+template <class C> VVB_DEV TwBase load_tw_base(const float2* tw2_global, int t)
+{
+    static_assert(C::T == 32 && C::R1 == 32 && C::R2 == 32 && C::NP == 2, "32 x 32 one-warp transform");
+    TwBase b;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) b.w[j] = __ldg(tw2_global + ((1 << j) - 1) * 32 + t);   /* r = 2^j, jm = t */
+    return b;
+}
+template <class C> VVB_DEV void team_fft_regtw(float2 (&v)[C::E], float2* xb, const TwBase& b, int t, int team)
+{
+    stockham_pass<C, 32, 1, true, false>(v, xb, nullptr, t, team);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) v[r] = xb[C::pad(t + r * 32)];
+    team_sync<C::T>(team);
+    apply_tw_powers(v, b, typename make_iseq<31>::type{});
+    fft_reg<32, 0>(v);
 }
 
 template <class C> struct LastPass {

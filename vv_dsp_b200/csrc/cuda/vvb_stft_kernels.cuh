@@ -220,15 +220,60 @@ VVB_DEV void split_and_store(const float2* xb, const float2* s_post, int t, void
         const float2 A = xb[C::pad(k)];
         const float2 Bc = xb[C::pad((M - k) & (M - 1))];
         const float2 hw = s_post[k];                                  /* (cos, sin)/2 */
-        const float sr = A.x + Bc.x, si = A.y - Bc.y;                 /* A + conj(Bc) */
-        const float dr = A.x - Bc.x, di = A.y + Bc.y;                 /* A - conj(Bc) */
-        const float gr = hw.y * dr - hw.x * di, gi = hw.y * di + hw.x * dr;
-        emit(k, 0.5f * sr - gr, 0.5f * si - gi);                     /* X[k]   */
-        emit(M - k, 0.5f * sr + gr, -(0.5f * si + gi));              /* X[M-k] */
+        const float2 sm = __fadd2_rn(A, make_float2(Bc.x, -Bc.y));    /* A + conj(Bc) */
+        const float2 df = __fadd2_rn(A, make_float2(-Bc.x, Bc.y));    /* A - conj(Bc) */
+        const float2 g = cmul(df, make_float2(hw.y, hw.x));           /* (sin + j cos)/2 * df */
+        const float2 x0 = __ffma2_rn(splat(0.5f), sm, make_float2(-g.x, -g.y));              /* X[k] = sm/2 - g */
+        const float2 x1 = __ffma2_rn(make_float2(0.5f, -0.5f), sm, make_float2(g.x, -g.y));  /* X[M-k] = conj(sm/2 + g) */
+        emit(k, x0.x, x0.y);
+        emit(M - k, x1.x, x1.y);
     }
     if (t == 0) {                                                     /* k = M/2: X = conj(Z[M/2]) */
         const float2 A = xb[C::pad(M / 2)];
         emit(M / 2, A.x, -A.y);
+    }
+}
+
+/* split step with the twiddle of bin k = t + T*i formed as (per-thread value) x (compile-time rotation
+ * by 2 pi i T / N) instead of loaded from the table: 16 LDS.64 fewer per frame */
+template <class C, int OUT, int I> VVB_DEV void split_pair_rot(const float2* xb, float2 hw_t, int t, void* out, long long row)
+{
+    constexpr int M = C::M, T = C::T;
+    const int k = t + T * I;
+    const float2 A = xb[C::pad(k)];
+    const float2 Bc = xb[C::pad((M - k) & (M - 1))];
+    constexpr float cr = TwC<2 * C::E, I>::c, sr = TwC<2 * C::E, I>::s;
+    const float2 hw = cmul(hw_t, make_float2(cr, sr));
+    const float2 sm = __fadd2_rn(A, make_float2(Bc.x, -Bc.y));
+    const float2 df = __fadd2_rn(A, make_float2(-Bc.x, Bc.y));
+    const float2 g = cmul(df, make_float2(hw.y, hw.x));
+    const float2 x0 = __ffma2_rn(splat(0.5f), sm, make_float2(-g.x, -g.y));
+    const float2 x1 = __ffma2_rn(make_float2(0.5f, -0.5f), sm, make_float2(g.x, -g.y));
+    if constexpr (OUT == OUT_COMPLEX) {
+        reinterpret_cast<float2*>(out)[row + k] = x0;
+        reinterpret_cast<float2*>(out)[row + M - k] = x1;
+    } else if constexpr (OUT == OUT_POWER) {
+        reinterpret_cast<float*>(out)[row + k] = x0.x * x0.x + x0.y * x0.y;
+        reinterpret_cast<float*>(out)[row + M - k] = x1.x * x1.x + x1.y * x1.y;
+    } else {
+        reinterpret_cast<float*>(out)[row + k] = sqrtf(x0.x * x0.x + x0.y * x0.y);
+        reinterpret_cast<float*>(out)[row + M - k] = sqrtf(x1.x * x1.x + x1.y * x1.y);
+    }
+}
+template <class C, int OUT, int... Is> VVB_DEV void split_pairs_rot(const float2* xb, float2 hw_t, int t, void* out, long long row, iseq<Is...>)
+{
+    (split_pair_rot<C, OUT, Is>(xb, hw_t, t, out, row), ...);
+}
+template <class C, int OUT>
+VVB_DEV void split_and_store_rot(const float2* xb, float2 hw_t, int t, void* out, long long row)
+{
+    constexpr int M = C::M;
+    split_pairs_rot<C, OUT>(xb, hw_t, t, out, row, typename make_iseq<C::E / 2>::type{});
+    if (t == 0) {                                                     /* k = M/2: X = conj(Z[M/2]) */
+        const float2 A = xb[C::pad(M / 2)];
+        if constexpr (OUT == OUT_COMPLEX) reinterpret_cast<float2*>(out)[row + M / 2] = make_float2(A.x, -A.y);
+        else if constexpr (OUT == OUT_POWER) reinterpret_cast<float*>(out)[row + M / 2] = A.x * A.x + A.y * A.y;
+        else reinterpret_cast<float*>(out)[row + M / 2] = sqrtf(A.x * A.x + A.y * A.y);
     }
 }
 
@@ -263,6 +308,13 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
     float2 win[E];                                                    /* window of this thread's sample pairs */
 #pragma unroll
     for (int r = 0; r < E; ++r) win[r] = __ldg(reinterpret_cast<const float2*>(a.tables + TB::WIN) + t + T * r);
+    constexpr bool REGTW = (C::T == 32 && C::NP == 2 && C::R1 == 32 && C::R2 == 32);
+    TwBase twb;
+    float2 hw_t = make_float2(0.f, 0.f);
+    if constexpr (REGTW) {
+        twb = load_tw_base<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);
+        hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);   /* (cos, sin)(2 pi t/N)/2 */
+    }
 
     const int F = a.frames;
     const long long total = (long long)a.num_groups * F;              /* num_groups carries the batch */
@@ -317,13 +369,14 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
             float2 v[E];
 #pragma unroll
             for (int r = 0; r < E; ++r) {
-                const float2 s = ring[((frame + r / S) % RING) * HB + t + T * (r % S)];
-                v[r] = make_float2(s.x * win[r].x, s.y * win[r].y);
+                v[r] = __fmul2_rn(ring[((frame + r / S) % RING) * HB + t + T * (r % S)], win[r]);
             }
-            team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+            if constexpr (REGTW) team_fft_regtw<C>(v, xb, twb, t, team);
+            else team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
             team_store_natural<C>(v, xb, t);
             team_sync<T>(team);
-            split_and_store<C, OUT>(xb, s_post, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+            if constexpr (REGTW) split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+            else split_and_store<C, OUT>(xb, s_post, t, a.out, ((long long)b * F + frame) * a.out_pitch);
             team_sync<T>(team);                                        /* xb is reused by the next frame */
         }
     }
@@ -515,11 +568,11 @@ template <class C, int R> VVB_DEV void march_merge_one(float2 (&v)[C::E], const 
         if (t == 0) { x.y = 0.f; y.y = 0.f; }                          /* Re(IDFT): DC / Nyquist imag drop out */
     }
     constexpr float cr = TwC<2 * C::E, R>::c, sr = TwC<2 * C::E, R>::s;
-    const float hc = hw_t.x * cr - hw_t.y * sr, hs = hw_t.y * cr + hw_t.x * sr;   /* (cos,sin)(2 pi k/N)/2 */
-    const float sre = x.x + y.x, sim = x.y - y.y;                     /* x + conj(y) */
-    const float dre = x.x - y.x, dim = x.y + y.y;                     /* x - conj(y) */
-    const float ur = -hs * dre - hc * dim, ui = -hs * dim + hc * dre;
-    v[R] = make_float2(0.5f * sim + ui, 0.5f * sre + ur);             /* (Im Z, Re Z) */
+    const float2 h = cmul(hw_t, make_float2(cr, sr));                 /* (cos, sin)(2 pi k/N)/2 = hw_t rotated */
+    const float2 sm = __fadd2_rn(x, make_float2(y.x, -y.y));          /* x + conj(y) */
+    const float2 df = __fadd2_rn(x, make_float2(-y.x, y.y));          /* x - conj(y) */
+    const float2 u = cmul(df, make_float2(-h.y, h.x));                /* (j/2) conj(W_N^k) * df */
+    v[R] = __ffma2_rn(splat(0.5f), make_float2(sm.y, sm.x), make_float2(u.y, u.x));   /* (Im Z, Re Z) */
 }
 template <class C, int... Rs> VVB_DEV void march_merge(float2 (&v)[C::E], const float2* st, int t, float2 hw_t, iseq<Rs...>)
 {
@@ -560,6 +613,11 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
     /* split-step twiddle of this thread: (cos, sin)(2 pi t / N) / 2; its bins k = t + T r differ from it
      * by the compile-time rotation 2 pi r / (2E) */
     const float2 hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);   /* t < T <= M/2 */
+    /* (computed inter-pass twiddles, as in the forward kernel, push this kernel from 242 to 255 registers
+     * and into spills -- 2.25 vs 2.12 ms measured -- because of the 64-register accumulator: tables here) */
+    constexpr bool REGTW = false;
+    TwBase twb;
+    if constexpr (REGTW) twb = load_tw_base<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);
     const int F = a.frames;
     const long long total = (long long)a.num_items * F;               /* num_items carries the batch */
     const long long nteams = (long long)gridDim.x * G;
@@ -605,16 +663,16 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
                 march_merge<C>(v, stage, t, hw_t, typename make_iseq<E>::type{});
                 team_sync<T>(team);                                    /* all reads of the staged X are done */
                 prefetch(frame + 1);
-                team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+                if constexpr (REGTW) team_fft_regtw<C>(v, xb, twb, t, team);
+                else team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
                 /* v[q*RL + r] is sample pair i = t + T*(q + NQ*r): accumulate into that slot */
 #pragma unroll
                 for (int q = 0; q < L::NQ; ++q)
 #pragma unroll
                     for (int r = 0; r < L::R; ++r) {
                         const int sl = q + L::NQ * r;
-                        const float2 z = v[q * L::R + r], w = wsyn2[t + T * sl];
-                        acc[sl].x = fmaf(z.y, w.x, acc[sl].x);        /* Re z * w  (z is stored swapped) */
-                        acc[sl].y = fmaf(z.x, w.y, acc[sl].y);
+                        const float2 z = v[q * L::R + r];
+                        acc[sl] = __ffma2_rn(make_float2(z.y, z.x), wsyn2[t + T * sl], acc[sl]);   /* z is stored swapped */
                     }
             }
             if (frame >= f_begin) {
