@@ -448,7 +448,7 @@ template <class C, int S> static int launch_inv_march_s(vvb_engine* e, InvArgs a
     constexpr int G = March<C>::G, MINB = March<C>::MINB;
     static int per_sm = -1;
     auto kern = istft_march_kernel<C, S, G, MINB>;
-    const size_t smem = sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3) + 2 * G * (C::XBUF + C::M + 2));
+    const size_t smem = sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3) + 2 * G * (C::XBUF + C::M + 2)) + 8 * G;
     if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
     if (per_sm == 0) return fail(4, "istft_march_kernel", "does not fit on this device");
     if (batch > 0x7fffffffLL) return fail(2, "vvb_stft_inverse", "batch");

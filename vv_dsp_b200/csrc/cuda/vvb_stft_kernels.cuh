@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
     using L = LastPass<C>;
     constexpr int M = C::M, N = 2 * M, E = C::E, T = C::T;
     constexpr int PERIOD = E / S, HOP = 2 * T * S, EDGE = N - HOP;    /* PERIOD frames overlap one sample */
-    constexpr int STG = M + 2;                                        /* staged half spectrum X[0..M] (+1 pad) */
+    constexpr int STG = M + 2;                                        /* staged half spectrum X[-1|0 .. M] */
 #ifdef VVB_EMU
     float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
 #else
@@ -598,17 +598,21 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
     float2* s_tw3 = s_tw2 + C::TW2;
     float2* s_xb = s_tw3 + C::TW3;
     float2* s_stage = s_xb + G * C::XBUF;
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_stage + G * STG);
     /* normalised synthesis: the steady-state 1/sum(w^2) is already folded into the window table, so the
      * main path has no per-sample table load or multiply; only the first/last PERIOD-1 hop-blocks of a
      * signal (fewer frames overlap there) are rescaled, below */
     const bool normalise = a.inv_norm != nullptr;
     copy_table(s_wsyn, a.tables + (normalise ? TB::WSYN_NORM : TB::WSYN), N);
     copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3));
+    const int team = threadIdx.x / T, t = threadIdx.x % T;
+    if (t == 0) mbar_init(&s_bar[team], 1);
     __syncthreads();
 
-    const int team = threadIdx.x / T, t = threadIdx.x % T;
     float2* xb = s_xb + team * C::XBUF;                               /* FFT exchange buffer of this team */
     float2* stage = s_stage + team * STG;                             /* next frame's spectrum lands here */
+    unsigned long long* bar = &s_bar[team];
+    unsigned parity = 0;
     const float2* wsyn2 = reinterpret_cast<const float2*>(s_wsyn);
     /* split-step twiddle of this thread: (cos, sin)(2 pi t / N) / 2; its bins k = t + T r differ from it
      * by the compile-time rotation 2 pi r / (2E) */
@@ -635,34 +639,55 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
         float* yb = a.y + (long long)b * a.y_pitch;
         g0 += f_end - f_begin;
 
-        /* asynchronous copy (LDGSTS) of one frame's half spectrum into the team's staging buffer; issued
-         * right after the previous frame's merge has consumed the buffer, so it is in flight for a whole
-         * frame time */
-        auto prefetch = [&](int frame) {
+        /* asynchronous copy of one frame's half spectrum X[0..M] into the team's staging buffer, issued right
+         * after the previous frame's merge has consumed the buffer, so it is in flight for a whole frame.
+         * Preferred: ONE TMA bulk copy (cp.async.bulk) by one thread.  Rows are (M+1)*8 bytes, i.e. only
+         * 8-byte aligned on odd rows; the copy then starts 8 bytes early (the previous row's last bin) and
+         * the merge reads at an offset of one element.  Both cases move (M+2)*8 bytes.  Fallback (base not
+         * 16-byte aligned, odd pitch overflow, or the very last row of the buffer, where reading 8 bytes
+         * past the end would leave the allocation): per-thread 8-byte cp.async (LDGSTS). */
+        const bool spec16 = (reinterpret_cast<uintptr_t>(a.spec) & 15) == 0;
+        auto prefetch = [&](int frame, int& off, bool& bulk) {
+            off = 0; bulk = false;
             if (frame < f_end) {
-                const float2* X = specb + (long long)frame * a.spec_pitch;
+                const long long rowi = (long long)b * F + frame;
+                const float2* X = a.spec + rowi * a.spec_pitch;
+                const int mis = (int)((rowi * a.spec_pitch) & 1);     /* 1: row starts 8 bytes past a 16-byte boundary */
+                const bool last_row = (b == a.num_items - 1) && (frame == F - 1);
+                if (spec16 && !last_row && (rowi > 0 || mis == 0)) {
+                    off = mis; bulk = true;
+                    if (t == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(bar, STG * 8);
+                        bulk_load(stage, X - mis, STG * 8, bar);
+                    }
+                } else {
 #pragma unroll
-                for (int r = 0; r < E; ++r) cp_async8(&stage[t + T * r], X + t + T * r);
-                if (t == 0) cp_async8(&stage[M], X + M);
+                    for (int r = 0; r < E; ++r) cp_async8(&stage[t + T * r], X + t + T * r);
+                    if (t == 0) cp_async8(&stage[M], X + M);
+                }
             }
             cp_async_commit();
         };
+        int off_next = 0, off_cur = 0;
+        bool bulk_next = false, bulk_cur = false;
 
         float2 acc[E];
 #pragma unroll
         for (int i = 0; i < E; ++i) acc[i] = make_float2(0.f, 0.f);
-        prefetch(fr0);
+        prefetch(fr0, off_next, bulk_next);
 
 #pragma unroll 1
         for (int frame = fr0; frame < emit_end; ++frame) {
             if (frame < f_end) {                                       /* team-uniform */
                 float2 v[E];
-                cp_async_wait_all();
+                off_cur = off_next; bulk_cur = bulk_next;
+                if (bulk_cur) { mbar_wait(bar, parity); parity ^= 1; } else cp_async_wait_all();
                 team_sync<T>(team);
                 /* merge straight into the pass-1 registers (see march_merge_one) */
-                march_merge<C>(v, stage, t, hw_t, typename make_iseq<E>::type{});
+                march_merge<C>(v, stage + off_cur, t, hw_t, typename make_iseq<E>::type{});
                 team_sync<T>(team);                                    /* all reads of the staged X are done */
-                prefetch(frame + 1);
+                prefetch(frame + 1, off_next, bulk_next);
                 if constexpr (REGTW) team_fft_regtw<C>(v, xb, twb, t, team);
                 else team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
                 /* v[q*RL + r] is sample pair i = t + T*(q + NQ*r): accumulate into that slot */
