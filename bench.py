@@ -261,9 +261,15 @@ def main():
     xh.copy_(x)
     xh_np, yh_np = xh.numpy(), yh.numpy()
 
+    # stream-ordered mode (vv_dsp_stft_set_async): both calls only enqueue; the library chains the synthesis
+    # of each chunk of signals to the analysis chunk that produced its spectra, so the H2D of later chunks
+    # overlaps the D2H of earlier ones.  synchronize() returns when yh is complete.
+    h.set_async(True)
+
     def e2e_step():
         h.batch_forward(xh_np, "complex", "valid", out=spec)      # H2D inside, spectra stay in HBM
-        h.batch_inverse(spec, N_SAMPLES, True, out=yh_np)          # D2H inside; returns when yh is complete
+        h.batch_inverse(spec, N_SAMPLES, True, out=yh_np)          # D2H inside
+        h.synchronize()
 
     e2e_step()
     barrier()
@@ -276,7 +282,9 @@ def main():
     if world > 1:
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * N_SAMPLES / float(te_t.item()) / 1e6
-    e2e_err = float(np.linalg.norm((yh_np[:4] - xh_np[:4])[:, NFFT:-NFFT]) / np.linalg.norm(xh_np[:4, NFFT:-NFFT]))
+    h.set_async(False)
+    sel = [0, 1, B // 2, B - 1]
+    e2e_err = float(np.linalg.norm((yh_np[sel] - xh_np[sel])[:, NFFT:-NFFT]) / np.linalg.norm(xh_np[sel][:, NFFT:-NFFT]))
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
@@ -306,7 +314,7 @@ def main():
                               "nominal_peak_tflops": 74.5},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": B * N_SAMPLES * 4,
                     "ms_per_step": float(te_t.item()) * 1e3, "steps": e2e_steps, "roundtrip_rel_l2": e2e_err,
-                    "api": "vv_dsp_stft_batch_forward(HOST signals -> DEVICE spectra) + vv_dsp_stft_batch_inverse(DEVICE spectra -> HOST signals)"},
+                    "api": "vv_dsp_stft_set_async(1); vv_dsp_stft_batch_forward(HOST signals -> DEVICE spectra); vv_dsp_stft_batch_inverse(DEVICE spectra -> HOST signals); vv_dsp_stft_synchronize()"},
             "gpu_launches": int(launches), "clocks": clocks, "roundtrip_rel_l2": err,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -71,8 +71,16 @@ size_t vv_dsp_stft_num_bins(const vv_dsp_stft* h);
 /* Bind the handle to a caller-owned cudaStream_t.  NULL = the handle's own (non-blocking) stream;
  * to address CUDA's default streams pass cudaStreamLegacy ((void*)1) or cudaStreamPerThread ((void*)2). */
 vv_dsp_status vv_dsp_stft_set_stream(vv_dsp_stft* h, void* cuda_stream);
-/* Block until everything enqueued on the handle's stream has finished. */
+/* Block until everything the handle has enqueued (its stream and its staging streams) has finished. */
 vv_dsp_status vv_dsp_stft_synchronize(vv_dsp_stft* h);
+/* Stream-ordered mode for calls with HOST buffers (off by default).  When enabled such calls only
+ * enqueue their copies and kernels and return, like cudaMemcpyAsync: host buffers (pin them) must stay
+ * valid and untouched until vv_dsp_stft_synchronize().  The library orders a call that reads a DEVICE
+ * buffer after the earlier stream-ordered call of the same handle that produced it, chunk by chunk,
+ * so the host->device copies of an analysis call overlap the device->host copies of the synthesis call
+ * that follows it (PCIe is full duplex).  Calls whose buffers are all DEVICE are not ordered against
+ * stream-ordered calls; synchronize in between. */
+vv_dsp_status vv_dsp_stft_set_async(vv_dsp_stft* h, int enable);
 
 /* Analysis of `batch` signals: framing + window + real FFT (+ |X|^2 or |X|) fused in
  * one kernel.  *out_frames receives the per-signal frame count (may be NULL). */

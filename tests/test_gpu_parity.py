@@ -115,6 +115,28 @@ def test_device_resident_torch_tensors(lib, oracle):
         assert np.array_equal(h.batch_forward(x, "complex", "valid"), sd.cpu().numpy())
 
 
+def test_stream_ordered_host_mode(lib, oracle):
+    """vv_dsp_stft_set_async: same bits as the synchronous host path, many chunks, pinned buffers"""
+    import torch
+    from vv_dsp_b200 import Stft
+    nfft, hop, n, B = 2048, 512, 480000, 260          # > 2 staging chunks of ~100 signals
+    xh = torch.empty((B, n), dtype=torch.float32).pin_memory()
+    xh.copy_(torch.from_numpy(np.stack([noise(700 + i % 7, n) for i in range(B)])))
+    yh = torch.empty((B, n), dtype=torch.float32).pin_memory()
+    spec = torch.empty((B, 934, 1025), dtype=torch.complex64, device="cuda")
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        ref = h.batch_inverse(h.batch_forward(xh.numpy(), "complex", "valid"), n, True)      # synchronous
+        h.set_async(True)
+        for _ in range(2):                                                                    # twice: slot reuse
+            yh.zero_()
+            h.batch_forward(xh.numpy(), "complex", "valid", out=spec)
+            h.batch_inverse(spec, n, True, out=yh.numpy())
+            h.synchronize()
+            assert np.array_equal(yh.numpy(), ref)
+        h.set_async(False)
+    assert rel_l2(ref[:, nfft:-nfft], xh.numpy()[:, nfft:-nfft]) < ROUNDTRIP_REL_L2
+
+
 def test_spectrogram(lib, oracle):
     pc.check_spectrogram(lib, oracle, 2048, 512, "hann", 30000)
     pc.check_spectrogram(lib, oracle, 64, 16, "hamming", 40)

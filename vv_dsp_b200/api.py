@@ -63,6 +63,7 @@ class Library:
         "vv_dsp_stft_num_bins": (_sz, [_vp]),
         "vv_dsp_stft_set_stream": (C.c_int, [_vp, _vp]),
         "vv_dsp_stft_synchronize": (C.c_int, [_vp]),
+        "vv_dsp_stft_set_async": (C.c_int, [_vp, C.c_int]),
         "vv_dsp_stft_batch_forward": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, C.c_int, _vp, C.c_int, _sz,
                                                 C.POINTER(_sz)]),
         "vv_dsp_stft_batch_inverse": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, _vp, C.c_int, _sz, _sz, C.c_int]),
@@ -226,6 +227,10 @@ class Stft:
 
     def synchronize(self):
         _check(self.lib, self.lib.vv_dsp_stft_synchronize(self._h), "vv_dsp_stft_synchronize")
+
+    def set_async(self, enable=True):
+        """stream-ordered mode for HOST-buffer calls (see include/vv_dsp/b200.h); finish with synchronize()"""
+        _check(self.lib, self.lib.vv_dsp_stft_set_async(self._h, int(bool(enable))), "vv_dsp_stft_set_async")
 
     def batch_forward(self, signals, kind="complex", convention="valid", out=None):
         """signals: [batch, n] float32, numpy (host) or torch CUDA tensor (device).  Returns

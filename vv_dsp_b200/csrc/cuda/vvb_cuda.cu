@@ -443,9 +443,13 @@ template <bool OLA> static int dispatch_inverse(vvb_engine* e, const InvArgs& a,
 }
 
 /* team-marching ISTFT: register-resident overlap-add (see istft_march_kernel) */
+template <class C> struct MarchInv : March<C> {};
+#ifdef VVB_INV_G12
+template <> struct MarchInv<Cfg1024> { static constexpr int G = 12, MINB = 1; };
+#endif
 template <class C, int S> static int launch_inv_march_s(vvb_engine* e, InvArgs a, long long batch, void* stream)
 {
-    constexpr int G = March<C>::G, MINB = March<C>::MINB;
+    constexpr int G = MarchInv<C>::G, MINB = MarchInv<C>::MINB;
     static int per_sm = -1;
     auto kern = istft_march_kernel<C, S, G, MINB>;
     const size_t smem = sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3) + 2 * G * (C::XBUF + C::M + 2)) + 8 * G;

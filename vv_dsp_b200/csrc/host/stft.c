@@ -18,7 +18,8 @@
 #include "vvb200_cuda.h"
 
 #define NORM_CACHE 4
-#define NSLOT 2
+#define NSLOT 4            /* slots 0,1: analysis (host -> device staging); slots 2,3: synthesis (device -> host) */
+#define NDEP 64            /* per-chunk completion events of the last stream-ordered analysis call */
 #define STAGE_TARGET_BYTES ((size_t)192 << 20)   /* per slot and direction */
 
 typedef struct stage_slot {
@@ -39,6 +40,11 @@ struct vv_dsp_stft {
     float* d_in;   vvb_cpx* d_spec;   float* d_frame;
     /* batched staging (host-space arguments) */
     stage_slot slot[NSLOT];
+    /* stream-ordered mode (vv_dsp_stft_set_async): host-space calls only enqueue work; a later call that
+     * reads a device buffer produced chunk by chunk by an earlier one waits per chunk, on these events */
+    int async;
+    struct { const char* lo; const char* hi; void* ev; int valid; } dep[NDEP];
+    int dep_next;
     /* 1/sum(w^2) tables per frame count: [head nfft-hop | mid hop | tail nfft-hop] */
     struct { size_t frames; float* d_tab; int used; } norm[NORM_CACHE];
     int norm_next;
@@ -65,6 +71,7 @@ static void handle_free(vv_dsp_stft* h)
         if (h->slot[i].stream) vvb_stream_destroy(h->slot[i].stream);
     }
     for (i = 0; i < NORM_CACHE; ++i) vvb_free(h->norm[i].d_tab);
+    for (i = 0; i < NDEP; ++i) if (h->dep[i].ev) vvb_event_destroy(h->dep[i].ev);
     vvb_host_free(h->h_in); vvb_host_free(h->h_spec); vvb_host_free(h->h_frame);
     vvb_free(h->d_in); vvb_free(h->d_spec); vvb_free(h->d_frame);
     vvb_engine_destroy(h->eng);
@@ -184,8 +191,42 @@ vv_dsp_status vv_dsp_stft_set_stream(vv_dsp_stft* h, void* cuda_stream)
 
 vv_dsp_status vv_dsp_stft_synchronize(vv_dsp_stft* h)
 {
+    int i, st;
     if (!h) return VV_DSP_ERROR_NULL_POINTER;
-    return map_status(vvb_stream_sync(h->stream));
+    st = vvb_stream_sync(h->stream);
+    for (i = 0; i < NSLOT; ++i)
+        if (h->slot[i].stream) { int s2 = vvb_stream_sync(h->slot[i].stream); if (!st) st = s2; }
+    for (i = 0; i < NDEP; ++i) h->dep[i].valid = 0;
+    return map_status(st);
+}
+
+vv_dsp_status vv_dsp_stft_set_async(vv_dsp_stft* h, int enable)
+{
+    if (!h) return VV_DSP_ERROR_NULL_POINTER;
+    if (h->async && !enable) { vv_dsp_status st = vv_dsp_stft_synchronize(h); if (st != VV_DSP_OK) return st; }
+    h->async = enable ? 1 : 0;
+    return VV_DSP_OK;
+}
+
+/* remember that the device range [lo, hi) is complete once everything enqueued so far on `stream` is */
+static int dep_record(vv_dsp_stft* h, const void* lo, size_t bytes, void* stream)
+{
+    int k = h->dep_next, st = 0;
+    h->dep_next = (h->dep_next + 1) % NDEP;
+    if (!h->dep[k].ev) st = vvb_event_create(&h->dep[k].ev);
+    if (!st) st = vvb_event_record(h->dep[k].ev, stream);
+    h->dep[k].lo = (const char*)lo; h->dep[k].hi = (const char*)lo + bytes; h->dep[k].valid = !st;
+    return st;
+}
+
+/* make `stream` wait for every recorded producer chunk that overlaps [lo, hi) */
+static int dep_wait(vv_dsp_stft* h, const void* lo, size_t bytes, void* stream)
+{
+    const char* a = (const char*)lo; const char* b = a + bytes;
+    int k, st = 0;
+    for (k = 0; k < NDEP && !st; ++k)
+        if (h->dep[k].valid && h->dep[k].lo < b && a < h->dep[k].hi) st = vvb_stream_wait_event(stream, h->dep[k].ev);
+    return st;
 }
 
 /* ---------------------------------------------------------------- staging helpers */
@@ -243,15 +284,18 @@ vv_dsp_status vv_dsp_stft_batch_forward(vv_dsp_stft* h, const vv_dsp_real* signa
         const size_t in_per = (signals_space == VV_DSP_MEM_HOST) ? (n ? n : 1) * sizeof(float) : 0;
         const size_t out_per = (out_space == VV_DSP_MEM_HOST) ? frames * h->bins * esize : 0;
         const size_t cs = chunk_signals(batch, in_per > out_per ? in_per : out_per);
-        st = vvb_stream_sync(h->stream);            /* device-side operands may still be in flight */
+        if (!h->async) st = vvb_stream_sync(h->stream);   /* device-side operands may still be in flight */
         for (done = 0; done < batch && !st; done += cs, ++c) {
-            stage_slot* s = &h->slot[c % NSLOT];
+            stage_slot* s = &h->slot[c % 2];
             const size_t nb = (batch - done < cs) ? batch - done : cs;
             const float* d_x;
             char* d_o;
             size_t xp, op;
-            st = slot_reserve(s, in_per * cs, out_per * cs);
-            if (!st) st = vvb_stream_sync(s->stream);                  /* slot free again */
+            if (s->in_bytes < in_per * cs || s->out_bytes < out_per * cs || !s->stream) {
+                if (s->stream) st = vvb_stream_sync(s->stream);        /* about to reallocate its buffers */
+                if (!st) st = slot_reserve(s, in_per * cs, out_per * cs);
+            }
+            if (!st && !h->async) st = vvb_stream_sync(s->stream);     /* slot free again (stream order suffices when async) */
             if (st) break;
             if (signals_space == VV_DSP_MEM_HOST) {
                 if (n)
@@ -261,13 +305,18 @@ vv_dsp_status vv_dsp_stft_batch_forward(vv_dsp_stft* h, const vv_dsp_real* signa
             } else { d_x = signals + done * signal_pitch; xp = signal_pitch; }
             if (out_space == VV_DSP_MEM_HOST) { d_o = (char*)s->d_out; op = h->bins; }
             else { d_o = (char*)out + done * frames * spec_pitch * esize; op = spec_pitch; }
+            if (!st && h->async && signals_space == VV_DSP_MEM_DEVICE)
+                st = dep_wait(h, d_x, nb * xp * sizeof(float), s->stream);
             if (!st) st = vvb_stft_forward(h->eng, d_x, nb, n, xp, frames, pad, (int)kind, d_o, op, s->stream);
             if (!st && out_space == VV_DSP_MEM_HOST)
                 st = vvb_memcpy2d_d2h((char*)out + done * frames * spec_pitch * esize, spec_pitch * esize, s->d_out,
                                       h->bins * esize, h->bins * esize, nb * frames, s->stream);
+            if (!st && h->async && out_space == VV_DSP_MEM_DEVICE)
+                st = dep_record(h, d_o, nb * frames * op * esize, s->stream);
         }
-        for (c = 0; c < NSLOT; ++c)
-            if (h->slot[c].stream) { int s2 = vvb_stream_sync(h->slot[c].stream); if (!st) st = s2; }
+        if (!h->async)
+            for (c = 0; c < NSLOT; ++c)
+                if (h->slot[c].stream) { int s2 = vvb_stream_sync(h->slot[c].stream); if (!st) st = s2; }
     }
     return map_status(st);
 }
@@ -345,15 +394,18 @@ vv_dsp_status vv_dsp_stft_batch_inverse(vv_dsp_stft* h, const vv_dsp_cpx* spectr
         const size_t in_per = (spectra_space == VV_DSP_MEM_HOST) ? frames * h->bins * sizeof(vvb_cpx) : 0;
         const size_t out_per = (out_space == VV_DSP_MEM_HOST) ? n_out * sizeof(float) : 0;
         const size_t cs = chunk_signals(batch, in_per > out_per ? in_per : out_per);
-        st = vvb_stream_sync(h->stream);
+        if (!h->async) st = vvb_stream_sync(h->stream);
         for (done = 0; done < batch && !st; done += cs, ++c) {
-            stage_slot* s = &h->slot[c % NSLOT];
+            stage_slot* s = &h->slot[2 + c % 2];                       /* own streams: D2H overlaps the analysis H2D */
             const size_t nb = (batch - done < cs) ? batch - done : cs;
             const vvb_cpx* d_s;
             float* d_y;
             size_t sp, yp;
-            st = slot_reserve(s, in_per * cs, out_per * cs);
-            if (!st) st = vvb_stream_sync(s->stream);
+            if (s->in_bytes < in_per * cs || s->out_bytes < out_per * cs || !s->stream) {
+                if (s->stream) st = vvb_stream_sync(s->stream);
+                if (!st) st = slot_reserve(s, in_per * cs, out_per * cs);
+            }
+            if (!st && !h->async) st = vvb_stream_sync(s->stream);
             if (st) break;
             if (spectra_space == VV_DSP_MEM_HOST) {
                 if (frames)
@@ -363,13 +415,18 @@ vv_dsp_status vv_dsp_stft_batch_inverse(vv_dsp_stft* h, const vv_dsp_cpx* spectr
             } else { d_s = (const vvb_cpx*)spectra + done * frames * spec_pitch; sp = spec_pitch; }
             if (out_space == VV_DSP_MEM_HOST) { d_y = (float*)s->d_out; yp = n_out; }
             else { d_y = out + done * out_pitch; yp = out_pitch; }
+            if (!st && h->async && spectra_space == VV_DSP_MEM_DEVICE && frames)
+                st = dep_wait(h, d_s, nb * frames * sp * sizeof(vvb_cpx), s->stream);
             if (!st) st = vvb_stft_inverse(h->eng, d_s, nb, frames, sp, d_y, n_out, yp, d_tab, s->stream);
             if (!st && out_space == VV_DSP_MEM_HOST)
                 st = vvb_memcpy2d_d2h(out + done * out_pitch, out_pitch * sizeof(float), s->d_out, n_out * sizeof(float),
                                       n_out * sizeof(float), nb, s->stream);
+            if (!st && h->async && out_space == VV_DSP_MEM_DEVICE)
+                st = dep_record(h, d_y, nb * yp * sizeof(float), s->stream);
         }
-        for (c = 0; c < NSLOT; ++c)
-            if (h->slot[c].stream) { int s2 = vvb_stream_sync(h->slot[c].stream); if (!st) st = s2; }
+        if (!h->async)
+            for (c = 0; c < NSLOT; ++c)
+                if (h->slot[c].stream) { int s2 = vvb_stream_sync(h->slot[c].stream); if (!st) st = s2; }
     }
     return map_status(st);
 }
