@@ -52,6 +52,14 @@ def _worker(rank, world, port, case, out_dir):
             lo, hi = max(s0, nfft), min(s1, n - nfft)
             assert rel_l2(y[lo - s0: hi - s0], refy[lo:hi]) < 5e-5
             assert rel_l2(y[lo - s0: hi - s0], x[lo:hi]) < 1e-5
+            # the precomputed plan object gives the same results as the functional form
+            plan = sharding.StreamPlan(h, n, w)
+            plan.x_owned.copy_(torch.from_numpy(x[s0:s1].copy()))
+            for _ in range(2):
+                sp = plan.stft()
+                assert np.array_equal(sp.numpy(), spec.numpy())
+                yp = plan.istft(sp).numpy()
+                assert np.allclose(yp[lo - s0: hi - s0], y[lo - s0: hi - s0], rtol=0, atol=2e-6)
             # shard-by-signal rule: disjoint cover, results identical to the unsharded call
             B = 5
             xb = np.stack([noise(100 + i, 6000) for i in range(B)])

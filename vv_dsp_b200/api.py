@@ -121,7 +121,7 @@ def _is_device(a) -> bool:
 def _ptr(a):
     if a is None:
         return None
-    if hasattr(a, "data_ptr"):
+    if hasattr(a, "data_ptr"):          # torch tensor, CUDA (device space) or CPU (host space)
         return _vp(a.data_ptr())
     return a.ctypes.data_as(_vp)
 

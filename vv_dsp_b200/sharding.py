@@ -113,3 +113,74 @@ def stream_istft(h, spec_local: torch.Tensor, n: int, window: torch.Tensor, grou
             norm = window_sum(w2, nfft, hop, frames, s0, edge)
             y[:edge] = torch.where(norm > 1e-12, raw / norm, torch.zeros_like(raw))
     return y[: s1 - s0].contiguous()
+
+
+class StreamPlan:
+    """Frame-range sharding of one stream with everything static hoisted out of the step: the local
+    buffer [owned span | halo] is allocated once (the neighbour's halo is received straight into its
+    tail, no concatenation), and the window-sum factors of the two nfft-hop edge regions are computed
+    once.  Per step and rank: one halo recv/send, one fused STFT kernel, one fused ISTFT kernel, one
+    tail send/recv and three small elementwise ops on nfft-hop samples.
+
+        plan = StreamPlan(h, n, window)            # collective: every rank constructs it
+        plan.x_owned[:] = my samples               # view into the local buffer
+        spec = plan.stft()                         # [f1-f0, bins]
+        y = plan.istft(spec)                       # [s1-s0]
+    """
+
+    def __init__(self, h, n: int, window: torch.Tensor, group=None):
+        self.h, self.n, self.group = h, n, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nfft, hop = h.nfft, h.hop
+        self.nfft, self.hop, self.edge = nfft, hop, nfft - hop
+        self.frames = 0 if n < nfft else 1 + (n - nfft) // hop
+        self.f0, self.f1 = frame_range(self.frames, self.world, self.rank)
+        self.s0, self.s1 = owned_samples(n, nfft, hop, self.world, self.rank)
+        self.fl = self.f1 - self.f0
+        assert self.world == 1 or self.frames // self.world >= (nfft + hop - 1) // hop, "shards must be longer than one frame"
+        dev = window.device
+        own = self.s1 - self.s0
+        self.has_right = self.rank < self.world - 1 and self.edge > 0
+        self.has_left = self.rank > 0 and self.edge > 0
+        self.local = torch.zeros(own + (self.edge if self.has_right else 0), dtype=torch.float32, device=dev)
+        self.x_owned = self.local[:own]
+        self.halo = self.local[own:] if self.has_right else None
+        span = (self.fl - 1) * hop + nfft if self.fl else 0
+        self.n_local = max(span, own)
+        self.y = torch.empty((1, self.n_local), dtype=torch.float32, device=dev)
+        self.bins = nfft // 2 + 1
+        self.spec = torch.empty((1, self.fl, self.bins), dtype=torch.complex64, device=dev)
+        w2 = (window * window).to(torch.float32)
+        if self.has_right:       # raw tail = y_tail * local window-sum there
+            self.tail_norm = window_sum(w2, nfft, hop, self.fl, self.fl * hop, self.edge)
+            self.tail_send = torch.empty(self.edge, dtype=torch.float32, device=dev)
+        if self.has_left:
+            self.head_norm = window_sum(w2, nfft, hop, self.fl, 0, self.edge)
+            gn = window_sum(w2, nfft, hop, self.frames, self.s0, self.edge)
+            self.head_inv = torch.where(gn > 1e-12, 1.0 / gn, torch.zeros_like(gn))
+            self.tail_recv = torch.empty(self.edge, dtype=torch.float32, device=dev)
+            self.head_send = torch.empty(self.edge, dtype=torch.float32, device=dev)
+
+    def stft(self, kind: str = "complex") -> torch.Tensor:
+        if self.world > 1 and self.edge:
+            if self.has_left:
+                self.head_send.copy_(self.x_owned[: self.edge])
+            _exchange(self.rank - 1 if self.has_left else None, self.head_send if self.has_left else None,
+                      self.rank + 1 if self.has_right else None, self.halo, self.group)
+        if kind == "complex":
+            self.h.batch_forward(self.local[None, :], "complex", "valid", out=self.spec)
+            return self.spec[0]
+        return self.h.batch_forward(self.local[None, :], kind, "valid")[0]
+
+    def istft(self, spec_local: torch.Tensor) -> torch.Tensor:
+        self.h.batch_inverse(spec_local[None], self.n_local, True, out=self.y)
+        y = self.y[0]
+        if self.world > 1 and self.edge:
+            if self.has_right:
+                torch.mul(y[self.fl * self.hop: self.fl * self.hop + self.edge], self.tail_norm, out=self.tail_send)
+            _exchange(self.rank + 1 if self.has_right else None, self.tail_send if self.has_right else None,
+                      self.rank - 1 if self.has_left else None, self.tail_recv if self.has_left else None, self.group)
+            if self.has_left:
+                head = y[: self.edge]
+                head.mul_(self.head_norm).add_(self.tail_recv).mul_(self.head_inv)
+        return y[: self.s1 - self.s0]
