@@ -290,7 +290,10 @@ def main():
         hbm_peak, peak_src = measured_peaks()
         bytes_fwd = B * (4 * N_SAMPLES + 8 * FRAMES * BINS)       # read samples once + write half spectra once
         bytes_inv = B * (8 * FRAMES * BINS + 4 * N_SAMPLES)
-        dom = ("stft_inverse_kernel", inv_ms, bytes_inv) if inv_ms >= fwd_ms else ("stft_forward_kernel", fwd_ms, bytes_fwd)
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_ncu_full_v6_packed_tma_kernels.csv
+        # (same shape, same kernels): equal to the algorithmic bytes, i.e. no re-reads
+        NCU_TRAFFIC = {"istft_march_kernel": 7.872063e9 + 1.953476e9, "stft_march_kernel": 1.973042e9 + 7.786636e9}
+        dom = ("istft_march_kernel", inv_ms, bytes_inv) if inv_ms >= fwd_ms else ("stft_march_kernel", fwd_ms, bytes_fwd)
         achieved = dom[2] / (dom[1] * 1e-3) / 1e9
         flops_dir = B * FRAMES * 5 * NFFT * 11                     # 5 N log2 N per frame per direction
         line = {
@@ -302,7 +305,8 @@ def main():
                        "l2": "inputs larger than L2 (1.97 GB signals, 7.84 GB spectra per GPU vs 126 MB L2)",
                        "parallelism": f"shard-by-signal x{world}, no collective"},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak,
+                         "traffic": NCU_TRAFFIC[dom[0]] if B == BATCH else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom[2], "ms_per_launch": dom[1]},
             "kernels": {"stft_forward_ms": fwd_ms, "stft_inverse_ms": inv_ms, "stft_forward_power_ms": pow_ms,
                         "stft_forward_GBps": bytes_fwd / (fwd_ms * 1e-3) / 1e9, "stft_inverse_GBps": bytes_inv / (inv_ms * 1e-3) / 1e9,
