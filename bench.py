@@ -286,6 +286,12 @@ def main():
     sel = [0, 1, B // 2, B - 1]
     e2e_err = float(np.linalg.norm((yh_np[sel] - xh_np[sel])[:, NFFT:-NFFT]) / np.linalg.norm(xh_np[sel][:, NFFT:-NFFT]))
 
+    fp32_scalar = fp32_packed = None
+    if rank == 0:
+        try:
+            fp32_scalar, fp32_packed = lib.fp32_peak(False), lib.fp32_peak(True)
+        except Exception:
+            pass
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
         bytes_fwd = B * (4 * N_SAMPLES + 8 * FRAMES * BINS)       # read samples once + write half spectra once
@@ -315,7 +321,10 @@ def main():
             "roofline_fp32": {"flops_per_direction": flops_dir, "convention": "5*N*log2(N) per frame (north-star)",
                               "achieved_tflops_forward": flops_dir / (fwd_ms * 1e-3) / 1e12,
                               "achieved_tflops_inverse": flops_dir / (inv_ms * 1e-3) / 1e12,
-                              "nominal_peak_tflops": 74.5},
+                              "nominal_peak_tflops": 74.5, "measured_peak_tflops_ffma": fp32_scalar,
+                              "measured_peak_tflops_ffma2": fp32_packed,
+                              "roofline_ms_power_variant": max(flops_dir / ((fp32_scalar or 74.5) * 1e12), B * (4 * N_SAMPLES + 4 * FRAMES * BINS) / (hbm_peak * 1e9)) * 1e3,
+                              "frac_power_variant": max(flops_dir / ((fp32_scalar or 74.5) * 1e12), B * (4 * N_SAMPLES + 4 * FRAMES * BINS) / (hbm_peak * 1e9)) * 1e3 / pow_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": B * N_SAMPLES * 4,
                     "ms_per_step": float(te_t.item()) * 1e3, "steps": e2e_steps, "roundtrip_rel_l2": e2e_err,
                     "api": "vv_dsp_stft_set_async(1); vv_dsp_stft_batch_forward(HOST signals -> DEVICE spectra); vv_dsp_stft_batch_inverse(DEVICE spectra -> HOST signals); vv_dsp_stft_synchronize()"},

@@ -109,6 +109,9 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_istft(vv_dsp_stft* h, const vv_dsp_cp
 const char* vv_dsp_b200_version(void);
 /* last CUDA error text seen by the calling thread ("" if none) */
 const char* vv_dsp_b200_last_error(void);
+/* diagnostics: measured FP32 FMA throughput of the current device in TFLOP/s (scalar FFMA when packed == 0,
+ * packed FFMA2 otherwise); the denominator of the FP32 side of the roofline */
+vv_dsp_status vv_dsp_b200_fp32_peak(int packed, double* tflops);
 /* number of kernels this process has launched through the library (bench.py's gpu_launches) */
 unsigned long long vv_dsp_b200_kernel_launches(void);
 

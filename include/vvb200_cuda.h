@@ -26,6 +26,7 @@ enum { VVB_PAD_ZERO = 0, VVB_PAD_REFLECT_CENTER = 1 };
 const char* vvb_last_error(void);
 unsigned long long vvb_kernel_launches(void);
 int vvb_device_ready(void);   /* 0 when a usable sm_100-class device is current */
+int vvb_fp32_peak(int packed, double* tflops);   /* diagnostics: measured FFMA (0) / FFMA2 (1) throughput */
 
 /* ---- memory / stream plumbing (device = the engine's device) */
 int vvb_malloc(void** dptr, size_t bytes);

@@ -71,6 +71,7 @@ class Library:
         "vv_dsp_b200_version": (C.c_char_p, []),
         "vv_dsp_b200_last_error": (C.c_char_p, []),
         "vv_dsp_b200_kernel_launches": (C.c_ulonglong, []),
+        "vv_dsp_b200_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     }
 
     def __init__(self, path: str | None = None):
@@ -94,6 +95,14 @@ class Library:
 
     def kernel_launches(self) -> int:
         return int(self.dll.vv_dsp_b200_kernel_launches())
+
+    def fp32_peak(self, packed: bool = False) -> float:
+        """measured FP32 FMA throughput of the current device, TFLOP/s"""
+        v = C.c_double(0.0)
+        st = self.dll.vv_dsp_b200_fp32_peak(int(packed), C.byref(v))
+        if st != 0:
+            raise VvDspError(st, "vv_dsp_b200_fp32_peak", self.last_error())
+        return float(v.value)
 
     def version(self) -> str:
         return self.dll.vv_dsp_b200_version().decode()

@@ -653,3 +653,56 @@ extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, si
         return vvb_stft_forward(e->real, (const float*)d_in, batch, e->n, e->n, 1, PAD_ZERO, OUT_COMPLEX, d_out, bins, stream);
     return vvb_stft_inverse_frames(e->real, (const vvb_cpx*)d_in, batch, bins, (float*)d_out, stream);   /* C2R */
 }
+
+/* ---------------------------------------------------------------- FP32 peak probe */
+/* Measures the FP32 FMA throughput the roofline is quoted against: 16 independent dependent-FMA
+ * chains per thread, scalar FFMA or packed FFMA2.  Diagnostics only (bench.py's roofline_fp32). */
+template <bool PACKED> __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters)
+{
+    float2 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = make_float2(threadIdx.x * 1e-3f + i, 1.0f - i * 1e-2f);
+    const float2 m = make_float2(0.999f, 1.001f), c = make_float2(1e-3f, -1e-3f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if constexpr (PACKED) a[i] = __ffma2_rn(a[i], m, c);
+                else { a[i].x = fmaf(a[i].x, m.x, c.x); a[i].y = fmaf(a[i].y, m.y, c.y); }
+            }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+    if (s == 123.456f) out[0] = s;
+}
+
+extern "C" int vvb_fp32_peak(int packed, double* tflops)
+{
+    if (!tflops) return fail(1, "vvb_fp32_peak", "null");
+#ifdef VVB_EMU
+    (void)packed; *tflops = 0.0; return 0;
+#else
+    if (int st = vvb_device_ready()) return st;
+    float* d = nullptr;
+    CK(cudaMalloc(&d, 4));
+    const int iters = 4096, grid = rt_num_sms() * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0));
+        if (packed) fp32_peak_kernel<true><<<grid, 256>>>(d, iters); else fp32_peak_kernel<false><<<grid, 256>>>(d, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)grid * 256 * iters * 4 * 8 * 2 * 2;   /* 64 FMA lanes-ops per iteration, 2 flop each */
+        if (rep > 0 && flops / (ms * 1e-3) / 1e12 > best) best = flops / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return 0;
+#endif
+}
