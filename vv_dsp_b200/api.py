@@ -114,7 +114,8 @@ _default = None
 def default_library() -> Library:
     global _default
     if _default is None:
-        _default = Library()
+        # VVDSP_B200_LIB: path of another nvcc-built libvvdsp_b200 variant (A/B measurements only)
+        _default = Library(os.environ.get("VVDSP_B200_LIB") or None)
     return _default
 
 
