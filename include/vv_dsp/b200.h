@@ -35,6 +35,7 @@
 #include <stddef.h>
 #include "vv_dsp/vv_dsp_types.h"
 #include "vv_dsp/spectral/stft.h"
+#include "vv_dsp/spectral/fft.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -104,6 +105,16 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_inverse(
  * (= reconstruct-all-frames + the caller-side divide of tools/dump_stft_roundtrip.c:50-54). */
 VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_istft(vv_dsp_stft* h, const vv_dsp_cpx* half_spectra, size_t frames,
                                                  vv_dsp_real* out, size_t n_out);
+
+/* Many transforms through one plan: `batch` contiguous transforms,
+ * C2C: cpx[batch][n] -> cpx[batch][n];  R2C: real[batch][n] -> cpx[batch][n/2+1];  C2R: the reverse.
+ * Same conventions as vv_dsp_fft_execute (forward unscaled, backward 1/n, R2C Nyquist real, C2R =
+ * Re of the inverse of the Hermitian extension).  DEVICE buffers: enqueued on `cuda_stream` (NULL = the
+ * plan's stream) and not awaited; any HOST buffer: staged and synchronous.  in == out is allowed for C2C
+ * with a power-of-two n in [128, 4096] only. */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_fft_execute_batch(const vv_dsp_fft_plan* plan, const void* in,
+                                                        vv_dsp_mem_space in_space, void* out,
+                                                        vv_dsp_mem_space out_space, size_t batch, void* cuda_stream);
 
 /* Library / device introspection */
 const char* vv_dsp_b200_version(void);

@@ -122,6 +122,25 @@ def check_fft_plans(lib, oracle, sizes):
         assert np.abs(back - x).max() < 1e-5
 
 
+def check_fft_batch(lib, oracle, sizes, batch=5):
+    """vv_dsp_fft_execute_batch == looping vv_dsp_fft_execute == the oracle, transform by transform"""
+    rng = np.random.default_rng(11)
+    for n in sizes:
+        x = (rng.uniform(-1, 1, (batch, n)) + 1j * rng.uniform(-1, 1, (batch, n))).astype(np.complex64)
+        xr = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+        pf, pb, pr, pc = (FftPlan(n, 0, +1, lib=lib), FftPlan(n, 0, -1, lib=lib), FftPlan(n, 1, +1, lib=lib), FftPlan(n, 2, -1, lib=lib))
+        F, B, R = pf.execute_batch(x), pb.execute_batch(x), pr.execute_batch(xr)
+        Cr = pc.execute_batch(R)
+        for i in range(batch):
+            for got, ref, what in ((F[i], oracle.fft_c2c(x[i], +1), "c2c fwd"), (B[i], oracle.fft_c2c(x[i], -1), "c2c bwd"),
+                                   (R[i], oracle.fft_r2c(xr[i]), "r2c")):
+                ok, frac = spectra_close(got, ref)
+                assert ok, (n, i, what, frac)
+            assert np.array_equal(F[i], pf.execute(x[i])) and np.array_equal(R[i], pr.execute(xr[i]))
+            assert np.abs(Cr[i] - xr[i]).max() < 1e-5
+        assert np.all(R[:, -1].imag == 0) if n % 2 == 0 and n > 1 else True
+
+
 def check_status_codes(lib):
     """Return codes of the reference boundary (SURVEY.md section 4 'lifecycle/validation')."""
     import ctypes as C

@@ -71,6 +71,10 @@ def test_fft_plans(emu, oracle):
     pc.check_fft_plans(emu, oracle, [1, 2, 3, 8, 16, 100, 128, 256, 1024, 2048])
 
 
+def test_fft_execute_batch(emu, oracle):
+    pc.check_fft_batch(emu, oracle, [1, 8, 100, 128, 256, 1024])
+
+
 def test_golden_slices(emu, golden):
     pc.check_golden_slices(emu, golden)
 

@@ -146,6 +146,20 @@ def test_fft_plans(lib, oracle):
     pc.check_fft_plans(lib, oracle, [1, 2, 3, 4, 8, 16, 32, 64, 100, 128, 200, 256, 512, 1024, 2048, 4096, 8192])
 
 
+def test_fft_execute_batch(lib, oracle):
+    pc.check_fft_batch(lib, oracle, [1, 2, 8, 16, 100, 128, 200, 256, 512, 1024, 2048, 4096, 8192], batch=7)
+    # device-resident, in place for a Stockham size
+    import torch
+    from vv_dsp_b200 import FftPlan
+    x = (torch.randn(64, 1024, device="cuda") + 1j * torch.randn(64, 1024, device="cuda")).to(torch.complex64)
+    ref = torch.fft.fft(x.to(torch.complex128), dim=-1)
+    p = FftPlan(1024, 0, +1, lib=lib)
+    y = x.clone()
+    p.execute_batch(y, out=y, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert float((y - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
 def test_golden_slices_of_the_real_reference(lib, golden):
     pc.check_golden_slices(lib, golden)
 

@@ -52,6 +52,7 @@ class Library:
         "vv_dsp_fft_make_plan": (C.c_int, [_sz, C.c_int, C.c_int, C.POINTER(_vp)]),
         "vv_dsp_fft_execute": (C.c_int, [_vp, _vp, _vp]),
         "vv_dsp_fft_destroy": (C.c_int, [_vp]),
+        "vv_dsp_fft_execute_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _sz, _vp]),
         "vv_dsp_window_boxcar": (C.c_int, [_sz, _vp]),
         "vv_dsp_window_hann": (C.c_int, [_sz, _vp]),
         "vv_dsp_window_hamming": (C.c_int, [_sz, _vp]),
@@ -315,6 +316,26 @@ class FftPlan:
         else:
             x = np.ascontiguousarray(x, np.complex64); out = np.empty(n, np.float32)
         _check(self.lib, self.lib.vv_dsp_fft_execute(self._p, _ptr(x), _ptr(out)), "vv_dsp_fft_execute")
+        return out
+
+    def execute_batch(self, x, out=None, stream=None):
+        """x: [batch, n] (C2C complex64 / R2C float32) or [batch, n/2+1] complex64 (C2R); numpy or torch CUDA"""
+        dev = _is_device(x)
+        n, bins = self.n, self.n // 2 + 1
+        if not dev:
+            x = np.ascontiguousarray(x, np.float32 if self.type == FFT_R2C else np.complex64)
+        batch = int(x.shape[0])
+        oshape = (batch, n if self.type != FFT_R2C else bins)
+        if out is None:
+            if dev:
+                import torch
+                out = torch.empty(oshape, device=x.device, dtype=torch.float32 if self.type == FFT_C2R else torch.complex64)
+            else:
+                out = np.empty(oshape, np.float32 if self.type == FFT_C2R else np.complex64)
+        st = self.lib.vv_dsp_fft_execute_batch(self._p, _ptr(x), DEVICE if dev else HOST, _ptr(out),
+                                               DEVICE if _is_device(out) else HOST, batch,
+                                               _vp(int(stream) or 1) if stream is not None else None)
+        _check(self.lib, st, "vv_dsp_fft_execute_batch")
         return out
 
     def close(self):

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "vv_dsp/spectral/fft.h"
+#include "vv_dsp/b200.h"
 #include "vvb200_cuda.h"
 
 struct vv_dsp_fft_plan {
@@ -110,5 +111,36 @@ vv_dsp_status vv_dsp_fft_execute(const vv_dsp_fft_plan* plan, const void* in, vo
 vv_dsp_status vv_dsp_fft_destroy(vv_dsp_fft_plan* plan)
 {
     plan_free(plan);   /* NULL is fine, like the reference */
+    return VV_DSP_OK;
+}
+
+/* batched execute (include/vv_dsp/b200.h): the same engine, `batch` transforms per launch */
+vv_dsp_status vv_dsp_fft_execute_batch(const vv_dsp_fft_plan* plan, const void* in, vv_dsp_mem_space in_space, void* out,
+                                       vv_dsp_mem_space out_space, size_t batch, void* cuda_stream)
+{
+    void *d_in = NULL, *d_out = NULL, *stream;
+    int st = 0;
+    if (!plan || !in || !out) return VV_DSP_ERROR_NULL_POINTER;
+    if ((unsigned)in_space > 1u || (unsigned)out_space > 1u) return VV_DSP_ERROR_OUT_OF_RANGE;
+    if (batch == 0) return VV_DSP_OK;
+    stream = cuda_stream ? cuda_stream : plan->stream;
+    if (in_space == VV_DSP_MEM_DEVICE && out_space == VV_DSP_MEM_DEVICE) {
+        st = vvb_fft_exec(plan->eng, in, out, batch, stream);
+        return st == 0 ? VV_DSP_OK : (st >= 1 && st <= 6 ? (vv_dsp_status)st : VV_DSP_ERROR_INTERNAL);
+    }
+    if (in_space == VV_DSP_MEM_HOST) {
+        st = vvb_malloc(&d_in, plan->in_bytes * batch);
+        if (!st) st = vvb_memcpy_h2d(d_in, in, plan->in_bytes * batch, stream);
+    }
+    if (!st && out_space == VV_DSP_MEM_HOST) st = vvb_malloc(&d_out, plan->out_bytes * batch);
+    if (!st) st = vvb_fft_exec(plan->eng, d_in ? d_in : in, d_out ? d_out : out, batch, stream);
+    if (!st && out_space == VV_DSP_MEM_HOST) st = vvb_memcpy_d2h(out, d_out, plan->out_bytes * batch, stream);
+    { int s2 = vvb_stream_sync(stream); if (!st) st = s2; }
+    vvb_free(d_in); vvb_free(d_out);
+    if (st) return (st >= 1 && st <= 6) ? (vv_dsp_status)st : VV_DSP_ERROR_INTERNAL;
+    if (out_space == VV_DSP_MEM_HOST && plan->type == VV_DSP_FFT_R2C && plan->n % 2 == 0 && plan->n > 1) {
+        size_t b, bins = plan->n / 2 + 1;
+        for (b = 0; b < batch; ++b) ((vv_dsp_cpx*)out)[b * bins + plan->n / 2].im = 0.0f;
+    }
     return VV_DSP_OK;
 }
