@@ -367,7 +367,7 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
         a.frames = (int)frames; a.hop = (int)e->hop; a.pad_mode = pad_mode;
         a.out = d_out; a.out_pitch = (long long)out_pitch; a.tables = e->d_tables;
         a.num_groups = (int)batch; a.groups_per_signal = 0;
-        if (pad_mode == PAD_ZERO && !getenv("VVB_NO_MARCH")) {
+        if (!getenv("VVB_NO_MARCH")) {           /* zero padding and centred reflect padding both */
             int r = -1;
             /* (at fft_size 512 / 1024 the 2-pass generic forward kernel is faster than a 3-pass marching one) */
             if (e->nfft == 2048) r = launch_fwd_march<Cfg1024>(e, a, out_kind, stream);

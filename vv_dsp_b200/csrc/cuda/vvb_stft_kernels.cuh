@@ -396,12 +396,16 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
         const bool bulk_ok = (reinterpret_cast<uintptr_t>(xs) & 15) == 0;
         g0 += f_end - f_begin;
 
-        /* bring hop-block j (samples [j*HOP, (j+1)*HOP), zeros past n) into its ring slot; returns true
-         * if a TMA copy was issued (completion must then be awaited on the mbarrier) */
+        /* bring hop-block j into its ring slot: samples [origin + j*HOP, origin + (j+1)*HOP), where origin is
+         * 0 (frames start at f*hop, zeros outside the signal) or -N/2 (centred frames, edge-inclusive
+         * reflection outside the signal: src/core/framing.c:21-56,86-102).  Returns true if a TMA copy was
+         * issued (completion must then be awaited on the mbarrier); blocks that touch a signal edge are
+         * filled by the threads with the padding rule. */
+        const long long origin = (a.pad_mode == PAD_REFLECT) ? -(long long)M : 0;      /* M = N/2 */
         auto load_block = [&](int j) -> bool {
             float2* dst = ring + (j % RING) * HB;
-            const long long s0 = (long long)j * HOP;
-            if (bulk_ok && s0 + HOP <= a.n) {
+            const long long s0 = origin + (long long)j * HOP;
+            if (bulk_ok && s0 >= 0 && s0 + HOP <= a.n) {
                 if (t == 0) {
                     fence_proxy_async();
                     mbar_expect_tx(bar, HOP * 4);
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
 #pragma unroll
             for (int r = 0; r < S; ++r) {
                 const long long i0 = s0 + 2 * (t + T * r);
-                dst[t + T * r] = make_float2(i0 < a.n ? __ldg(xs + i0) : 0.f, i0 + 1 < a.n ? __ldg(xs + i0 + 1) : 0.f);
+                dst[t + T * r] = make_float2(fetch_sample(xs, a.n, i0, a.pad_mode), fetch_sample(xs, a.n, i0 + 1, a.pad_mode));
             }
             return false;
         };
