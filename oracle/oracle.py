@@ -248,6 +248,24 @@ class Oracle(_Base):
         self.lib.orc_stft_destroy(h)
         return y
 
+    # --- mel
+    def mel_filterbank(self, n_fft, n_mels, sr, fmin, fmax, variant=0):
+        bins = n_fft // 2 + 1
+        w = np.zeros((max(n_mels, 1), bins), np.float32)
+        self.lib.orc_mel_filterbank.restype = C.c_int
+        st = self.lib.orc_mel_filterbank(_sz(n_fft), _sz(n_mels), C.c_float(sr), C.c_float(fmin), C.c_float(fmax),
+                                         C.c_int(variant), _p(w))
+        return st, w[:n_mels]
+
+    def log_mel(self, power, weights, eps):
+        power, weights = _f32(power), _f32(weights)
+        out = np.empty((power.shape[0], weights.shape[0]), np.float32)
+        self.lib.orc_log_mel.restype = C.c_int
+        st = self.lib.orc_log_mel(_p(power), _sz(power.shape[0]), _sz(power.shape[1]), _p(weights), _sz(weights.shape[0]),
+                                  C.c_float(eps), _p(out))
+        assert st == 0, st
+        return out
+
 
 class _Params(C.Structure):
     _fields_ = [("fft_size", _sz), ("hop_size", _sz), ("window", C.c_int)]
@@ -384,6 +402,25 @@ class Reference(_Base):
             assert self.lib.vv_dsp_stft_process(h, _p(frame), _p(spec)) == 0
             out[f] = spec[:bins]
         self.lib.vv_dsp_stft_destroy(h)
+        return out
+
+    def mel_filterbank(self, n_fft, n_mels, sr, fmin, fmax, variant=0):
+        w = C.POINTER(C.c_float)()
+        nf, fl = _sz(0), _sz(0)
+        st = self.lib.vv_dsp_mel_filterbank_create(_sz(n_fft), _sz(n_mels), C.c_float(sr), C.c_float(fmin), C.c_float(fmax),
+                                                   C.c_int(variant), C.byref(w), C.byref(nf), C.byref(fl))
+        if st != 0:
+            return st, None
+        out = np.ctypeslib.as_array(w, shape=(nf.value, fl.value)).copy()
+        self.lib.vv_dsp_mel_filterbank_free(w, nf)
+        return st, out
+
+    def log_mel(self, power, weights, eps):
+        power, weights = _f32(power), _f32(weights)
+        out = np.empty((power.shape[0], weights.shape[0]), np.float32)
+        st = self.lib.vv_dsp_compute_log_mel_spectrogram(_p(power), _sz(power.shape[0]), _sz(power.shape[1]), _p(weights),
+                                                         _sz(weights.shape[0]), C.c_float(eps), _p(out))
+        assert st == 0, st
         return out
 
     def istft(self, spec, nfft, hop, n_out, win="hann", half=True, normalise=True):

@@ -459,3 +459,71 @@ int orc_stft_roundtrip(orc_stft *h, const float *x, size_t n, float *y)
     free(recon); free(norm); free(spec);
     return 0;
 }
+
+/* ---------------------------------------------- mel filterbank / log-mel */
+
+/* src/features/mel.c:14-29 -- HTK mel scale in float32: 2595 log10f(1 + hz/700), inverse with powf */
+float orc_hz_to_mel(float hz) { return hz < 0.0f ? 0.0f : 2595.0f * log10f(1.0f + hz / 700.0f); }
+float orc_mel_to_hz(float mel) { return mel < 0.0f ? 0.0f : 700.0f * (powf(10.0f, mel / 2595.0f) - 1.0f); }
+
+/* src/features/mel.c:51-62: first index whose value is not below v (lower bound) */
+static size_t orc_lower_bound(const float *a, size_t n, float v)
+{
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        const size_t mid = lo + (hi - lo) / 2;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+/* src/features/mel.c:66-185: dense [n_mels][n_fft/2+1] triangular filters; band edges are n_mels+2
+ * points equally spaced in mel (start + step*i in float32, :35-46) mapped back to Hz; rising slope over
+ * bins [left_idx, center_idx), falling over [center_idx, right_idx); each filter divided by its sum.
+ * Status codes as the reference: NULL -> 1, bad sizes / n_mels >= bins -> 2, fmax > sr/2 or a variant
+ * other than HTK -> 3.  weights must hold n_mels*(n_fft/2+1) floats. */
+int orc_mel_filterbank(size_t n_fft, size_t n_mels, float sr, float fmin, float fmax, int variant, float *weights)
+{
+    if (!weights) return 1;
+    if (n_fft == 0 || n_mels == 0 || sr <= 0.0f || fmin < 0.0f || fmax <= fmin) return 2;
+    if (fmax > sr / 2.0f) return 3;
+    if (variant != 0) return 3;
+    const size_t bins = n_fft / 2 + 1, npts = n_mels + 2;
+    if (n_mels >= bins) return 2;
+    float *hz = (float *)malloc(npts * sizeof(float));
+    float *freq = (float *)malloc(bins * sizeof(float));
+    if (!hz || !freq) { free(hz); free(freq); return 4; }
+    memset(weights, 0, n_mels * bins * sizeof(float));
+    const float m0 = orc_hz_to_mel(fmin), m1 = orc_hz_to_mel(fmax);
+    const float step = (m1 - m0) / (float)(npts - 1);
+    for (size_t i = 0; i < npts; ++i) hz[i] = orc_mel_to_hz(m0 + step * (float)i);
+    for (size_t k = 0; k < bins; ++k) freq[k] = (float)k * sr / (float)n_fft;
+    for (size_t m = 0; m < n_mels; ++m) {
+        const float left = hz[m], center = hz[m + 1], right = hz[m + 2];
+        const size_t li = orc_lower_bound(freq, bins, left), ci = orc_lower_bound(freq, bins, center),
+                     ri = orc_lower_bound(freq, bins, right);
+        float *w = weights + m * bins;
+        for (size_t k = li; k < ci && k < bins; ++k) w[k] = (freq[k] - left) / (center - left);
+        for (size_t k = ci; k < ri && k < bins; ++k) w[k] = (right - freq[k]) / (right - center);
+        float sum = 0.0f;
+        for (size_t k = 0; k < bins; ++k) sum += w[k];
+        if (sum > 0.0f) for (size_t k = 0; k < bins; ++k) w[k] /= sum;
+    }
+    free(hz); free(freq);
+    return 0;
+}
+
+/* src/features/mel.c:204-245: out[f][m] = logf(sum_k power[f][k]*W[m][k] + eps), k ascending in float32 */
+int orc_log_mel(const float *power, size_t frames, size_t bins, const float *weights, size_t n_mels, float eps, float *out)
+{
+    if (!power || !weights || !out) return 1;
+    if (frames == 0 || bins == 0 || n_mels == 0) return 2;
+    if (eps < 0.0f) return 3;
+    for (size_t f = 0; f < frames; ++f)
+        for (size_t m = 0; m < n_mels; ++m) {
+            float e = 0.0f;
+            for (size_t k = 0; k < bins; ++k) e += power[f * bins + k] * weights[m * bins + k];
+            out[f * n_mels + m] = logf(e + eps);
+        }
+    return 0;
+}

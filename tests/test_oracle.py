@@ -229,3 +229,22 @@ def test_oracle_accuracy_envelope(oracle, nfft, bound):
     truth = stft_truth_f64(x, w, nfft, hop, s.shape[0])
     err = np.abs(s - truth).max() / np.abs(truth).max()
     assert err < bound, err
+
+
+# ------------------------------------------------------------------ groundwork for SURVEY.md 8(f) rank 2
+def test_mel_oracle_against_reference(oracle, reference):
+    """The mel filterbank / log-mel restatement (src/features/mel.c:14-245) is bit-exact against the
+    compiled reference; the GPU side of this row is not built yet."""
+    if not hasattr(reference.lib, "vv_dsp_mel_filterbank_create"):
+        pytest.skip("oracle/_ref was built without mel.c")
+    for args in [(2048, 80, 48000.0, 0.0, 24000.0), (2048, 128, 48000.0, 20.0, 20000.0), (1024, 40, 44100.0, 0.0, 22050.0),
+                 (512, 26, 16000.0, 300.0, 8000.0)]:
+        so, wo = oracle.mel_filterbank(*args)
+        sr, wr = reference.mel_filterbank(*args)
+        assert so == sr == 0 and wo.tobytes() == wr.tobytes(), args
+        assert np.allclose(wo.sum(axis=1), 1.0, atol=1e-5)
+        p = np.random.default_rng(1).uniform(0, 10, (5, args[0] // 2 + 1)).astype(np.float32)
+        assert oracle.log_mel(p, wo, 1e-10).tobytes() == reference.log_mel(p, wr, 1e-10).tobytes()
+    for bad in [(0, 10, 48000.0, 0.0, 100.0), (512, 0, 48000.0, 0.0, 100.0), (512, 300, 48000.0, 0.0, 100.0),
+                (512, 10, 48000.0, 0.0, 30000.0), (512, 10, 48000.0, 100.0, 50.0), (512, 10, 48000.0, 0.0, 8000.0, 1)]:
+        assert oracle.mel_filterbank(*bad)[0] == reference.mel_filterbank(*bad)[0], bad
