@@ -507,6 +507,65 @@ VVB_DEV void team_inverse_frame(float2 (&v)[C::E], const float2* X, bool active,
     team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
 }
 
+/* one round of the slot-based overlap-add of stft_inverse_kernel (V samples per thread and step) */
+template <class C, int G, int V>
+VVB_DEV void ola_combine(const InvArgs& a, const float2* s_xb, const float* carry_in, float* carry_out, float* yb,
+                         long long fb, int hop, int edge, int K, int nblk, long long out_lo, long long out_hi, bool normalise)
+{
+    using TB = Tables<C>;
+    constexpr int N = 2 * C::M;
+    const long long tail0 = (long long)a.frames * hop;
+    for (int hb = 0; hb < nblk; ++hb) {
+        const int g_lo = max(0, hb - K + 1), g_hi = min(G - 1, hb);
+        for (int cidx = threadIdx.x * V; cidx < hop; cidx += blockDim.x * V) {
+            const int s = hb * hop + cidx;
+            if (s >= G * hop + edge) break;
+            float acc[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = (s < edge) ? carry_in[s + j] : 0.f;
+            for (int g = g_lo; g <= g_hi; ++g) {
+                const int p = s - g * hop;
+                if (p < N) {
+                    const float* slot = reinterpret_cast<const float*>(s_xb + g * C::XBUF) + p;
+                    if constexpr (V == 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(slot);
+                        acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+                    } else {
+                        acc[0] += slot[0];
+                    }
+                }
+            }
+            if (s < G * hop) {
+                const long long tt = fb * hop + s;
+                if (normalise && (tt < edge || tt + V > tail0)) {
+                    /* edge region: undo the steady-state factor folded into the window, apply the true one */
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const long long u = tt + j;
+                        float sc;
+                        if (u >= tail0) sc = (u - tail0 < edge) ? __ldg(a.inv_norm + edge + hop + (u - tail0)) : 0.f;
+                        else if (u < edge) sc = __ldg(a.inv_norm + u);
+                        else sc = __ldg(a.inv_norm + edge + cidx + j);
+                        acc[j] *= sc * __ldg(a.tables + TB::MIDNORM + cidx + j);
+                    }
+                }
+                if constexpr (V == 4) {
+                    if (tt >= out_lo && tt + 3 < out_hi) {
+                        *reinterpret_cast<float4*>(yb + tt) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        continue;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if (tt + j >= out_lo && tt + j < out_hi) yb[tt + j] = acc[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) carry_out[s - G * hop + j] = acc[j];
+            }
+        }
+    }
+}
+
 template <class C, int G, bool OLA>
 __global__ void __launch_bounds__(C::T* G) stft_inverse_kernel(const InvArgs a)
 {
@@ -524,7 +583,9 @@ __global__ void __launch_bounds__(C::T* G) stft_inverse_kernel(const InvArgs a)
     float2* s_post = s_tw3 + C::TW3;
     float2* s_xb = s_post + C::POST + 1;
     float* s_carry = reinterpret_cast<float*>(s_xb + G * C::XBUF);    /* 2 x (N - hop) floats (OLA) */
-    copy_table(s_wsyn, a.tables + TB::WSYN, N);
+    /* normalised overlap-add: steady-state 1/sum(w^2) folded into the synthesis window (see istft_march_kernel) */
+    const bool normalise = OLA && a.inv_norm != nullptr;
+    copy_table(s_wsyn, a.tables + (normalise ? TB::WSYN_NORM : TB::WSYN), N);
     copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3 + C::POST));
     __syncthreads();
 
@@ -590,36 +651,14 @@ __global__ void __launch_bounds__(C::T* G) stft_inverse_kernel(const InvArgs a)
                     }
                 __syncthreads();
 
-                /* conflict-free overlap-add: one thread per output sample, ascending frame order */
+                /* conflict-free overlap-add: every output sample is summed once, by one thread, from the slots
+                 * that cover it, in ascending frame order; four samples per thread (128-bit shared-memory and
+                 * global accesses) when hop and the output row are 4-sample aligned */
                 const float* carry_in = s_carry + cur * edge;
                 float* carry_out = s_carry + (cur ^ 1) * edge;
-                for (int hb = 0; hb < nblk; ++hb) {
-                    const int g_lo = max(0, hb - K + 1), g_hi = min(G - 1, hb);
-                    for (int cidx = threadIdx.x; cidx < hop; cidx += blockDim.x) {
-                        const int s = hb * hop + cidx;
-                        if (s >= G * hop + edge) break;
-                        float acc = (s < edge) ? carry_in[s] : 0.f;
-                        for (int g = g_lo; g <= g_hi; ++g) {
-                            const int p = s - g * hop;
-                            if (p < N) acc += reinterpret_cast<const float*>(s_xb + g * C::XBUF)[p];
-                        }
-                        if (s < G * hop) {
-                            const long long tt = fb * hop + s;
-                            if (tt >= out_lo && tt < out_hi) {
-                                float scale = 1.0f;
-                                if (a.inv_norm) {
-                                    const long long tail0 = (long long)a.frames * hop;
-                                    if (tt >= tail0) scale = (tt - tail0 < edge) ? __ldg(a.inv_norm + edge + hop + (tt - tail0)) : 0.f;
-                                    else if (tt < edge) scale = __ldg(a.inv_norm + tt);
-                                    else scale = __ldg(a.inv_norm + edge + cidx);
-                                }
-                                yb[tt] = acc * scale;
-                            }
-                        } else {
-                            carry_out[s - G * hop] = acc;
-                        }
-                    }
-                }
+                const bool vec4 = ((hop & 3) == 0) && ((reinterpret_cast<uintptr_t>(yb) & 15) == 0);
+                if (vec4) ola_combine<C, G, 4>(a, s_xb, carry_in, carry_out, yb, fb, hop, edge, K, nblk, out_lo, out_hi, normalise);
+                else ola_combine<C, G, 1>(a, s_xb, carry_in, carry_out, yb, fb, hop, edge, K, nblk, out_lo, out_hi, normalise);
                 cur ^= 1;
                 __syncthreads();
             }
