@@ -375,11 +375,8 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
     for (int r = 0; r < E; ++r) win[r] = __ldg(reinterpret_cast<const float2*>(a.tables + TB::WIN) + t + T * r);
     constexpr bool REGTW = (C::T == 32 && C::NP == 2 && C::R1 == 32 && C::R2 == 32);
     TwBase twb;
-    float2 hw_t = make_float2(0.f, 0.f);
-    if constexpr (REGTW) {
-        twb = load_tw_base<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);
-        hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);   /* (cos, sin)(2 pi t/N)/2 */
-    }
+    if constexpr (REGTW) twb = load_tw_base<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);
+    const float2 hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);   /* (cos, sin)(2 pi t/N)/2, t < T <= M/2 */
 
     const int F = a.frames;
     const long long total = (long long)a.num_groups * F;              /* num_groups carries the batch */
@@ -458,7 +455,9 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
                 team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
                 team_store_natural<C>(v, xb, t);
                 team_sync<T>(team);
-                split_and_store<C, OUT>(xb, s_post, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+                /* computed split twiddles help at fft_size 4096 (2.94 -> 2.86 ms) and hurt at 8192 (3.24 -> 3.75 ms) */
+                if constexpr (C::M <= 2048) split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+                else split_and_store<C, OUT>(xb, s_post, t, a.out, ((long long)b * F + frame) * a.out_pitch);
                 team_sync<T>(team);                                    /* xb is reused by the next frame */
             }
         }
