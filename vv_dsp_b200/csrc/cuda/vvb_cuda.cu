@@ -186,8 +186,8 @@ using Cfg256m = Cfg<256, 8, 8, 8, 4>;       /* T = 32: whole-warp team for the m
 using Cfg512 = Cfg<512, 32, 32, 16>;
 using Cfg512m = Cfg<512, 16, 16, 16, 2>;    /* T = 32 */
 using Cfg1024 = Cfg<1024, 32, 32, 32>;
-using Cfg2048 = Cfg<2048, 16, 16, 16, 8>;
-using Cfg4096 = Cfg<4096, 16, 16, 16, 16>;
+using Cfg2048 = Cfg<2048, 32, 32, 8, 8>;      /* T = 64 (two warps per frame), E = 32 */
+using Cfg4096 = Cfg<4096, 32, 32, 16, 8>;     /* T = 128, E = 32 */
 template <class C> struct Teams { static constexpr int G = (C::T >= 256) ? 2 : 256 / C::T; };
 
 template <class C> static constexpr size_t smem_fwd() { return sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3 + C::POST + 1) + 2 * Teams<C>::G * C::XBUF); }
@@ -316,8 +316,8 @@ template <class C> struct March;
 template <> struct March<Cfg256m> { static constexpr int G = 8, MINB = 3; };    /* 256 thr, <= 80 regs */
 template <> struct March<Cfg512m> { static constexpr int G = 8, MINB = 2; };    /* 256 thr, <= 128 regs */
 template <> struct March<Cfg1024> { static constexpr int G = 8, MINB = 1; };   /* 256 thr, 232 regs, 1 CTA/SM */
-template <> struct March<Cfg2048> { static constexpr int G = 2, MINB = 2; };   /* 256 thr, 2 CTAs/SM */
-template <> struct March<Cfg4096> { static constexpr int G = 2, MINB = 1; };   /* 512 thr, 1 CTA/SM */
+template <> struct March<Cfg2048> { static constexpr int G = 4, MINB = 1; };   /* 256 thr, 1 CTA/SM, up to 255 regs */
+template <> struct March<Cfg4096> { static constexpr int G = 2, MINB = 1; };   /* 256 thr, 1 CTA/SM, up to 255 regs */
 
 template <class C, int S, int OUT> static int launch_fwd_march_t(vvb_engine* e, FwdArgs a, void* stream)
 {
