@@ -36,6 +36,7 @@
 #include "vv_dsp/vv_dsp_types.h"
 #include "vv_dsp/spectral/stft.h"
 #include "vv_dsp/spectral/fft.h"
+#include "vv_dsp/features/mel.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -105,6 +106,19 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_inverse(
  * (= reconstruct-all-frames + the caller-side divide of tools/dump_stft_roundtrip.c:50-54). */
 VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_istft(vv_dsp_stft* h, const vv_dsp_cpx* half_spectra, size_t frames,
                                                  vv_dsp_real* out, size_t n_out);
+
+/* STFT -> power -> mel filterbank -> log for a whole batch:
+ * out[b][f][m] = logf(sum_k |X_bf[k]|^2 W[m][k] + log_epsilon), i.e. vv_dsp_compute_log_mel_spectrogram
+ * applied to the power output of vv_dsp_stft_batch_forward.  filterbank_weights: HOST, dense
+ * [n_mels][fft_size/2+1] as produced by vv_dsp_mel_filterbank_create.  out: [batch][frames][n_mels]
+ * float32.  Two kernels (power, then an HBM-bound log-mel kernel) chained on the device per chunk of
+ * signals; the power spectrogram only ever lives in a bounded device scratch buffer. */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_logmel(
+    vv_dsp_stft* h,
+    const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch, size_t n, size_t signal_pitch,
+    vv_dsp_frame_convention convention,
+    const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
+    vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames);
 
 /* Many transforms through one plan: `batch` contiguous transforms,
  * C2C: cpx[batch][n] -> cpx[batch][n];  R2C: real[batch][n] -> cpx[batch][n/2+1];  C2R: the reverse.

@@ -5,5 +5,6 @@
 #include "vv_dsp/core.h"
 #include "vv_dsp/window.h"
 #include "vv_dsp/spectral.h"
+#include "vv_dsp/features/mel.h"
 #include "vv_dsp/b200.h"
 #endif

@@ -190,4 +190,6 @@ static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_floa
 static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }

@@ -141,6 +141,29 @@ def check_fft_batch(lib, oracle, sizes, batch=5):
         assert np.all(R[:, -1].imag == 0) if n % 2 == 0 and n > 1 else True
 
 
+def check_mel(lib, oracle, nfft=2048, hop=512, n_mels=80, sr=48000.0, n=30000, batch=3):
+    """mel filterbank (host, bit-exact), log-mel on given power (sum order = reference's; logf within 2 ulp),
+    and the batched STFT -> log-mel chain against the oracle's process -> power -> log-mel."""
+    from vv_dsp_b200 import log_mel_spectrogram, mel_filterbank
+    st, w = mel_filterbank(nfft, n_mels, sr, 0.0, sr / 2, lib=lib)
+    so, wo = oracle.mel_filterbank(nfft, n_mels, sr, 0.0, sr / 2)
+    assert st == so == 0 and w.tobytes() == wo.tobytes()
+    for bad in [(0, 10, sr, 0.0, 100.0), (512, 0, sr, 0.0, 100.0), (512, 300, sr, 0.0, 100.0), (512, 10, sr, 0.0, sr),
+                (512, 10, sr, 100.0, 50.0), (512, 10, sr, 0.0, 8000.0, 1)]:
+        assert mel_filterbank(*bad, lib=lib)[0] == oracle.mel_filterbank(*bad)[0], bad
+    p = np.random.default_rng(1).uniform(0, 10, (70, nfft // 2 + 1)).astype(np.float32)
+    a, b = log_mel_spectrogram(p, w, 1e-10, lib=lib), oracle.log_mel(p, wo, 1e-10)
+    assert np.abs(a - b).max() <= 1e-6                                # same float32 sums; only logf may differ in the last ulp
+    x = np.stack([noise(60 + i, n) for i in range(batch)])
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        for conv in ("valid", "center"):
+            lm = h.batch_logmel(x, w, 1e-10, conv)
+            ref = np.stack([oracle.log_mel(np.abs(oracle.stft(x[i], nfft, hop, convention=conv)) ** 2, wo, 1e-10) for i in range(batch)])
+            assert lm.shape == ref.shape
+            e, er = np.exp(lm.astype(np.float64)), np.exp(ref.astype(np.float64))
+            assert np.abs(e - er).max() <= 1e-4 * er.max(), np.abs(e - er).max() / er.max()
+
+
 def check_status_codes(lib):
     """Return codes of the reference boundary (SURVEY.md section 4 'lifecycle/validation')."""
     import ctypes as C

@@ -75,6 +75,11 @@ def test_fft_execute_batch(emu, oracle):
     pc.check_fft_batch(emu, oracle, [1, 8, 100, 128, 256, 1024])
 
 
+def test_mel(emu, oracle):
+    pc.check_mel(emu, oracle, 2048, 512, 80, 48000.0, 12000)
+    pc.check_mel(emu, oracle, 512, 128, 26, 16000.0, 6000)
+
+
 def test_golden_slices(emu, golden):
     pc.check_golden_slices(emu, golden)
 

@@ -160,6 +160,13 @@ def test_fft_execute_batch(lib, oracle):
     assert float((y - ref).abs().max() / ref.abs().max()) < 2e-6
 
 
+def test_mel(lib, oracle):
+    pc.check_mel(lib, oracle, 2048, 512, 80, 48000.0, 60000, batch=5)
+    pc.check_mel(lib, oracle, 1024, 256, 40, 44100.0, 30000)
+    pc.check_mel(lib, oracle, 4096, 1024, 128, 48000.0, 60000)
+    pc.check_mel(lib, oracle, 400, 160, 40, 16000.0, 16000)          # non power of two fft_size (direct path)
+
+
 def test_golden_slices_of_the_real_reference(lib, golden):
     pc.check_golden_slices(lib, golden)
 

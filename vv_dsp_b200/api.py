@@ -69,6 +69,14 @@ class Library:
                                                 C.POINTER(_sz)]),
         "vv_dsp_stft_batch_inverse": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, _vp, C.c_int, _sz, _sz, C.c_int]),
         "vv_dsp_stft_istft": (C.c_int, [_vp, _vp, _sz, _vp, _sz]),
+        "vv_dsp_hz_to_mel": (C.c_float, [C.c_float]),
+        "vv_dsp_mel_to_hz": (C.c_float, [C.c_float]),
+        "vv_dsp_mel_filterbank_create": (C.c_int, [_sz, _sz, C.c_float, C.c_float, C.c_float, C.c_int, C.POINTER(C.POINTER(C.c_float)),
+                                                   C.POINTER(_sz), C.POINTER(_sz)]),
+        "vv_dsp_mel_filterbank_free": (None, [C.POINTER(C.c_float), _sz]),
+        "vv_dsp_compute_log_mel_spectrogram": (C.c_int, [_vp, _sz, _sz, _vp, _sz, C.c_float, _vp]),
+        "vv_dsp_stft_batch_logmel": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, _vp, _sz, C.c_float, _vp, C.c_int,
+                                               C.POINTER(_sz)]),
         "vv_dsp_b200_version": (C.c_char_p, []),
         "vv_dsp_b200_last_error": (C.c_char_p, []),
         "vv_dsp_b200_kernel_launches": (C.c_ulonglong, []),
@@ -171,6 +179,31 @@ def overlap_add(frame, output, hop_len, frame_index, lib: Library | None = None)
     return lib.vv_dsp_overlap_add(_ptr(frame), _ptr(output), output.size, frame.size, hop_len, frame_index)
 
 
+def mel_filterbank(n_fft, n_mels, sample_rate, fmin, fmax, variant=0, lib: Library | None = None):
+    """vv_dsp_mel_filterbank_create -> (status, float32[n_mels, n_fft/2+1] or None)"""
+    lib = lib or default_library()
+    w = C.POINTER(C.c_float)()
+    nf, fl = _sz(0), _sz(0)
+    st = lib.vv_dsp_mel_filterbank_create(n_fft, n_mels, sample_rate, fmin, fmax, variant, C.byref(w), C.byref(nf), C.byref(fl))
+    if st != 0:
+        return st, None
+    out = np.ctypeslib.as_array(w, shape=(nf.value, fl.value)).copy()
+    lib.vv_dsp_mel_filterbank_free(w, nf)
+    return st, out
+
+
+def log_mel_spectrogram(power, weights, log_epsilon, lib: Library | None = None):
+    """vv_dsp_compute_log_mel_spectrogram: power [frames, bins], weights [n_mels, bins] (host) -> [frames, n_mels]"""
+    lib = lib or default_library()
+    power = np.ascontiguousarray(power, np.float32)
+    weights = np.ascontiguousarray(weights, np.float32)
+    out = np.empty((power.shape[0], weights.shape[0]), np.float32)
+    st = lib.vv_dsp_compute_log_mel_spectrogram(_ptr(power), power.shape[0], power.shape[1], _ptr(weights), weights.shape[0],
+                                                log_epsilon, _ptr(out))
+    _check(lib, st, "vv_dsp_compute_log_mel_spectrogram")
+    return out
+
+
 # ----------------------------------------------------------------------------- STFT handle
 class Stft:
     """vv_dsp_stft handle: create / process / reconstruct / spectrogram + the batched extension."""
@@ -266,6 +299,29 @@ class Stft:
                                                 DEVICE if _is_device(out) else HOST, 0, C.byref(nf))
         _check(self.lib, st, "vv_dsp_stft_batch_forward")
         assert nf.value == frames
+        return out
+
+    def batch_logmel(self, signals, weights, log_epsilon=1e-10, convention="valid", out=None):
+        """STFT -> power -> mel -> log: signals [batch, n] (numpy or torch CUDA), weights [n_mels, bins] numpy"""
+        dev_in = _is_device(signals)
+        if not dev_in:
+            signals = np.ascontiguousarray(signals, np.float32)
+        weights = np.ascontiguousarray(weights, np.float32)
+        assert weights.shape[1] == self.bins
+        batch, n = int(signals.shape[0]), int(signals.shape[1])
+        pitch = int(signals.stride(0)) if dev_in else n
+        frames = self.num_frames(n, convention)
+        if out is None:
+            if dev_in:
+                import torch
+                out = torch.empty((batch, frames, weights.shape[0]), device=signals.device, dtype=torch.float32)
+            else:
+                out = np.empty((batch, frames, weights.shape[0]), np.float32)
+        nf = _sz(0)
+        st = self.lib.vv_dsp_stft_batch_logmel(self._h, _ptr(signals), DEVICE if dev_in else HOST, batch, n, pitch,
+                                               CONVENTIONS[convention], _ptr(weights), weights.shape[0], log_epsilon,
+                                               _ptr(out), DEVICE if _is_device(out) else HOST, C.byref(nf))
+        _check(self.lib, st, "vv_dsp_stft_batch_logmel")
         return out
 
     def batch_inverse(self, spectra, n_out, normalise=True, out=None):

@@ -654,6 +654,27 @@ extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, si
     return vvb_stft_inverse_frames(e->real, (const vvb_cpx*)d_in, batch, bins, (float*)d_out, stream);   /* C2R */
 }
 
+/* ---------------------------------------------------------------------- log-mel */
+extern "C" int vvb_logmel(const float* d_power, size_t frames, size_t bins, size_t power_pitch, const int* d_meta, const float* d_w,
+                          size_t n_mels, float eps, float* d_out, void* stream)
+{
+    if (!d_power || !d_meta || !d_w || !d_out) return fail(1, "vvb_logmel", "null");
+    if (frames == 0 || n_mels == 0) return 0;
+    if (bins > 0x7fffffffu || n_mels > 0x7fffffffu) return fail(2, "vvb_logmel", "size");
+#ifndef VVB_EMU
+    if (int st = vvb_device_ready()) return st;
+#endif
+    MelArgs a;
+    a.power = d_power; a.pitch = (long long)power_pitch; a.frames = (long long)frames; a.bins = (int)bins; a.n_mels = (int)n_mels;
+    a.meta = d_meta; a.w = d_w; a.eps = eps; a.out = d_out;
+    static int per_sm = -1;
+    const size_t smem = sizeof(float) * MEL_KC * 33;
+    if (per_sm < 0) per_sm = rt_blocks_per_sm(logmel_kernel, 256, smem);
+    if (per_sm == 0) return fail(4, "logmel_kernel", "does not fit on this device");
+    VVB_LAUNCH(logmel_kernel, persistent_grid((long long)((frames + 31) / 32), per_sm, rt_num_sms()), 256, smem, stream, a);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- FP32 peak probe */
 /* Measures the FP32 FMA throughput the roofline is quoted against: 16 independent dependent-FMA
  * chains per thread, scalar FFMA or packed FFMA2.  Diagnostics only (bench.py's roofline_fp32). */

@@ -145,4 +145,85 @@ __global__ void overlap_add_kernel(const OlaArgs a)
     }
 }
 
+/* ------------------------------------------------------------------ log-mel */
+/* out[f][m] = logf(sum_k power[f][k] W[m][k] + eps), the reference's src/features/mel.c:204-245, with the
+ * filterbank stored sparsely (each triangular filter is non-zero on one contiguous bin range).
+ * A CTA takes a tile of 32 frames: the power rows are loaded coalesced (lanes along bins) and parked
+ * TRANSPOSED in shared memory, Ps[bin][frame] with a row pitch of 33, so that in the reduction lane = frame
+ * reads conflict-free while the weight is one broadcast load for the whole warp.  Warp w owns bands
+ * m = w, w+8, ...; every band sum is accumulated by one thread in ascending bin order with a separate
+ * multiply and add (no FMA contraction), i.e. bit-for-bit the reference's float32 sum.  Results are
+ * transposed back through shared memory and stored coalesced.  HBM-bound: reads each power value once. */
+struct MelArgs {
+    const float* power; long long pitch; long long frames;
+    int bins, n_mels;
+    const int* meta;         /* lo[n_mels] | len[n_mels] | off[n_mels] */
+    const float* w;
+    float eps;
+    float* out;              /* [frames][n_mels] */
+};
+constexpr int MEL_KC = 512;       /* bins per shared-memory chunk: 66 KB, three CTAs per SM */
+constexpr int MEL_BG = 128;       /* bands per pass: 8 warps x 16 accumulators */
+
+__global__ void __launch_bounds__(256) logmel_kernel(const MelArgs a)
+{
+#ifdef VVB_EMU
+    float* Ps = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float Ps[];
+#endif
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long ntiles = (a.frames + 31) / 32;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long f0 = tile * 32;
+        const int nf = (int)min((long long)32, a.frames - f0);
+        for (int mg = 0; mg < a.n_mels; mg += MEL_BG) {
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            for (int k0 = 0; k0 < a.bins; k0 += MEL_KC) {
+                const int kc = min(MEL_KC, a.bins - k0);
+                __syncthreads();                                   /* the previous chunk / output staging is consumed */
+                for (int r = warp; r < 32; r += 8) {
+                    const float* row = a.power + (f0 + r) * a.pitch + k0;
+                    for (int kb = lane; kb < kc; kb += 32 * 8) {       /* 8 independent loads in flight per lane */
+                        float tmp[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int k = kb + 32 * u;
+                            tmp[u] = (r < nf && k < kc) ? __ldg(row + k) : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int k = kb + 32 * u;
+                            if (k < kc) Ps[k * 33 + r] = tmp[u];
+                        }
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int m = mg + warp + 8 * j;
+                    if (m < a.n_mels) {                            /* warp-uniform */
+                        const int lo = __ldg(a.meta + m), len = __ldg(a.meta + a.n_mels + m), off = __ldg(a.meta + 2 * a.n_mels + m);
+                        const int ka = max(lo, k0), kb = min(lo + len, k0 + kc);
+                        for (int k = ka; k < kb; ++k)
+                            acc[j] = __fadd_rn(acc[j], __fmul_rn(Ps[(k - k0) * 33 + lane], __ldg(a.w + off + (k - lo))));
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int m = mg + warp + 8 * j;
+                if (m < a.n_mels) Ps[(m - mg) * 33 + lane] = logf(acc[j] + a.eps);
+            }
+            __syncthreads();
+            const int nb = min(MEL_BG, a.n_mels - mg);
+            for (int r = warp; r < nf; r += 8)
+                for (int mm = lane; mm < nb; mm += 32) a.out[(f0 + r) * a.n_mels + mg + mm] = Ps[mm * 33 + r];
+        }
+    }
+}
+
 }  // namespace vvb

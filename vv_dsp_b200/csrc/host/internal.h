@@ -1,0 +1,11 @@
+/* internal.h -- helpers shared between the C99 host translation units (not part of the ABI) */
+#ifndef VVDSP_B200_HOST_INTERNAL_H
+#define VVDSP_B200_HOST_INTERNAL_H
+#include <stddef.h>
+
+/* device-resident sparse mel filterbank: meta = lo | len | off per band, packed non-zero weights */
+typedef struct mel_device { int* d_meta; float* d_w; } mel_device;
+int vvdsp_internal_mel_device_build(const float* dense_weights, size_t n_mels, size_t bins, void* stream, mel_device* md);
+void vvdsp_internal_mel_device_free(mel_device* md);
+
+#endif

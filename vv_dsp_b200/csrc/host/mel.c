@@ -1,0 +1,140 @@
+/*
+ * mel.c -- mel filterbank (host) and log-mel spectrogram (GPU) behind the reference's API
+ * (include/vv_dsp/features/mel.h:12-66, src/features/mel.c:14-245), plus the batched
+ * STFT -> log-mel entry point of include/vv_dsp/b200.h.  SURVEY.md section 8f, rank 2.
+ *
+ * The filterbank is built on the host with the reference's float32 formulas, so it is
+ * bit-identical: HTK scale 2595 log10f(1 + hz/700), n_mels + 2 points equally spaced in mel
+ * (start + step*i), lower-bound search of each edge in the bin frequencies k*sr/n_fft, rising
+ * slope on [left, center), falling on [center, right), every filter divided by its sum.
+ * The log-mel reduction runs on the GPU (csrc/cuda/vvb_direct_kernels.cuh: logmel_kernel).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "vv_dsp/b200.h"
+#include "vv_dsp/features/mel.h"
+#include "vvb200_cuda.h"
+#include "internal.h"
+
+vv_dsp_real vv_dsp_hz_to_mel(vv_dsp_real hz) { return hz < 0.0f ? 0.0f : 2595.0f * log10f(1.0f + hz / 700.0f); }
+
+vv_dsp_real vv_dsp_mel_to_hz(vv_dsp_real mel) { return mel < 0.0f ? 0.0f : 700.0f * (powf(10.0f, mel / 2595.0f) - 1.0f); }
+
+static size_t first_not_below(const float* v, size_t n, float x)
+{
+    size_t a = 0, b = n;
+    while (a < b) {
+        const size_t mid = a + (b - a) / 2;
+        if (v[mid] < x) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+
+vv_dsp_status vv_dsp_mel_filterbank_create(size_t n_fft, size_t n_mels, vv_dsp_real sample_rate, vv_dsp_real fmin,
+                                           vv_dsp_real fmax, vv_dsp_mel_variant variant, vv_dsp_real** out_filterbank_weights,
+                                           size_t* out_num_filters, size_t* out_filter_len)
+{
+    size_t bins, npts, i, m, k;
+    float *fb, *edges, *freqs, mel_lo, mel_hi, step;
+    if (!out_filterbank_weights || !out_num_filters || !out_filter_len) return VV_DSP_ERROR_NULL_POINTER;
+    if (n_fft == 0 || n_mels == 0 || sample_rate <= 0.0f || fmin < 0.0f || fmax <= fmin) return VV_DSP_ERROR_INVALID_SIZE;
+    if (fmax > sample_rate / 2.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
+    if (variant != VV_DSP_MEL_VARIANT_HTK) return VV_DSP_ERROR_OUT_OF_RANGE;
+    bins = n_fft / 2 + 1;
+    if (n_mels >= bins) return VV_DSP_ERROR_INVALID_SIZE;
+    npts = n_mels + 2;
+    fb = (float*)calloc(n_mels * bins, sizeof(float));
+    edges = (float*)malloc(npts * sizeof(float));
+    freqs = (float*)malloc(bins * sizeof(float));
+    if (!fb || !edges || !freqs) { free(fb); free(edges); free(freqs); return VV_DSP_ERROR_INTERNAL; }
+    mel_lo = vv_dsp_hz_to_mel(fmin);
+    mel_hi = vv_dsp_hz_to_mel(fmax);
+    step = (mel_hi - mel_lo) / (float)(npts - 1);
+    for (i = 0; i < npts; ++i) edges[i] = vv_dsp_mel_to_hz(mel_lo + step * (float)i);
+    for (k = 0; k < bins; ++k) freqs[k] = (float)k * sample_rate / (float)n_fft;
+    for (m = 0; m < n_mels; ++m) {
+        const float left = edges[m], center = edges[m + 1], right = edges[m + 2];
+        const size_t il = first_not_below(freqs, bins, left), ic = first_not_below(freqs, bins, center),
+                     ir = first_not_below(freqs, bins, right);
+        float* w = fb + m * bins;
+        float total = 0.0f;
+        for (k = il; k < ic && k < bins; ++k) w[k] = (freqs[k] - left) / (center - left);
+        for (k = ic; k < ir && k < bins; ++k) w[k] = (right - freqs[k]) / (right - center);
+        for (k = 0; k < bins; ++k) total += w[k];
+        if (total > 0.0f) for (k = 0; k < bins; ++k) w[k] /= total;
+    }
+    free(edges); free(freqs);
+    *out_filterbank_weights = fb; *out_num_filters = n_mels; *out_filter_len = bins;
+    return VV_DSP_OK;
+}
+
+void vv_dsp_mel_filterbank_free(vv_dsp_real* filterbank_weights, size_t n_mels)
+{
+    (void)n_mels;
+    free(filterbank_weights);
+}
+
+/* dense [n_mels][bins] -> device-resident sparse form: meta = lo | len | off, packed non-zero runs */
+void vvdsp_internal_mel_device_free(mel_device* md) { vvb_free(md->d_meta); vvb_free(md->d_w); md->d_meta = NULL; md->d_w = NULL; }
+
+int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t bins, void* stream, mel_device* md)
+{
+    int* meta = (int*)malloc(3 * n_mels * sizeof(int));
+    float* packed = (float*)malloc((n_mels * bins ? n_mels * bins : 1) * sizeof(float));
+    size_t m, k, total = 0;
+    int st;
+    md->d_meta = NULL; md->d_w = NULL;
+    if (!meta || !packed) { free(meta); free(packed); return 4; }
+    for (m = 0; m < n_mels; ++m) {
+        const float* w = weights + m * bins;
+        size_t lo = bins, hi = 0;
+        for (k = 0; k < bins; ++k) if (w[k] != 0.0f) { if (lo == bins) lo = k; hi = k + 1; }
+        if (lo == bins) { lo = 0; hi = 0; }
+        meta[m] = (int)lo; meta[n_mels + m] = (int)(hi - lo); meta[2 * n_mels + m] = (int)total;
+        memcpy(packed + total, w + lo, (hi - lo) * sizeof(float));
+        total += hi - lo;
+    }
+    st = vvb_malloc((void**)&md->d_meta, 3 * n_mels * sizeof(int));
+    if (!st) st = vvb_malloc((void**)&md->d_w, (total ? total : 1) * sizeof(float));
+    if (!st) st = vvb_memcpy_h2d(md->d_meta, meta, 3 * n_mels * sizeof(int), stream);
+    if (!st && total) st = vvb_memcpy_h2d(md->d_w, packed, total * sizeof(float), stream);
+    if (!st) st = vvb_stream_sync(stream);          /* the host staging arrays die below */
+    free(meta); free(packed);
+    if (st) vvdsp_internal_mel_device_free(md);
+    return st;
+}
+
+static vv_dsp_status to_status(int st)
+{
+    if (st == 0) return VV_DSP_OK;
+    return (st >= 1 && st <= 6 && st != 5) ? (vv_dsp_status)st : VV_DSP_ERROR_INTERNAL;
+}
+
+vv_dsp_status vv_dsp_compute_log_mel_spectrogram(const vv_dsp_real* power_spectrogram, size_t num_frames, size_t n_fft_bins,
+                                                 const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
+                                                 vv_dsp_real* out_log_mel_spectrogram)
+{
+    mel_device md;
+    float *d_p = NULL, *d_o = NULL;
+    void* stream = NULL;
+    int st;
+    if (!power_spectrogram || !filterbank_weights || !out_log_mel_spectrogram) return VV_DSP_ERROR_NULL_POINTER;
+    if (num_frames == 0 || n_fft_bins == 0 || n_mels == 0) return VV_DSP_ERROR_INVALID_SIZE;
+    if (log_epsilon < 0.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
+    md.d_meta = NULL; md.d_w = NULL;
+    st = vvb_device_ready();                         /* no CUDA device -> UNSUPPORTED, never a CPU computation */
+    if (st) return to_status(st);
+    st = vvb_stream_create(&stream);
+    if (!st) st = vvdsp_internal_mel_device_build(filterbank_weights, n_mels, n_fft_bins, stream, &md);
+    if (!st) st = vvb_malloc((void**)&d_p, num_frames * n_fft_bins * sizeof(float));
+    if (!st) st = vvb_malloc((void**)&d_o, num_frames * n_mels * sizeof(float));
+    if (!st) st = vvb_memcpy_h2d(d_p, power_spectrogram, num_frames * n_fft_bins * sizeof(float), stream);
+    if (!st) st = vvb_logmel(d_p, num_frames, n_fft_bins, n_fft_bins, md.d_meta, md.d_w, n_mels, log_epsilon, d_o, stream);
+    if (!st) st = vvb_memcpy_d2h(out_log_mel_spectrogram, d_o, num_frames * n_mels * sizeof(float), stream);
+    if (stream) { int s2 = vvb_stream_sync(stream); if (!st) st = s2; }
+    vvb_free(d_p); vvb_free(d_o); vvdsp_internal_mel_device_free(&md);
+    if (stream) vvb_stream_destroy(stream);
+    return to_status(st);
+}
+

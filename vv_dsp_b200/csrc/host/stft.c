@@ -16,6 +16,7 @@
 #include "vv_dsp/core.h"
 #include "vv_dsp/window.h"
 #include "vvb200_cuda.h"
+#include "internal.h"
 
 #define NORM_CACHE 4
 #define NSLOT 4            /* slots 0,1: analysis (host -> device staging); slots 2,3: synthesis (device -> host) */
@@ -45,6 +46,9 @@ struct vv_dsp_stft {
     int async;
     struct { const char* lo; const char* hi; void* ev; int valid; } dep[NDEP];
     int dep_next;
+    /* log-mel chain: power scratch (grown on demand) and the last filterbank in device-sparse form */
+    float* d_mel_scratch; size_t mel_scratch_bytes;
+    mel_device mel; const float* mel_key_ptr; size_t mel_key_n; unsigned long long mel_key_hash;
     /* 1/sum(w^2) tables per frame count: [head nfft-hop | mid hop | tail nfft-hop] */
     struct { size_t frames; float* d_tab; int used; } norm[NORM_CACHE];
     int norm_next;
@@ -72,6 +76,7 @@ static void handle_free(vv_dsp_stft* h)
         if (h->slot[i].stream) vvb_stream_destroy(h->slot[i].stream);
     }
     for (i = 0; i < NORM_CACHE; ++i) vvb_free(h->norm[i].d_tab);
+    vvb_free(h->d_mel_scratch); vvdsp_internal_mel_device_free(&h->mel);
     for (i = 0; i < NDEP; ++i) if (h->dep[i].ev) vvb_event_destroy(h->dep[i].ev);
     vvb_host_free(h->h_in); vvb_host_free(h->h_spec); vvb_host_free(h->h_frame);
     vvb_free(h->d_in); vvb_free(h->d_spec); vvb_free(h->d_frame);
@@ -463,4 +468,76 @@ vv_dsp_status vv_dsp_stft_spectrogram(vv_dsp_stft* h, const vv_dsp_real* signal,
     }
     free(half);
     return st;
+}
+
+/* -------------------------------------------------- STFT -> power -> log-mel (include/vv_dsp/b200.h) */
+/* Chunks of signals whose power spectrogram fits a bounded device scratch; per chunk the fused power
+ * kernel and the HBM-bound log-mel kernel run back to back on one stream. */
+vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch,
+                                       size_t n, size_t signal_pitch, vv_dsp_frame_convention convention,
+                                       const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
+                                       vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames)
+{
+    const size_t scratch_target = (size_t)768 << 20;
+    size_t frames, per_signal, cs, done, i;
+    float *d_power, *d_x = NULL, *d_o = NULL;
+    unsigned long long hash = 1469598103934665603ull;
+    void* stream;
+    int st = 0, pad;
+    if (!h || !signals || !filterbank_weights || !out) return VV_DSP_ERROR_NULL_POINTER;
+    if ((unsigned)convention > 3u || (unsigned)signals_space > 1u || (unsigned)out_space > 1u) return VV_DSP_ERROR_OUT_OF_RANGE;
+    if (n_mels == 0) return VV_DSP_ERROR_INVALID_SIZE;
+    if (log_epsilon < 0.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
+    if (signal_pitch == 0) signal_pitch = n;
+    if (signal_pitch < n) return VV_DSP_ERROR_INVALID_SIZE;
+    frames = vv_dsp_stft_num_frames(h, n, convention);
+    if (out_frames) *out_frames = frames;
+    if (batch == 0 || frames == 0) return VV_DSP_OK;
+    pad = (convention == VV_DSP_FRAMES_CENTER) ? VVB_PAD_REFLECT_CENTER : VVB_PAD_ZERO;
+    per_signal = frames * h->bins * sizeof(float);
+    cs = scratch_target / per_signal; if (cs < 1) cs = 1; if (cs > batch) cs = batch;
+    stream = h->stream;
+    /* the device-sparse filterbank is cached per handle; fingerprint = pointer, size and a strided FNV-1a hash */
+    for (i = 0; i < n_mels * h->bins; i += 13) {
+        unsigned int bits; memcpy(&bits, filterbank_weights + i, sizeof(bits));
+        hash = (hash ^ bits) * 1099511628211ull;
+    }
+    if (!h->mel.d_meta || h->mel_key_ptr != filterbank_weights || h->mel_key_n != n_mels || h->mel_key_hash != hash) {
+        st = vvb_stream_sync(stream);
+        vvdsp_internal_mel_device_free(&h->mel);
+        if (!st) st = vvdsp_internal_mel_device_build(filterbank_weights, n_mels, h->bins, stream, &h->mel);
+        h->mel_key_ptr = filterbank_weights; h->mel_key_n = n_mels; h->mel_key_hash = hash;
+    }
+    if (!st && h->mel_scratch_bytes < cs * per_signal) {
+        st = vvb_stream_sync(stream);
+        vvb_free(h->d_mel_scratch); h->d_mel_scratch = NULL; h->mel_scratch_bytes = 0;
+        if (!st) st = vvb_malloc((void**)&h->d_mel_scratch, cs * per_signal);
+        if (!st) h->mel_scratch_bytes = cs * per_signal;
+    }
+    d_power = h->d_mel_scratch;
+    if (!st && signals_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&d_x, cs * (n ? n : 1) * sizeof(float));
+    if (!st && out_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&d_o, cs * frames * n_mels * sizeof(float));
+    for (done = 0; done < batch && !st; done += cs) {
+        const size_t nb = (batch - done < cs) ? batch - done : cs;
+        const float* x_dev = signals + done * signal_pitch;
+        size_t xp = signal_pitch;
+        float* o_dev = out + done * frames * n_mels;
+        if (signals_space == VV_DSP_MEM_HOST) {
+            if (n) st = vvb_memcpy2d_h2d(d_x, n * sizeof(float), signals + done * signal_pitch, signal_pitch * sizeof(float),
+                                         n * sizeof(float), nb, stream);
+            x_dev = d_x; xp = n ? n : 1;
+        }
+        if (out_space == VV_DSP_MEM_HOST) o_dev = d_o;
+        if (!st) st = vvb_stft_forward(h->eng, x_dev, nb, n, xp, frames, pad, VVB_OUT_POWER, d_power, h->bins, stream);
+        if (!st) st = vvb_logmel(d_power, nb * frames, h->bins, h->bins, h->mel.d_meta, h->mel.d_w, n_mels, log_epsilon, o_dev, stream);
+        if (!st && out_space == VV_DSP_MEM_HOST)
+            st = vvb_memcpy_d2h(out + done * frames * n_mels, d_o, nb * frames * n_mels * sizeof(float), stream);
+        if (!st && signals_space == VV_DSP_MEM_HOST) st = vvb_stream_sync(stream);   /* staging buffer reuse */
+    }
+    /* device-resident calls only enqueue (scratch and filterbank live in the handle); host buffers: synchronous */
+    if (signals_space == VV_DSP_MEM_HOST || out_space == VV_DSP_MEM_HOST) {
+        int s2 = vvb_stream_sync(stream); if (!st) st = s2;
+        vvb_free(d_x); vvb_free(d_o);
+    }
+    return map_status(st);
 }
