@@ -37,4 +37,4 @@ with Stft(nfft, hop, "hann") as h:
     ms_pow = e0.elapsed_time(e1) / 5
 print(json.dumps({"workload": f"STFT->log-mel, {B} x {n} samples, nfft={nfft} hop={hop}, {n_mels} mels", "ms": ms,
                   "Msamples_per_s": B * n / ms / 1e3, "power_kernel_ms": ms_pow, "logmel_and_overhead_ms": ms - ms_pow,
-                  "note": "includes per-call scratch allocation and filterbank upload; power goes through a 768 MB scratch"}))
+                  "note": "power goes through a 768 MB device scratch in chunks; scratch and the device filterbank are cached in the handle"}))

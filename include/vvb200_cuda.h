@@ -70,9 +70,11 @@ int vvb_stft_inverse_frames(vvb_engine* e, const vvb_cpx* d_spec, size_t count, 
                             float* d_frames, void* stream);
 
 /* ---- log-mel: d_out[f][m] = logf(sum_{k in [lo[m], lo[m]+len[m])} d_power[f][k] * w[off[m] + k - lo[m]] + eps).
- * d_meta: int[3*n_mels] = lo | len | off; d_w: packed non-zero weights, ascending k per band. */
+ * d_meta: int[3*n_mels] = lo | len | off, followed by the slot-ordered group tables csrc/host/mel.c builds;
+ * d_w: packed non-zero weights, ascending k per band, followed by the same runs in zero-padded groups of four.
+ * n_groups: number of four-tap groups in those tables (0 = tables absent: only the plain kernel is used). */
 int vvb_logmel(const float* d_power, size_t frames, size_t bins, size_t power_pitch, const int* d_meta, const float* d_w,
-               size_t n_mels, float eps, float* d_out, void* stream);
+               size_t n_mels, size_t n_groups, float eps, float* d_out, void* stream);
 
 /* ---- FFT engine (plan API): type 0 C2C, 1 R2C, 2 C2R; dir +1 / -1 */
 int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine** out);

@@ -154,6 +154,14 @@ def check_mel(lib, oracle, nfft=2048, hop=512, n_mels=80, sr=48000.0, n=30000, b
     p = np.random.default_rng(1).uniform(0, 10, (70, nfft // 2 + 1)).astype(np.float32)
     a, b = log_mel_spectrogram(p, w, 1e-10, lib=lib), oracle.log_mel(p, wo, 1e-10)
     assert np.abs(a - b).max() <= 1e-6                                # same float32 sums; only logf may differ in the last ulp
+    # every tile shape of the log-mel kernel: 32/16/8/4 frames per tile, more than 128 bands (two passes),
+    # ragged last tile, a single frame
+    for nf2, nm2, frames2 in ((256, 40, 100), (512, 200, 67), (4096, 128, 21), (8192, 64, 9), (2048, 150, 1), (16384, 30, 5)):
+        st2, w2 = mel_filterbank(nf2, nm2, sr, 20.0, sr / 2, lib=lib)
+        assert st2 == 0
+        p2 = np.random.default_rng(nf2).uniform(0, 3, (frames2, nf2 // 2 + 1)).astype(np.float32)
+        a2, b2 = log_mel_spectrogram(p2, w2, 1e-10, lib=lib), oracle.log_mel(p2, w2, 1e-10)
+        assert a2.shape == b2.shape and np.abs(a2 - b2).max() <= 1e-6, (nf2, nm2, frames2)
     x = np.stack([noise(60 + i, n) for i in range(batch)])
     with Stft(nfft, hop, "hann", lib=lib) as h:
         for conv in ("valid", "center"):

@@ -65,8 +65,8 @@ extern "C" int vvb_event_create(void** e) { *e = malloc(1); return 0; }
 extern "C" int vvb_event_destroy(void* e) { free(e); return 0; }
 extern "C" int vvb_event_record(void*, void*) { return 0; }
 extern "C" int vvb_stream_wait_event(void*, void*) { return 0; }
-#define VVB_LAUNCH(kern, grid, block, smem, stream, args) \
-    do { g_launches++; vvb_emu::launch(dim3(grid), dim3(block), smem, [&] { kern(args); }); } while (0)
+#define VVB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    do { g_launches++; vvb_emu::launch(dim3(grid), dim3(block), smem, [&] { kern(__VA_ARGS__); }); } while (0)
 template <class K> static int rt_blocks_per_sm(K, int, size_t) { return 1; }
 #else
 /* ---- CUDA runtime */
@@ -111,8 +111,8 @@ extern "C" int vvb_event_create(void** e) { cudaEvent_t ev; CK(cudaEventCreateWi
 extern "C" int vvb_event_destroy(void* e) { if (e) CK(cudaEventDestroy((cudaEvent_t)e)); return 0; }
 extern "C" int vvb_event_record(void* e, void* s) { CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s)); return 0; }
 extern "C" int vvb_stream_wait_event(void* s, void* e) { CK(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0)); return 0; }
-#define VVB_LAUNCH(kern, grid, block, smem, stream, args) \
-    do { g_launches++; kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(args); CK(cudaGetLastError()); } while (0)
+#define VVB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    do { g_launches++; kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); CK(cudaGetLastError()); } while (0)
 /* opt in to the dynamic shared memory the kernel needs and ask how many CTAs fit per SM */
 template <class K> static int rt_blocks_per_sm(K kern, int threads, size_t smem)
 {
@@ -655,8 +655,19 @@ extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, si
 }
 
 /* ---------------------------------------------------------------------- log-mel */
+template <int R> static int launch_logmel_tma(const MelArgs& a, int grid, size_t smem, int stages, int stage_floats, int n_groups, void* stream)
+{
+    static size_t opted = 0;                               /* largest dynamic shared-memory size opted in to so far */
+    if (smem > opted) {
+        if (rt_blocks_per_sm(logmel_tma_kernel<R>, 256, smem) == 0) return fail(4, "logmel_tma_kernel", "does not fit on this device");
+        opted = smem;
+    }
+    VVB_LAUNCH(logmel_tma_kernel<R>, grid, 256, smem, stream, a, stages, stage_floats, n_groups);
+    return 0;
+}
+
 extern "C" int vvb_logmel(const float* d_power, size_t frames, size_t bins, size_t power_pitch, const int* d_meta, const float* d_w,
-                          size_t n_mels, float eps, float* d_out, void* stream)
+                          size_t n_mels, size_t n_groups, float eps, float* d_out, void* stream)
 {
     if (!d_power || !d_meta || !d_w || !d_out) return fail(1, "vvb_logmel", "null");
     if (frames == 0 || n_mels == 0) return 0;
@@ -667,6 +678,30 @@ extern "C" int vvb_logmel(const float* d_power, size_t frames, size_t bins, size
     MelArgs a;
     a.power = d_power; a.pitch = (long long)power_pitch; a.frames = (long long)frames; a.bins = (int)bins; a.n_mels = (int)n_mels;
     a.meta = d_meta; a.w = d_w; a.eps = eps; a.out = d_out;
+    /* densely packed, aligned rows: the TMA-fed kernel, with the largest frame tile that still leaves a
+     * three-deep ring (then two, then one) inside 220 KB of shared memory */
+    if (power_pitch == bins && ((uintptr_t)d_power & 15u) == 0 && n_mels <= MEL_TMA_MAX_MELS && n_groups > 0 &&
+        n_groups <= 3072 && getenv("VVB_MEL_NO_TMA") == nullptr) {
+        const size_t budget = 226 * 1024;
+        for (int want = 3; want >= 1; --want) {
+            for (int R = 32; R >= 4; R >>= 1) {
+                const size_t stage_bytes = (size_t)R * bins * 4, fixed = MEL_HDR + n_groups * 32 + (size_t)R * (n_mels | 1) * 4 + 16;
+                if (fixed + want * stage_bytes > budget) continue;
+                int stages = (int)((budget - fixed) / stage_bytes);
+                if (stages > 4) stages = 4;
+                const size_t smem = fixed + (size_t)stages * stage_bytes;
+                const long long tiles = (long long)((frames + R - 1) / R);
+                const int grid = (int)std::min<long long>(tiles, rt_num_sms());
+                const int sf = (int)(stage_bytes / 4);
+                switch (R) {
+                    case 32: return launch_logmel_tma<32>(a, grid, smem, stages, sf, (int)n_groups, stream);
+                    case 16: return launch_logmel_tma<16>(a, grid, smem, stages, sf, (int)n_groups, stream);
+                    case 8:  return launch_logmel_tma<8>(a, grid, smem, stages, sf, (int)n_groups, stream);
+                    default: return launch_logmel_tma<4>(a, grid, smem, stages, sf, (int)n_groups, stream);
+                }
+            }
+        }
+    }
     static int per_sm = -1;
     const size_t smem = sizeof(float) * MEL_KC * 33;
     if (per_sm < 0) per_sm = rt_blocks_per_sm(logmel_kernel, 256, smem);

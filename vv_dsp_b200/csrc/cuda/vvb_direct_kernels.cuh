@@ -226,4 +226,131 @@ __global__ void __launch_bounds__(256) logmel_kernel(const MelArgs a)
     }
 }
 
+/* The same reduction fed by TMA, for the usual case of densely packed power rows (pitch == bins, base 16-byte
+ * aligned).  R consecutive frames are one contiguous run of R*bins floats, so ONE bulk copy per tile brings
+ * them into shared memory untransposed; because bins = nfft/2+1 is odd the row pitch is already conflict-free
+ * for lane = frame.  `stages` tile buffers form a ring: thread 0 issues the copy for tile it+stages-1 right
+ * after the CTA has finished tile it-1, so stages-1 tiles (>= 128 KB at the headline shape) are in flight per
+ * SM while the warps reduce the current one.
+ * Work split: a thread owns TWO frames (r and r + R/2: two independent sums that share every weight) and one
+ * of 8*64/R band slots.  The host has cut every filter into groups of four taps and dealt whole filters to
+ * slots, longest first (mel.c), so a slot is one flat list of groups: no per-band inner loop, nothing to
+ * diverge on inside a warp, and the loads of group g+1 (descriptor, four weights, eight power values) are
+ * issued before the sums of group g.  Summation order per band is unchanged: ascending bins, separate
+ * multiply and add, taps beyond the filter's end predicated off. */
+constexpr int MEL_HDR = 64;       /* bytes reserved for the mbarriers in front of the tile ring */
+constexpr int MEL_TMA_MAX_MELS = 512;
+
+struct MelGroup { int4 d; float4 w; float p0[4], p1[4]; };
+
+template <int R> __global__ void __launch_bounds__(256) logmel_tma_kernel(const MelArgs a, const int stages, const int stage_floats,
+                                                                           const int n_groups)
+{
+    constexpr int HALF = R / 2, SUB = 32 / HALF, NSLOT = 8 * SUB;
+    constexpr int VARIANT = (R == 32) ? 0 : (R == 16) ? 1 : (R == 8) ? 2 : 3;
+    static_assert(NSLOT == (16 << VARIANT), "slot count must match the host-side tables");
+#ifdef VVB_EMU
+    unsigned char* mel_smem = reinterpret_cast<unsigned char*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float smem[];
+    unsigned char* mel_smem = reinterpret_cast<unsigned char*>(smem);
+#endif
+    /* shared memory: mbarriers | group descriptors | quad weights | tile ring | output staging */
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(mel_smem);
+    int4* s_desc = reinterpret_cast<int4*>(mel_smem + MEL_HDR);
+    float4* s_wq = reinterpret_cast<float4*>(s_desc + n_groups);
+    float* ring = reinterpret_cast<float*>(s_wq + n_groups);
+    float* sOut = ring + (size_t)stages * stage_floats;                 /* [R][n_mels | 1] */
+    const int opitch = a.n_mels | 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = lane & (HALF - 1), r1 = r0 + HALF, slot = warp * SUB + lane / HALF;
+    const long long ntiles = (a.frames + R - 1) / R;
+    const long long tile_floats = (long long)R * a.bins;
+    const int* hdr = a.meta + 3 * a.n_mels;
+    const int* slot_ptr = a.meta + __ldg(hdr + VARIANT);
+    const int g_begin = __ldg(slot_ptr + slot), g_end = __ldg(slot_ptr + slot + 1);
+
+    auto issue = [&](long long it) {                                    /* thread 0 only */
+        const long long tile = blockIdx.x + it * gridDim.x;
+        if (tile >= ntiles) return;
+        const long long nf = min((long long)R, a.frames - tile * R);
+        const unsigned bytes = (unsigned)(nf * a.bins * 4);
+        if (bytes & 15u) return;                                        /* ragged tail: plain loads below */
+        const int s = (int)(it % stages);
+        fence_proxy_async();
+        mbar_expect_tx(&bars[s], bytes);
+        bulk_load(ring + (size_t)s * stage_floats, a.power + tile * tile_floats, bytes, &bars[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        for (int it = 0; it < stages - 1; ++it) issue(it);
+    }
+    {   /* the tables of this tile shape, once per CTA (the first tiles are already in flight) */
+        const int4* gdesc = reinterpret_cast<const int4*>(a.meta + __ldg(hdr + 4 + VARIANT));
+        const float4* gwq = reinterpret_cast<const float4*>(a.w + __ldg(hdr + 8));
+        for (int g = tid; g < n_groups; g += 256) {
+            const int4 d = __ldg(gdesc + g);
+            s_desc[g] = d;
+            s_wq[g] = __ldg(gwq + d.y);                                 /* weights follow the slot order too */
+        }
+    }
+    for (long long it = 0;; ++it) {
+        const long long tile = blockIdx.x + it * gridDim.x;
+        if (tile >= ntiles) break;
+        __syncthreads();                                   /* tile it-1 and its output staging are consumed */
+        if (tid == 0) issue(it + stages - 1);
+        const int s = (int)(it % stages);
+        const long long f0 = tile * R;
+        const int nf = (int)min((long long)R, a.frames - f0);
+        float* P = ring + (size_t)s * stage_floats;
+        if (((unsigned)(nf * (long long)a.bins * 4) & 15u) == 0) {
+            mbar_wait(&bars[s], (unsigned)((it / stages) & 1));
+        } else {
+            const float* src = a.power + tile * tile_floats;
+            for (long long i = tid; i < (long long)nf * a.bins; i += 256) P[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        const float* P0 = P + (size_t)r0 * a.bins;
+        const float* P1 = P + (size_t)r1 * a.bins;
+        /* taps past the end of a run are read (they stay inside the shared-memory allocation: the output
+         * staging follows the ring) but never added */
+        auto fetch = [&](int g, MelGroup& q) {
+            q.d = s_desc[g];
+            q.w = s_wq[g];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { q.p0[u] = P0[q.d.x + u]; q.p1[u] = P1[q.d.x + u]; }
+        };
+        float acc0 = 0.f, acc1 = 0.f;
+        auto reduce = [&](const MelGroup& q) {
+            const int taps = q.d.z & 7;
+            const float wv[4] = {q.w.x, q.w.y, q.w.z, q.w.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float t0 = __fmul_rn(q.p0[u], wv[u]), t1 = __fmul_rn(q.p1[u], wv[u]);
+                if (u < taps) { acc0 = __fadd_rn(acc0, t0); acc1 = __fadd_rn(acc1, t1); }
+            }
+            if (q.d.z & 8) {                                            /* last group of a filter */
+                sOut[r0 * opitch + q.d.w] = acc0;
+                sOut[r1 * opitch + q.d.w] = acc1;
+                acc0 = 0.f; acc1 = 0.f;
+            }
+        };
+        MelGroup ga, gb;
+        if (g_begin < g_end) fetch(g_begin, ga);
+        for (int g = g_begin; g < g_end; g += 2) {                      /* ping-pong: group g+1 is in flight while g is summed */
+            if (g + 1 < g_end) fetch(g + 1, gb);
+            reduce(ga);
+            if (g + 1 < g_end) {
+                if (g + 2 < g_end) fetch(g + 2, ga);
+                reduce(gb);
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nf * a.n_mels; idx += 256) {
+            const int rr = idx / a.n_mels, mm = idx - rr * a.n_mels;
+            a.out[(f0 + rr) * a.n_mels + mm] = logf(sOut[rr * opitch + mm] + a.eps);
+        }
+    }
+}
+
 }  // namespace vvb

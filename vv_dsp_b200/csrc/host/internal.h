@@ -4,7 +4,7 @@
 #include <stddef.h>
 
 /* device-resident sparse mel filterbank: meta = lo | len | off per band, packed non-zero weights */
-typedef struct mel_device { int* d_meta; float* d_w; } mel_device;
+typedef struct mel_device { int* d_meta; float* d_w; size_t n_groups; } mel_device;
 int vvdsp_internal_mel_device_build(const float* dense_weights, size_t n_mels, size_t bins, void* stream, mel_device* md);
 void vvdsp_internal_mel_device_free(mel_device* md);
 

@@ -75,17 +75,50 @@ void vv_dsp_mel_filterbank_free(vv_dsp_real* filterbank_weights, size_t n_mels)
     free(filterbank_weights);
 }
 
-/* dense [n_mels][bins] -> device-resident sparse form: meta = lo | len | off, packed non-zero runs */
+/* dense [n_mels][bins] -> device-resident sparse form.
+ *   meta : lo[n_mels] | len[n_mels] | off[n_mels]            one contiguous non-zero run per filter
+ *          header[12]: slot_ptr start (x4), group start (x4), quad-weight offset, spare
+ *          then, for each of the four tile shapes of the log-mel kernel (16, 32, 64, 128 band slots):
+ *          slot_ptr[slots + 1] and the slot-ordered group list {first bin, quad index, taps | 8*last, band}
+ *   w    : the packed runs | the same runs padded with zeros to groups of four taps (16-byte loads)
+ * A group is four consecutive taps of one filter.  Filters are dealt to slots longest first, each to the
+ * least loaded slot, so that every slot of the kernel walks about the same number of groups. */
 void vvdsp_internal_mel_device_free(mel_device* md) { vvb_free(md->d_meta); vvb_free(md->d_w); md->d_meta = NULL; md->d_w = NULL; }
 
 int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t bins, void* stream, mel_device* md)
 {
-    int* meta = (int*)malloc(3 * n_mels * sizeof(int));
-    float* packed = (float*)malloc((n_mels * bins ? n_mels * bins : 1) * sizeof(float));
-    size_t m, k, total = 0;
-    int st;
-    md->d_meta = NULL; md->d_w = NULL;
-    if (!meta || !packed) { free(meta); free(packed); return 4; }
+    const size_t hdr = 3 * n_mels;
+    size_t m, k, total = 0, groups = 0, meta_len, w_len, quad0, v, pos;
+    int *meta = NULL, *order = NULL, *gcount = NULL, *gfirst = NULL, *load = NULL, *owner = NULL;
+    float* packed = NULL;
+    int st = 4;
+    md->d_meta = NULL; md->d_w = NULL; md->n_groups = 0;
+    gcount = (int*)malloc(n_mels * sizeof(int)); gfirst = (int*)malloc(n_mels * sizeof(int));
+    order = (int*)malloc(n_mels * sizeof(int)); owner = (int*)malloc(n_mels * sizeof(int));
+    load = (int*)malloc(128 * sizeof(int));
+    packed = (float*)malloc((2 * n_mels * bins + 8 * n_mels + 8) * sizeof(float));
+    if (!gcount || !gfirst || !order || !owner || !load || !packed) goto done;
+    /* first pass: runs and group counts, to size the tables */
+    for (m = 0; m < n_mels; ++m) {
+        const float* w = weights + m * bins;
+        size_t lo = bins, hi = 0;
+        for (k = 0; k < bins; ++k) if (w[k] != 0.0f) { if (lo == bins) lo = k; hi = k + 1; }
+        if (lo == bins) { lo = 0; hi = 0; }
+        gcount[m] = (int)((hi - lo + 3) / 4);
+        if (gcount[m] == 0) gcount[m] = 1;              /* an all-zero filter still has to emit log(eps) */
+        gfirst[m] = (int)groups;
+        groups += (size_t)gcount[m];
+        total += hi - lo;
+    }
+    meta_len = hdr + 12;
+    for (v = 0; v < 4; ++v) meta_len += ((size_t)(16u << v) + 1 + 3) / 4 * 4 + 4 * groups;
+    meta_len = (meta_len + 3) / 4 * 4 + 4;
+    meta = (int*)calloc(meta_len, sizeof(int));
+    if (!meta) goto done;
+    quad0 = (total + 3) / 4 * 4;
+    w_len = quad0 + 4 * groups;
+    memset(packed, 0, (w_len ? w_len : 1) * sizeof(float));
+    total = 0;
     for (m = 0; m < n_mels; ++m) {
         const float* w = weights + m * bins;
         size_t lo = bins, hi = 0;
@@ -93,14 +126,60 @@ int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t 
         if (lo == bins) { lo = 0; hi = 0; }
         meta[m] = (int)lo; meta[n_mels + m] = (int)(hi - lo); meta[2 * n_mels + m] = (int)total;
         memcpy(packed + total, w + lo, (hi - lo) * sizeof(float));
+        memcpy(packed + quad0 + 4 * (size_t)gfirst[m], w + lo, (hi - lo) * sizeof(float));
         total += hi - lo;
     }
-    st = vvb_malloc((void**)&md->d_meta, 3 * n_mels * sizeof(int));
-    if (!st) st = vvb_malloc((void**)&md->d_w, (total ? total : 1) * sizeof(float));
-    if (!st) st = vvb_memcpy_h2d(md->d_meta, meta, 3 * n_mels * sizeof(int), stream);
-    if (!st && total) st = vvb_memcpy_h2d(md->d_w, packed, total * sizeof(float), stream);
+    /* filters by descending group count (insertion sort: n_mels is small) */
+    for (m = 0; m < n_mels; ++m) {
+        size_t q = m;
+        while (q > 0 && gcount[order[q - 1]] < gcount[m]) { order[q] = order[q - 1]; --q; }
+        order[q] = (int)m;
+    }
+    meta[hdr + 8] = (int)quad0;
+    pos = (hdr + 12 + 3) / 4 * 4;
+    for (v = 0; v < 4; ++v) {
+        const size_t slots = (size_t)16u << v;
+        size_t s, q, g, at;
+        int* slot_ptr = meta + pos;
+        int* desc;
+        meta[hdr + v] = (int)pos;
+        pos += (slots + 1 + 3) / 4 * 4;
+        meta[hdr + 4 + v] = (int)pos;
+        desc = meta + pos;
+        pos += 4 * groups;
+        for (s = 0; s < slots; ++s) load[s] = 0;
+        for (q = 0; q < n_mels; ++q) {
+            size_t best = 0;
+            for (s = 1; s < slots; ++s) if (load[s] < load[best]) best = s;
+            owner[order[q]] = (int)best;
+            load[best] += gcount[order[q]];
+        }
+        at = 0;
+        for (s = 0; s < slots; ++s) {
+            slot_ptr[s] = (int)at;
+            for (m = 0; m < n_mels; ++m) {
+                if (owner[m] != (int)s) continue;
+                for (g = 0; g < (size_t)gcount[m]; ++g) {
+                    const int len = meta[n_mels + m], left = len - (int)(4 * g);
+                    const int taps = left > 4 ? 4 : (left > 0 ? left : 0);
+                    int* d = desc + 4 * at++;
+                    d[0] = meta[m] + (int)(4 * g);
+                    d[1] = gfirst[m] + (int)g;
+                    d[2] = taps | ((g + 1 == (size_t)gcount[m]) ? 8 : 0);
+                    d[3] = (int)m;
+                }
+            }
+        }
+        slot_ptr[slots] = (int)at;
+    }
+    st = vvb_malloc((void**)&md->d_meta, meta_len * sizeof(int));
+    if (!st) st = vvb_malloc((void**)&md->d_w, (w_len ? w_len : 1) * sizeof(float));
+    if (!st) st = vvb_memcpy_h2d(md->d_meta, meta, meta_len * sizeof(int), stream);
+    if (!st && w_len) st = vvb_memcpy_h2d(md->d_w, packed, w_len * sizeof(float), stream);
     if (!st) st = vvb_stream_sync(stream);          /* the host staging arrays die below */
-    free(meta); free(packed);
+    if (!st) md->n_groups = groups;
+done:
+    free(meta); free(packed); free(order); free(gcount); free(gfirst); free(load); free(owner);
     if (st) vvdsp_internal_mel_device_free(md);
     return st;
 }
@@ -122,7 +201,7 @@ vv_dsp_status vv_dsp_compute_log_mel_spectrogram(const vv_dsp_real* power_spectr
     if (!power_spectrogram || !filterbank_weights || !out_log_mel_spectrogram) return VV_DSP_ERROR_NULL_POINTER;
     if (num_frames == 0 || n_fft_bins == 0 || n_mels == 0) return VV_DSP_ERROR_INVALID_SIZE;
     if (log_epsilon < 0.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
-    md.d_meta = NULL; md.d_w = NULL;
+    md.d_meta = NULL; md.d_w = NULL; md.n_groups = 0;
     st = vvb_device_ready();                         /* no CUDA device -> UNSUPPORTED, never a CPU computation */
     if (st) return to_status(st);
     st = vvb_stream_create(&stream);
@@ -130,7 +209,7 @@ vv_dsp_status vv_dsp_compute_log_mel_spectrogram(const vv_dsp_real* power_spectr
     if (!st) st = vvb_malloc((void**)&d_p, num_frames * n_fft_bins * sizeof(float));
     if (!st) st = vvb_malloc((void**)&d_o, num_frames * n_mels * sizeof(float));
     if (!st) st = vvb_memcpy_h2d(d_p, power_spectrogram, num_frames * n_fft_bins * sizeof(float), stream);
-    if (!st) st = vvb_logmel(d_p, num_frames, n_fft_bins, n_fft_bins, md.d_meta, md.d_w, n_mels, log_epsilon, d_o, stream);
+    if (!st) st = vvb_logmel(d_p, num_frames, n_fft_bins, n_fft_bins, md.d_meta, md.d_w, n_mels, md.n_groups, log_epsilon, d_o, stream);
     if (!st) st = vvb_memcpy_d2h(out_log_mel_spectrogram, d_o, num_frames * n_mels * sizeof(float), stream);
     if (stream) { int s2 = vvb_stream_sync(stream); if (!st) st = s2; }
     vvb_free(d_p); vvb_free(d_o); vvdsp_internal_mel_device_free(&md);

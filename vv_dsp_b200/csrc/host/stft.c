@@ -529,7 +529,7 @@ vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signal
         }
         if (out_space == VV_DSP_MEM_HOST) o_dev = d_o;
         if (!st) st = vvb_stft_forward(h->eng, x_dev, nb, n, xp, frames, pad, VVB_OUT_POWER, d_power, h->bins, stream);
-        if (!st) st = vvb_logmel(d_power, nb * frames, h->bins, h->bins, h->mel.d_meta, h->mel.d_w, n_mels, log_epsilon, o_dev, stream);
+        if (!st) st = vvb_logmel(d_power, nb * frames, h->bins, h->bins, h->mel.d_meta, h->mel.d_w, n_mels, h->mel.n_groups, log_epsilon, o_dev, stream);
         if (!st && out_space == VV_DSP_MEM_HOST)
             st = vvb_memcpy_d2h(out + done * frames * n_mels, d_o, nb * frames * n_mels * sizeof(float), stream);
         if (!st && signals_space == VV_DSP_MEM_HOST) st = vvb_stream_sync(stream);   /* staging buffer reuse */
