@@ -38,3 +38,17 @@ with Stft(nfft, hop, "hann") as h:
 print(json.dumps({"workload": f"STFT->log-mel, {B} x {n} samples, nfft={nfft} hop={hop}, {n_mels} mels", "ms": ms,
                   "Msamples_per_s": B * n / ms / 1e3, "power_kernel_ms": ms_pow, "logmel_and_overhead_ms": ms - ms_pow,
                   "note": "power goes through a 768 MB device scratch in chunks; scratch and the device filterbank are cached in the handle"}))
+# MFCC tail: same chain + DCT-II (13 coefficients, lifter 22)
+out2 = torch.empty((B, F, 13), device=dev)
+with Stft(nfft, hop, "hann") as h:
+    h.set_stream(s.cuda_stream)
+    for _ in range(2):
+        h.batch_mfcc(x, w, 13, lifter=22.0, out=out2)
+    torch.cuda.synchronize()
+    e0.record(s)
+    for _ in range(5):
+        h.batch_mfcc(x, w, 13, lifter=22.0, out=out2)
+    e1.record(s); torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / 5
+print(json.dumps({"workload": f"STFT->MFCC, {B} x {n} samples, nfft={nfft} hop={hop}, {n_mels} mels, 13 coefficients", "ms": ms2,
+                  "Msamples_per_s": B * n / ms2 / 1e3, "mfcc_stage_ms": ms2 - ms}))

@@ -120,6 +120,17 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_logmel(
     const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
     vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames);
 
+/* The same chain followed by the MFCC stage of vv_dsp_mfcc (unnormalised DCT-II of every log-mel frame, first
+ * num_mfcc_coeffs kept, liftering when lifter_coeff > 0): out is [batch][frames][num_mfcc_coeffs].  Frame for
+ * frame equal to vv_dsp_mfcc(vv_dsp_compute_log_mel_spectrogram(|process|^2)). */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_mfcc(
+    vv_dsp_stft* h,
+    const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch, size_t n, size_t signal_pitch,
+    vv_dsp_frame_convention convention,
+    const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
+    size_t num_mfcc_coeffs, vv_dsp_real lifter_coeff,
+    vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames);
+
 /* Many transforms through one plan: `batch` contiguous transforms,
  * C2C: cpx[batch][n] -> cpx[batch][n];  R2C: real[batch][n] -> cpx[batch][n/2+1];  C2R: the reverse.
  * Same conventions as vv_dsp_fft_execute (forward unscaled, backward 1/n, R2C Nyquist real, C2R =

@@ -76,6 +76,10 @@ int vvb_stft_inverse_frames(vvb_engine* e, const vvb_cpx* d_spec, size_t count, 
 int vvb_logmel(const float* d_power, size_t frames, size_t bins, size_t power_pitch, const int* d_meta, const float* d_w,
                size_t n_mels, size_t n_groups, float eps, float* d_out, void* stream);
 
+/* ---- MFCC: d_out[f][k] = d_lifter[k] * sum_n d_logmel[f][n] * d_table[k*n_mels + n], n ascending */
+int vvb_mfcc(const float* d_logmel, size_t frames, size_t n_mels, size_t n_coeffs, const float* d_table,
+             const float* d_lifter, float* d_out, void* stream);
+
 /* ---- FFT engine (plan API): type 0 C2C, 1 R2C, 2 C2R; dir +1 / -1 */
 int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine** out);
 void vvb_fft_engine_destroy(vvb_fft_engine* e);

@@ -266,6 +266,14 @@ class Oracle(_Base):
         assert st == 0, st
         return out
 
+    def mfcc(self, log_mel, n_coeffs, lifter=0.0, dct_type=2):
+        log_mel = _f32(log_mel)
+        out = np.empty((log_mel.shape[0], max(n_coeffs, 1)), np.float32)
+        self.lib.orc_mfcc.restype = C.c_int
+        st = self.lib.orc_mfcc(_p(log_mel), _sz(log_mel.shape[0]), _sz(log_mel.shape[1]), _sz(n_coeffs), C.c_int(dct_type),
+                               C.c_float(lifter), _p(out))
+        return st, out[:, :n_coeffs]
+
 
 class _Params(C.Structure):
     _fields_ = [("fft_size", _sz), ("hop_size", _sz), ("window", C.c_int)]
@@ -422,6 +430,26 @@ class Reference(_Base):
                                                          _sz(weights.shape[0]), C.c_float(eps), _p(out))
         assert st == 0, st
         return out
+
+    def mfcc(self, log_mel, n_coeffs, lifter=0.0, dct_type=2):
+        log_mel = _f32(log_mel)
+        out = np.empty((log_mel.shape[0], max(n_coeffs, 1)), np.float32)
+        st = self.lib.vv_dsp_mfcc(_p(log_mel), _sz(log_mel.shape[0]), _sz(log_mel.shape[1]), _sz(n_coeffs), C.c_int(dct_type),
+                                  C.c_float(lifter), _p(out))
+        return st, out[:, :n_coeffs]
+
+    def mfcc_plan_process(self, power, n_fft, n_mels, n_coeffs, sr, fmin, fmax, lifter, eps):
+        """vv_dsp_mfcc_init -> vv_dsp_mfcc_process -> vv_dsp_mfcc_destroy (src/features/mel.c:333-461)"""
+        power = _f32(power)
+        plan = C.c_void_p()
+        st = self.lib.vv_dsp_mfcc_init(_sz(n_fft), _sz(n_mels), _sz(n_coeffs), C.c_float(sr), C.c_float(fmin), C.c_float(fmax),
+                                       C.c_int(0), C.c_int(2), C.c_float(lifter), C.c_float(eps), C.byref(plan))
+        if st != 0:
+            return st, None
+        out = np.empty((power.shape[0], n_coeffs), np.float32)
+        st = self.lib.vv_dsp_mfcc_process(plan, _p(power), _sz(power.shape[0]), _p(out))
+        self.lib.vv_dsp_mfcc_destroy(plan)
+        return st, out
 
     def istft(self, spec, nfft, hop, n_out, win="hann", half=True, normalise=True):
         """Per-frame python loop: reconstruct at f*hop, then the caller-side divide."""

@@ -527,3 +527,34 @@ int orc_log_mel(const float *power, size_t frames, size_t bins, const float *wei
         }
     return 0;
 }
+
+/* src/features/mel.c:249-310 on top of the naive DCT-II of src/spectral/dct.c:21-30:
+ * c[k] = sum_n x[n]*cosf(pi*(n+0.5)*k/N) (angle and sum in float32, n ascending, unnormalised), the first
+ * n_coeffs kept, then c[i] *= 1 + (L/2)*sinf(pi*i/L) for i >= 1 when L > 0.  dct_type: only DCT-II (2). */
+int orc_mfcc(const float *log_mel, size_t frames, size_t n_mels, size_t n_coeffs, int dct_type, float lifter, float *out)
+{
+    const float pi = (float)3.141592653589793238462643383279502884;
+    if (!log_mel || !out) return 1;
+    if (frames == 0 || n_mels == 0 || n_coeffs == 0) return 2;
+    if (n_coeffs > n_mels) return 2;
+    if (dct_type != 2) return 3;
+    if (lifter < 0.0f) return 3;
+    for (size_t f = 0; f < frames; ++f) {
+        const float *x = log_mel + f * n_mels;
+        float *c = out + f * n_coeffs;
+        for (size_t k = 0; k < n_coeffs; ++k) {
+            float sum = 0;
+            for (size_t n = 0; n < n_mels; ++n) {
+                float ang = pi * ((float)n + 0.5f) * (float)k / (float)n_mels;
+                sum += x[n] * cosf(ang);
+            }
+            c[k] = sum;
+        }
+        if (lifter > 0.0f)
+            for (size_t i = 1; i < n_coeffs; ++i) {
+                float factor = 1.0f + (lifter / 2.0f) * sinf((float)3.14159265358979323846 * (float)i / lifter);
+                c[i] *= factor;
+            }
+    }
+    return 0;
+}

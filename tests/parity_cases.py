@@ -172,6 +172,47 @@ def check_mel(lib, oracle, nfft=2048, hop=512, n_mels=80, sr=48000.0, n=30000, b
             assert np.abs(e - er).max() <= 1e-4 * er.max(), np.abs(e - er).max() / er.max()
 
 
+def check_mfcc(lib, oracle):
+    """vv_dsp_mfcc, the MFCC plan and the batched STFT -> MFCC chain against the oracle (same float32 sums as the
+    reference: only the logf feeding the DCT may differ in the last ulp)."""
+    from vv_dsp_b200 import MfccPlan, mel_filterbank, mfcc
+    rng = np.random.default_rng(9)
+    for n_mels, n_coeffs, lifter, frames in ((80, 13, 22.0, 70), (40, 40, 0.0, 33), (26, 12, 22.0, 1), (128, 20, 5.5, 65)):
+        lm = rng.normal(-3, 4, (frames, n_mels)).astype(np.float32)
+        st, a = mfcc(lm, n_coeffs, lifter, lib=lib)
+        so, b = oracle.mfcc(lm, n_coeffs, lifter)
+        assert st == so == 0 and a.tobytes() == b.tobytes(), (n_mels, n_coeffs, lifter)
+    lm = np.zeros((2, 8), np.float32)
+    for bad in ((0, 0.0, 2), (9, 0.0, 2), (4, -1.0, 2), (4, 0.0, 3), (4, 0.0, 4)):
+        assert mfcc(lm, bad[0], bad[1], bad[2], lib=lib)[0] == oracle.mfcc(lm, bad[0], bad[1], bad[2])[0], bad
+    # plan: power -> log-mel -> MFCC
+    nfft, n_mels, n_coeffs, sr = 512, 40, 13, 16000.0
+    p = rng.uniform(0, 5, (37, nfft // 2 + 1)).astype(np.float32)
+    _, w = oracle.mel_filterbank(nfft, n_mels, sr, 0.0, sr / 2)
+    want = oracle.mfcc(oracle.log_mel(p, w, 1e-10), n_coeffs, 22.0)[1]
+    with MfccPlan(nfft, n_mels, n_coeffs, sr, 0.0, sr / 2, lifter=22.0, lib=lib) as plan:
+        assert plan.status == 0
+        st, got = plan.process(p)
+        assert st == 0 and np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+        assert plan.process(np.zeros((0, nfft // 2 + 1), np.float32))[0] == 2
+    for bad in ((0, 40, 13, sr, 0.0, 8000.0, 2), (512, 40, 41, sr, 0.0, 8000.0, 3), (512, 40, 13, sr, 0.0, 9000.0, 3),
+                (512, 40, 13, 0.0, 0.0, 8000.0, 2)):
+        plan = MfccPlan(*bad[:6], lib=lib)
+        assert plan.status == bad[6], bad
+        plan.close()
+    with MfccPlan(nfft, n_mels, n_coeffs, sr, 0.0, sr / 2, dct_type=3, lib=lib) as plan:     # rejected at process time, as in mel.c:249-270
+        assert plan.status == 0 and plan.process(p)[0] == 3
+    # batched chain
+    nfft, hop, n_mels = 1024, 256, 64
+    _, w = mel_filterbank(nfft, n_mels, 48000.0, 0.0, 24000.0, lib=lib)
+    x = np.stack([noise(80 + i, 12000) for i in range(2)])
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        got = h.batch_mfcc(x, w, 20, lifter=22.0)
+        lm = h.batch_logmel(x, w)
+        want = np.stack([oracle.mfcc(lm[i], 20, 22.0)[1] for i in range(2)])
+        assert got.shape == want.shape and got.tobytes() == want.tobytes()       # same log-mel in, same sums
+
+
 def check_status_codes(lib):
     """Return codes of the reference boundary (SURVEY.md section 4 'lifecycle/validation')."""
     import ctypes as C

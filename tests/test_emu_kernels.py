@@ -80,6 +80,10 @@ def test_mel(emu, oracle):
     pc.check_mel(emu, oracle, 512, 128, 26, 16000.0, 6000)
 
 
+def test_mfcc(emu, oracle):
+    pc.check_mfcc(emu, oracle)
+
+
 def test_golden_slices(emu, golden):
     pc.check_golden_slices(emu, golden)
 

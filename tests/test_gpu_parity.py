@@ -167,6 +167,11 @@ def test_mel(lib, oracle):
     pc.check_mel(lib, oracle, 400, 160, 40, 16000.0, 16000)          # non power of two fft_size (direct path)
 
 
+@pytest.mark.gpu
+def test_mfcc(lib, oracle):
+    pc.check_mfcc(lib, oracle)
+
+
 def test_golden_slices_of_the_real_reference(lib, golden):
     pc.check_golden_slices(lib, golden)
 

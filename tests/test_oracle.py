@@ -248,3 +248,24 @@ def test_mel_oracle_against_reference(oracle, reference):
     for bad in [(0, 10, 48000.0, 0.0, 100.0), (512, 0, 48000.0, 0.0, 100.0), (512, 300, 48000.0, 0.0, 100.0),
                 (512, 10, 48000.0, 0.0, 30000.0), (512, 10, 48000.0, 100.0, 50.0), (512, 10, 48000.0, 0.0, 8000.0, 1)]:
         assert oracle.mel_filterbank(*bad)[0] == reference.mel_filterbank(*bad)[0], bad
+
+
+def test_mfcc_oracle_against_reference(oracle, reference):
+    """orc_mfcc (DCT-II of src/spectral/dct.c:21-30 + liftering, src/features/mel.c:249-310) is bit-exact against the
+    reference, and so is the plan pipeline power -> log-mel -> MFCC (mel.c:333-450) rebuilt from the oracle's pieces."""
+    if not hasattr(reference.lib, "vv_dsp_mfcc"):
+        pytest.skip("oracle/_ref was built without mel.c")
+    rng = np.random.default_rng(5)
+    for n_mels, n_coeffs, lifter in ((80, 13, 0.0), (40, 40, 22.0), (26, 12, 22.0), (7, 1, 3.5)):
+        lm = rng.normal(-3, 4, (17, n_mels)).astype(np.float32)
+        so, co = oracle.mfcc(lm, n_coeffs, lifter)
+        sr, cr = reference.mfcc(lm, n_coeffs, lifter)
+        assert so == sr == 0 and co.tobytes() == cr.tobytes(), (n_mels, n_coeffs, lifter)
+    lm = np.zeros((2, 8), np.float32)
+    for bad in ((0, 0.0, 2), (9, 0.0, 2), (4, -1.0, 2), (4, 0.0, 3), (4, 0.0, 4)):
+        assert oracle.mfcc(lm, bad[0], bad[1], bad[2])[0] == reference.mfcc(lm, bad[0], bad[1], bad[2])[0], bad
+    p = rng.uniform(0, 5, (9, 257)).astype(np.float32)
+    st, ref = reference.mfcc_plan_process(p, 512, 40, 13, 16000.0, 0.0, 8000.0, 22.0, 1e-10)
+    _, w = oracle.mel_filterbank(512, 40, 16000.0, 0.0, 8000.0)
+    st2, mine = oracle.mfcc(oracle.log_mel(p, w, 1e-10), 13, 22.0)
+    assert st == st2 == 0 and mine.tobytes() == ref.tobytes()

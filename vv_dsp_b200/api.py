@@ -77,6 +77,13 @@ class Library:
         "vv_dsp_compute_log_mel_spectrogram": (C.c_int, [_vp, _sz, _sz, _vp, _sz, C.c_float, _vp]),
         "vv_dsp_stft_batch_logmel": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, _vp, _sz, C.c_float, _vp, C.c_int,
                                                C.POINTER(_sz)]),
+        "vv_dsp_stft_batch_mfcc": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, _vp, _sz, C.c_float, _sz, C.c_float, _vp, C.c_int,
+                                             C.POINTER(_sz)]),
+        "vv_dsp_mfcc": (C.c_int, [_vp, _sz, _sz, _sz, C.c_int, C.c_float, _vp]),
+        "vv_dsp_mfcc_init": (C.c_int, [_sz, _sz, _sz, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float,
+                                       C.POINTER(_vp)]),
+        "vv_dsp_mfcc_process": (C.c_int, [_vp, _vp, _sz, _vp]),
+        "vv_dsp_mfcc_destroy": (C.c_int, [_vp]),
         "vv_dsp_b200_version": (C.c_char_p, []),
         "vv_dsp_b200_last_error": (C.c_char_p, []),
         "vv_dsp_b200_kernel_launches": (C.c_ulonglong, []),
@@ -204,6 +211,47 @@ def log_mel_spectrogram(power, weights, log_epsilon, lib: Library | None = None)
     return out
 
 
+DCT_II = 2
+
+
+def mfcc(log_mel, num_coeffs, lifter=0.0, dct_type=DCT_II, lib: Library | None = None):
+    """vv_dsp_mfcc: log_mel [frames, n_mels] (host) -> (status, [frames, num_coeffs])"""
+    lib = lib or default_library()
+    log_mel = np.ascontiguousarray(log_mel, np.float32)
+    out = np.empty((log_mel.shape[0], max(int(num_coeffs), 1)), np.float32)
+    st = lib.vv_dsp_mfcc(_ptr(log_mel), log_mel.shape[0], log_mel.shape[1], num_coeffs, dct_type, lifter, _ptr(out))
+    return st, out[:, :num_coeffs]
+
+
+class MfccPlan:
+    """vv_dsp_mfcc_init / process / destroy (power spectrogram -> log-mel -> MFCC, host buffers)"""
+
+    def __init__(self, n_fft, n_mels, num_coeffs, sample_rate, fmin, fmax, variant=0, dct_type=DCT_II, lifter=0.0,
+                 log_epsilon=1e-10, lib: Library | None = None):
+        self.lib = lib or default_library()
+        self._p = _vp()
+        self.num_coeffs = num_coeffs
+        self.status = self.lib.vv_dsp_mfcc_init(n_fft, n_mels, num_coeffs, sample_rate, fmin, fmax, variant, dct_type, lifter,
+                                                log_epsilon, C.byref(self._p))
+
+    def process(self, power):
+        power = np.ascontiguousarray(power, np.float32)
+        out = np.empty((power.shape[0], self.num_coeffs), np.float32)
+        st = self.lib.vv_dsp_mfcc_process(self._p, _ptr(power), power.shape[0], _ptr(out))
+        return st, out
+
+    def close(self):
+        if self._p:
+            self.lib.vv_dsp_mfcc_destroy(self._p)
+            self._p = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 # ----------------------------------------------------------------------------- STFT handle
 class Stft:
     """vv_dsp_stft handle: create / process / reconstruct / spectrogram + the batched extension."""
@@ -322,6 +370,29 @@ class Stft:
                                                CONVENTIONS[convention], _ptr(weights), weights.shape[0], log_epsilon,
                                                _ptr(out), DEVICE if _is_device(out) else HOST, C.byref(nf))
         _check(self.lib, st, "vv_dsp_stft_batch_logmel")
+        return out
+
+    def batch_mfcc(self, signals, weights, num_coeffs, lifter=0.0, log_epsilon=1e-10, convention="valid", out=None):
+        """STFT -> power -> mel -> log -> DCT-II (+ liftering): [batch, frames, num_coeffs]"""
+        dev_in = _is_device(signals)
+        if not dev_in:
+            signals = np.ascontiguousarray(signals, np.float32)
+        weights = np.ascontiguousarray(weights, np.float32)
+        assert weights.shape[1] == self.bins
+        batch, n = int(signals.shape[0]), int(signals.shape[1])
+        pitch = int(signals.stride(0)) if dev_in else n
+        frames = self.num_frames(n, convention)
+        if out is None:
+            if dev_in:
+                import torch
+                out = torch.empty((batch, frames, num_coeffs), device=signals.device, dtype=torch.float32)
+            else:
+                out = np.empty((batch, frames, num_coeffs), np.float32)
+        nf = _sz(0)
+        st = self.lib.vv_dsp_stft_batch_mfcc(self._h, _ptr(signals), DEVICE if dev_in else HOST, batch, n, pitch,
+                                             CONVENTIONS[convention], _ptr(weights), weights.shape[0], log_epsilon,
+                                             num_coeffs, lifter, _ptr(out), DEVICE if _is_device(out) else HOST, C.byref(nf))
+        _check(self.lib, st, "vv_dsp_stft_batch_mfcc")
         return out
 
     def batch_inverse(self, spectra, n_out, normalise=True, out=None):

@@ -710,6 +710,30 @@ extern "C" int vvb_logmel(const float* d_power, size_t frames, size_t bins, size
     return 0;
 }
 
+extern "C" int vvb_mfcc(const float* d_logmel, size_t frames, size_t n_mels, size_t n_coeffs, const float* d_table,
+                        const float* d_lifter, float* d_out, void* stream)
+{
+    if (!d_logmel || !d_table || !d_lifter || !d_out) return fail(1, "vvb_mfcc", "null");
+    if (frames == 0 || n_coeffs == 0) return 0;
+    const size_t smem = sizeof(float) * (32 * (n_mels | 1) + n_coeffs * n_mels + 32 * (n_coeffs | 1));
+    if (n_mels > 0x7fffffffu || smem > 200 * 1024) return fail(2, "vvb_mfcc", "n_mels x n_coeffs table does not fit in shared memory");
+#ifndef VVB_EMU
+    if (int st = vvb_device_ready()) return st;
+#endif
+    MfccArgs a;
+    a.logmel = d_logmel; a.frames = (long long)frames; a.n_mels = (int)n_mels; a.n_coeffs = (int)n_coeffs;
+    a.table = d_table; a.lifter = d_lifter; a.out = d_out;
+    static size_t opted = 0;
+    static int per_sm = 1;
+    if (smem > opted) {
+        per_sm = rt_blocks_per_sm(mfcc_kernel, 256, smem);
+        if (per_sm == 0) return fail(4, "mfcc_kernel", "does not fit on this device");
+        opted = smem;
+    }
+    VVB_LAUNCH(mfcc_kernel, persistent_grid((long long)((frames + 31) / 32), per_sm, rt_num_sms()), 256, smem, stream, a);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- FP32 peak probe */
 /* Measures the FP32 FMA throughput the roofline is quoted against: 16 independent dependent-FMA
  * chains per thread, scalar FFMA or packed FFMA2.  Diagnostics only (bench.py's roofline_fp32). */

@@ -353,4 +353,60 @@ template <int R> __global__ void __launch_bounds__(256) logmel_tma_kernel(const 
     }
 }
 
+/* ------------------------------------------------------------------ MFCC (second half) */
+/* out[f][k] = lifter[k] * sum_n logmel[f][n] * table[k][n], the reference's unnormalised DCT-II
+ * (src/spectral/dct.c:21-30) truncated to n_coeffs and liftered (src/features/mel.c:283-295).  The cosine
+ * table and lifter factors come from the host (same libm calls as the reference), the sum runs over n
+ * ascending with a separate multiply and add, so the result is the reference's float32 value bit for bit.
+ * A CTA takes 32 frames: the log-mel tile is parked in shared memory with an odd row pitch (lane = frame
+ * reads conflict-free, the table entry is a broadcast); warp w owns coefficients w, w+8, ... */
+struct MfccArgs {
+    const float* logmel; long long frames;
+    int n_mels, n_coeffs;
+    const float* table;      /* [n_coeffs][n_mels] */
+    const float* lifter;     /* [n_coeffs] */
+    float* out;              /* [frames][n_coeffs] */
+};
+
+__global__ void __launch_bounds__(256) mfcc_kernel(const MfccArgs a)
+{
+#ifdef VVB_EMU
+    float* ms = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float smem[];
+    float* ms = smem;
+#endif
+    const int pitch = a.n_mels | 1, opitch = a.n_coeffs | 1;
+    float* tile = ms;                                    /* [32][pitch] */
+    float* tab = tile + 32 * pitch;                      /* [n_coeffs][n_mels] */
+    float* so = tab + a.n_coeffs * a.n_mels;             /* [32][opitch] */
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < a.n_coeffs * a.n_mels; i += 256) tab[i] = __ldg(a.table + i);
+    const long long ntiles = (a.frames + 31) / 32;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long f0 = t * 32;
+        const int nf = (int)min((long long)32, a.frames - f0);
+        __syncthreads();
+        for (int i = tid; i < nf * a.n_mels; i += 256) {
+            const int r = i / a.n_mels, n = i - r * a.n_mels;
+            tile[r * pitch + n] = __ldg(a.logmel + f0 * a.n_mels + i);
+        }
+        __syncthreads();
+        if (lane < nf) {
+            const float* x = tile + lane * pitch;
+            for (int k = warp; k < a.n_coeffs; k += 8) {
+                const float* c = tab + k * a.n_mels;
+                float sum = 0.f;
+                for (int n = 0; n < a.n_mels; ++n) sum = __fadd_rn(sum, __fmul_rn(x[n], c[n]));
+                so[lane * opitch + k] = __fmul_rn(sum, __ldg(a.lifter + k));
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nf * a.n_coeffs; i += 256) {
+            const int r = i / a.n_coeffs, k = i - r * a.n_coeffs;
+            a.out[f0 * a.n_coeffs + i] = so[r * opitch + k];
+        }
+    }
+}
+
 }  // namespace vvb

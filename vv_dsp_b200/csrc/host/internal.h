@@ -8,4 +8,9 @@ typedef struct mel_device { int* d_meta; float* d_w; size_t n_groups; } mel_devi
 int vvdsp_internal_mel_device_build(const float* dense_weights, size_t n_mels, size_t bins, void* stream, mel_device* md);
 void vvdsp_internal_mel_device_free(mel_device* md);
 
+/* MFCC tables on the device: cosine table [n_coeffs][n_mels] and lifter factors [n_coeffs] */
+typedef struct mfcc_device { float* d_table; float* d_lifter; size_t n_mels, n_coeffs; float lifter; } mfcc_device;
+int vvdsp_internal_mfcc_device_build(size_t n_mels, size_t n_coeffs, float lifter, void* stream, mfcc_device* md);
+void vvdsp_internal_mfcc_device_free(mfcc_device* md);
+
 #endif

@@ -217,3 +217,148 @@ vv_dsp_status vv_dsp_compute_log_mel_spectrogram(const vv_dsp_real* power_spectr
     return to_status(st);
 }
 
+/* ------------------------------------------------------------------ MFCC (src/features/mel.c:249-461) */
+void vvdsp_internal_mfcc_device_free(mfcc_device* md) { vvb_free(md->d_table); vvb_free(md->d_lifter); md->d_table = NULL; md->d_lifter = NULL; }
+
+/* cos(pi (n + 1/2) k / N) and the lifter factors, evaluated in float32 exactly as the reference evaluates
+ * them per term (src/spectral/dct.c:25, mel.c:292) */
+int vvdsp_internal_mfcc_device_build(size_t n_mels, size_t n_coeffs, float lifter, void* stream, mfcc_device* md)
+{
+    const float pi = (float)3.141592653589793238462643383279502884;
+    float* tab = (float*)malloc(n_coeffs * n_mels * sizeof(float));
+    float* lif = (float*)malloc(n_coeffs * sizeof(float));
+    size_t k, n;
+    int st = 4;
+    md->d_table = NULL; md->d_lifter = NULL; md->n_mels = n_mels; md->n_coeffs = n_coeffs; md->lifter = lifter;
+    if (tab && lif) {
+        for (k = 0; k < n_coeffs; ++k) {
+            for (n = 0; n < n_mels; ++n) {
+                const float ang = pi * ((float)n + 0.5f) * (float)k / (float)n_mels;
+                tab[k * n_mels + n] = cosf(ang);
+            }
+            lif[k] = 1.0f;
+            if (lifter > 0.0f && k >= 1) lif[k] = 1.0f + (lifter / 2.0f) * sinf((float)3.14159265358979323846 * (float)k / lifter);
+        }
+        st = vvb_malloc((void**)&md->d_table, n_coeffs * n_mels * sizeof(float));
+        if (!st) st = vvb_malloc((void**)&md->d_lifter, n_coeffs * sizeof(float));
+        if (!st) st = vvb_memcpy_h2d(md->d_table, tab, n_coeffs * n_mels * sizeof(float), stream);
+        if (!st) st = vvb_memcpy_h2d(md->d_lifter, lif, n_coeffs * sizeof(float), stream);
+        if (!st) st = vvb_stream_sync(stream);
+    }
+    free(tab); free(lif);
+    if (st) vvdsp_internal_mfcc_device_free(md);
+    return st;
+}
+
+static vv_dsp_status mfcc_validate(size_t num_frames, size_t n_mels, size_t n_coeffs, vv_dsp_dct_type dct_type, vv_dsp_real lifter)
+{
+    if (num_frames == 0 || n_mels == 0 || n_coeffs == 0) return VV_DSP_ERROR_INVALID_SIZE;
+    if (n_coeffs > n_mels) return VV_DSP_ERROR_INVALID_SIZE;
+    if (dct_type != VV_DSP_DCT_II) return VV_DSP_ERROR_OUT_OF_RANGE;
+    if (lifter < 0.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
+    return VV_DSP_OK;
+}
+
+vv_dsp_status vv_dsp_mfcc(const vv_dsp_real* log_mel_spectrogram, size_t num_frames, size_t n_mels, size_t num_mfcc_coeffs,
+                          vv_dsp_dct_type dct_type, vv_dsp_real lifter_coeff, vv_dsp_real* out_mfcc_coeffs)
+{
+    mfcc_device md;
+    float *d_in = NULL, *d_out = NULL;
+    void* stream = NULL;
+    vv_dsp_status v;
+    int st;
+    if (!log_mel_spectrogram || !out_mfcc_coeffs) return VV_DSP_ERROR_NULL_POINTER;
+    v = mfcc_validate(num_frames, n_mels, num_mfcc_coeffs, dct_type, lifter_coeff);
+    if (v != VV_DSP_OK) return v;
+    md.d_table = NULL; md.d_lifter = NULL;
+    st = vvb_device_ready();
+    if (st) return to_status(st);
+    st = vvb_stream_create(&stream);
+    if (!st) st = vvdsp_internal_mfcc_device_build(n_mels, num_mfcc_coeffs, lifter_coeff, stream, &md);
+    if (!st) st = vvb_malloc((void**)&d_in, num_frames * n_mels * sizeof(float));
+    if (!st) st = vvb_malloc((void**)&d_out, num_frames * num_mfcc_coeffs * sizeof(float));
+    if (!st) st = vvb_memcpy_h2d(d_in, log_mel_spectrogram, num_frames * n_mels * sizeof(float), stream);
+    if (!st) st = vvb_mfcc(d_in, num_frames, n_mels, num_mfcc_coeffs, md.d_table, md.d_lifter, d_out, stream);
+    if (!st) st = vvb_memcpy_d2h(out_mfcc_coeffs, d_out, num_frames * num_mfcc_coeffs * sizeof(float), stream);
+    if (stream) { int s2 = vvb_stream_sync(stream); if (!st) st = s2; }
+    vvb_free(d_in); vvb_free(d_out); vvdsp_internal_mfcc_device_free(&md);
+    if (stream) vvb_stream_destroy(stream);
+    return to_status(st);
+}
+
+struct vv_dsp_mfcc_plan {
+    size_t n_fft, n_mels, n_coeffs, bins;
+    vv_dsp_dct_type dct_type;
+    vv_dsp_real lifter, log_epsilon;
+    vv_dsp_real* weights;            /* host filterbank, as the reference keeps it */
+    mel_device mel; mfcc_device mfcc; int on_device;
+    void* stream;
+};
+
+vv_dsp_status vv_dsp_mfcc_init(size_t n_fft, size_t n_mels, size_t num_mfcc_coeffs, vv_dsp_real sample_rate, vv_dsp_real fmin,
+                               vv_dsp_real fmax, vv_dsp_mel_variant variant, vv_dsp_dct_type dct_type, vv_dsp_real lifter_coeff,
+                               vv_dsp_real log_epsilon, vv_dsp_mfcc_plan** out_plan)
+{
+    vv_dsp_mfcc_plan* p;
+    size_t nf = 0, fl = 0;
+    vv_dsp_status v;
+    if (!out_plan) return VV_DSP_ERROR_NULL_POINTER;
+    if (n_fft == 0 || n_mels == 0 || num_mfcc_coeffs == 0 || sample_rate <= 0.0f) return VV_DSP_ERROR_INVALID_SIZE;
+    if (num_mfcc_coeffs > n_mels || fmin < 0.0f || fmax <= fmin || fmax > sample_rate / 2.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
+    p = (vv_dsp_mfcc_plan*)calloc(1, sizeof(*p));
+    if (!p) return VV_DSP_ERROR_INTERNAL;
+    p->n_fft = n_fft; p->n_mels = n_mels; p->n_coeffs = num_mfcc_coeffs; p->bins = n_fft / 2 + 1;
+    p->dct_type = dct_type; p->lifter = lifter_coeff; p->log_epsilon = log_epsilon;
+    v = vv_dsp_mel_filterbank_create(n_fft, n_mels, sample_rate, fmin, fmax, variant, &p->weights, &nf, &fl);
+    if (v != VV_DSP_OK) { free(p); return v; }
+    *out_plan = p;                   /* device tables are built on first use, so init works like the reference's */
+    return VV_DSP_OK;
+}
+
+vv_dsp_status vv_dsp_mfcc_process(const vv_dsp_mfcc_plan* plan, const vv_dsp_real* power_spectrogram, size_t num_frames,
+                                  vv_dsp_real* out_mfcc_coeffs)
+{
+    vv_dsp_mfcc_plan* p = (vv_dsp_mfcc_plan*)plan;    /* the device tables are a cache, not logical state */
+    float *d_p = NULL, *d_lm = NULL, *d_o = NULL;
+    vv_dsp_status v;
+    int st;
+    if (!plan || !power_spectrogram || !out_mfcc_coeffs) return VV_DSP_ERROR_NULL_POINTER;
+    if (num_frames == 0) return VV_DSP_ERROR_INVALID_SIZE;
+    if (p->log_epsilon < 0.0f) return VV_DSP_ERROR_OUT_OF_RANGE;         /* compute_log_mel's check comes first */
+    v = mfcc_validate(num_frames, p->n_mels, p->n_coeffs, p->dct_type, p->lifter);
+    if (v != VV_DSP_OK) return v;
+    st = vvb_device_ready();
+    if (st) return to_status(st);
+    if (!p->on_device) {
+        st = vvb_stream_create(&p->stream);
+        if (!st) st = vvdsp_internal_mel_device_build(p->weights, p->n_mels, p->bins, p->stream, &p->mel);
+        if (!st) st = vvdsp_internal_mfcc_device_build(p->n_mels, p->n_coeffs, p->lifter, p->stream, &p->mfcc);
+        if (st) {
+            vvdsp_internal_mel_device_free(&p->mel); vvdsp_internal_mfcc_device_free(&p->mfcc);
+            if (p->stream) { vvb_stream_destroy(p->stream); p->stream = NULL; }
+            return to_status(st);
+        }
+        p->on_device = 1;
+    }
+    st = vvb_malloc((void**)&d_p, num_frames * p->bins * sizeof(float));
+    if (!st) st = vvb_malloc((void**)&d_lm, num_frames * p->n_mels * sizeof(float));
+    if (!st) st = vvb_malloc((void**)&d_o, num_frames * p->n_coeffs * sizeof(float));
+    if (!st) st = vvb_memcpy_h2d(d_p, power_spectrogram, num_frames * p->bins * sizeof(float), p->stream);
+    if (!st) st = vvb_logmel(d_p, num_frames, p->bins, p->bins, p->mel.d_meta, p->mel.d_w, p->n_mels, p->mel.n_groups,
+                             p->log_epsilon, d_lm, p->stream);
+    if (!st) st = vvb_mfcc(d_lm, num_frames, p->n_mels, p->n_coeffs, p->mfcc.d_table, p->mfcc.d_lifter, d_o, p->stream);
+    if (!st) st = vvb_memcpy_d2h(out_mfcc_coeffs, d_o, num_frames * p->n_coeffs * sizeof(float), p->stream);
+    { int s2 = vvb_stream_sync(p->stream); if (!st) st = s2; }
+    vvb_free(d_p); vvb_free(d_lm); vvb_free(d_o);
+    return to_status(st);
+}
+
+vv_dsp_status vv_dsp_mfcc_destroy(vv_dsp_mfcc_plan* plan)
+{
+    if (!plan) return VV_DSP_ERROR_NULL_POINTER;
+    if (plan->on_device) { vvdsp_internal_mel_device_free(&plan->mel); vvdsp_internal_mfcc_device_free(&plan->mfcc); }
+    if (plan->stream) vvb_stream_destroy(plan->stream);
+    vv_dsp_mel_filterbank_free(plan->weights, plan->n_mels);
+    free(plan);
+    return VV_DSP_OK;
+}

@@ -49,6 +49,9 @@ struct vv_dsp_stft {
     /* log-mel chain: power scratch (grown on demand) and the last filterbank in device-sparse form */
     float* d_mel_scratch; size_t mel_scratch_bytes;
     mel_device mel; const float* mel_key_ptr; size_t mel_key_n; unsigned long long mel_key_hash;
+    /* MFCC tail of that chain: log-mel scratch and the cosine / lifter tables of the last (n_mels, n_coeffs, lifter) */
+    float* d_logmel_scratch; size_t logmel_scratch_bytes;
+    mfcc_device mfcc;
     /* 1/sum(w^2) tables per frame count: [head nfft-hop | mid hop | tail nfft-hop] */
     struct { size_t frames; float* d_tab; int used; } norm[NORM_CACHE];
     int norm_next;
@@ -77,6 +80,7 @@ static void handle_free(vv_dsp_stft* h)
     }
     for (i = 0; i < NORM_CACHE; ++i) vvb_free(h->norm[i].d_tab);
     vvb_free(h->d_mel_scratch); vvdsp_internal_mel_device_free(&h->mel);
+    vvb_free(h->d_logmel_scratch); vvdsp_internal_mfcc_device_free(&h->mfcc);
     for (i = 0; i < NDEP; ++i) if (h->dep[i].ev) vvb_event_destroy(h->dep[i].ev);
     vvb_host_free(h->h_in); vvb_host_free(h->h_spec); vvb_host_free(h->h_frame);
     vvb_free(h->d_in); vvb_free(h->d_spec); vvb_free(h->d_frame);
@@ -473,12 +477,15 @@ vv_dsp_status vv_dsp_stft_spectrogram(vv_dsp_stft* h, const vv_dsp_real* signal,
 /* -------------------------------------------------- STFT -> power -> log-mel (include/vv_dsp/b200.h) */
 /* Chunks of signals whose power spectrogram fits a bounded device scratch; per chunk the fused power
  * kernel and the HBM-bound log-mel kernel run back to back on one stream. */
-vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch,
-                                       size_t n, size_t signal_pitch, vv_dsp_frame_convention convention,
-                                       const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
-                                       vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames)
+/* STFT -> power -> log-mel [-> MFCC when n_coeffs > 0]; `width` = floats per output frame */
+static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch,
+                                     size_t n, size_t signal_pitch, vv_dsp_frame_convention convention,
+                                     const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
+                                     size_t n_coeffs, vv_dsp_real lifter,
+                                     vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames)
 {
     const size_t scratch_target = (size_t)768 << 20;
+    const size_t width = n_coeffs ? n_coeffs : n_mels;
     size_t frames, per_signal, cs, done, i;
     float *d_power, *d_x = NULL, *d_o = NULL;
     unsigned long long hash = 1469598103934665603ull;
@@ -488,6 +495,8 @@ vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signal
     if ((unsigned)convention > 3u || (unsigned)signals_space > 1u || (unsigned)out_space > 1u) return VV_DSP_ERROR_OUT_OF_RANGE;
     if (n_mels == 0) return VV_DSP_ERROR_INVALID_SIZE;
     if (log_epsilon < 0.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
+    if (n_coeffs > n_mels) return VV_DSP_ERROR_INVALID_SIZE;
+    if (lifter < 0.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
     if (signal_pitch == 0) signal_pitch = n;
     if (signal_pitch < n) return VV_DSP_ERROR_INVALID_SIZE;
     frames = vv_dsp_stft_num_frames(h, n, convention);
@@ -515,13 +524,27 @@ vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signal
         if (!st) h->mel_scratch_bytes = cs * per_signal;
     }
     d_power = h->d_mel_scratch;
+    if (!st && n_coeffs) {
+        if (!h->mfcc.d_table || h->mfcc.n_mels != n_mels || h->mfcc.n_coeffs != n_coeffs || h->mfcc.lifter != lifter) {
+            st = vvb_stream_sync(stream);
+            vvdsp_internal_mfcc_device_free(&h->mfcc);
+            if (!st) st = vvdsp_internal_mfcc_device_build(n_mels, n_coeffs, lifter, stream, &h->mfcc);
+        }
+        if (!st && h->logmel_scratch_bytes < cs * frames * n_mels * sizeof(float)) {
+            st = vvb_stream_sync(stream);
+            vvb_free(h->d_logmel_scratch); h->d_logmel_scratch = NULL; h->logmel_scratch_bytes = 0;
+            if (!st) st = vvb_malloc((void**)&h->d_logmel_scratch, cs * frames * n_mels * sizeof(float));
+            if (!st) h->logmel_scratch_bytes = cs * frames * n_mels * sizeof(float);
+        }
+    }
     if (!st && signals_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&d_x, cs * (n ? n : 1) * sizeof(float));
-    if (!st && out_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&d_o, cs * frames * n_mels * sizeof(float));
+    if (!st && out_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&d_o, cs * frames * width * sizeof(float));
     for (done = 0; done < batch && !st; done += cs) {
         const size_t nb = (batch - done < cs) ? batch - done : cs;
         const float* x_dev = signals + done * signal_pitch;
         size_t xp = signal_pitch;
-        float* o_dev = out + done * frames * n_mels;
+        float* o_dev = out + done * frames * width;
+        float* lm_dev;
         if (signals_space == VV_DSP_MEM_HOST) {
             if (n) st = vvb_memcpy2d_h2d(d_x, n * sizeof(float), signals + done * signal_pitch, signal_pitch * sizeof(float),
                                          n * sizeof(float), nb, stream);
@@ -529,9 +552,11 @@ vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signal
         }
         if (out_space == VV_DSP_MEM_HOST) o_dev = d_o;
         if (!st) st = vvb_stft_forward(h->eng, x_dev, nb, n, xp, frames, pad, VVB_OUT_POWER, d_power, h->bins, stream);
-        if (!st) st = vvb_logmel(d_power, nb * frames, h->bins, h->bins, h->mel.d_meta, h->mel.d_w, n_mels, h->mel.n_groups, log_epsilon, o_dev, stream);
+        lm_dev = n_coeffs ? h->d_logmel_scratch : o_dev;
+        if (!st) st = vvb_logmel(d_power, nb * frames, h->bins, h->bins, h->mel.d_meta, h->mel.d_w, n_mels, h->mel.n_groups, log_epsilon, lm_dev, stream);
+        if (!st && n_coeffs) st = vvb_mfcc(lm_dev, nb * frames, n_mels, n_coeffs, h->mfcc.d_table, h->mfcc.d_lifter, o_dev, stream);
         if (!st && out_space == VV_DSP_MEM_HOST)
-            st = vvb_memcpy_d2h(out + done * frames * n_mels, d_o, nb * frames * n_mels * sizeof(float), stream);
+            st = vvb_memcpy_d2h(out + done * frames * width, d_o, nb * frames * width * sizeof(float), stream);
         if (!st && signals_space == VV_DSP_MEM_HOST) st = vvb_stream_sync(stream);   /* staging buffer reuse */
     }
     /* device-resident calls only enqueue (scratch and filterbank live in the handle); host buffers: synchronous */
@@ -540,4 +565,24 @@ vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signal
         vvb_free(d_x); vvb_free(d_o);
     }
     return map_status(st);
+}
+
+vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch,
+                                       size_t n, size_t signal_pitch, vv_dsp_frame_convention convention,
+                                       const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
+                                       vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames)
+{
+    return batch_mel_chain(h, signals, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels, log_epsilon,
+                           0, 0.0f, out, out_space, out_frames);
+}
+
+vv_dsp_status vv_dsp_stft_batch_mfcc(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch,
+                                     size_t n, size_t signal_pitch, vv_dsp_frame_convention convention,
+                                     const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
+                                     size_t num_mfcc_coeffs, vv_dsp_real lifter_coeff,
+                                     vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames)
+{
+    if (num_mfcc_coeffs == 0) return VV_DSP_ERROR_INVALID_SIZE;
+    return batch_mel_chain(h, signals, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels, log_epsilon,
+                           num_mfcc_coeffs, lifter_coeff, out, out_space, out_frames);
 }
