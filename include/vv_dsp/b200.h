@@ -141,6 +141,15 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_fft_execute_batch(const vv_dsp_fft_plan* p
                                                         vv_dsp_mem_space in_space, void* out,
                                                         vv_dsp_mem_space out_space, size_t batch, void* cuda_stream);
 
+/* WAV sample decode on the device: interleaved little-endian samples, as they
+ * sit in the data chunk of a WAV file, to planar float32 [channels][planar_pitch] with the scaling of the
+ * reference's reader (src/audio/wav.c:458-521): format 16 / 24 / 32 = signed PCM times 2^-15 / 2^-23 / 2^-31,
+ * format -32 = IEEE float32.  planar_pitch 0 = num_samples.  A HOST input is staged (the upload carries 2 or
+ * 3 bytes per sample instead of 4); DEVICE in and out: enqueued on cuda_stream and not awaited. */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_b200_pcm_to_planar(const void* interleaved, vv_dsp_mem_space in_space, int format,
+                                                         size_t num_samples, size_t channels, vv_dsp_real* planar,
+                                                         vv_dsp_mem_space out_space, size_t planar_pitch, void* cuda_stream);
+
 /* Library / device introspection */
 const char* vv_dsp_b200_version(void);
 /* last CUDA error text seen by the calling thread ("" if none) */

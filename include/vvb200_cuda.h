@@ -80,6 +80,10 @@ int vvb_logmel(const float* d_power, size_t frames, size_t bins, size_t power_pi
 int vvb_mfcc(const float* d_logmel, size_t frames, size_t n_mels, size_t n_coeffs, const float* d_table,
              const float* d_lifter, float* d_out, void* stream);
 
+/* ---- PCM decode: interleaved little-endian samples (format 16/24/32 = signed PCM, -32 = float32) -> planar float32 */
+int vvb_pcm_to_planar(const void* d_interleaved, int format, size_t num_samples, size_t channels, float* d_planar,
+                      size_t pitch, void* stream);
+
 /* ---- FFT engine (plan API): type 0 C2C, 1 R2C, 2 C2R; dir +1 / -1 */
 int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine** out);
 void vvb_fft_engine_destroy(vvb_fft_engine* e);

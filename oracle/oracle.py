@@ -266,6 +266,16 @@ class Oracle(_Base):
         assert st == 0, st
         return out
 
+    def pcm_to_planar(self, raw, fmt, channels):
+        """raw: bytes-like interleaved little-endian samples; fmt 16 / 24 / 32 (PCM) or -32 (float32)"""
+        raw = np.frombuffer(bytes(raw), np.uint8)
+        n = raw.size // (abs(fmt) // 8) // channels
+        out = np.zeros((channels, n), np.float32)
+        self.lib.orc_pcm_to_planar.restype = C.c_int
+        st = self.lib.orc_pcm_to_planar(_p(raw), C.c_int(fmt), _sz(n), _sz(channels), _p(out), _sz(n))
+        assert st == 0, st
+        return out
+
     def mfcc(self, log_mel, n_coeffs, lifter=0.0, dct_type=2):
         log_mel = _f32(log_mel)
         out = np.empty((log_mel.shape[0], max(n_coeffs, 1)), np.float32)
@@ -437,6 +447,19 @@ class Reference(_Base):
         st = self.lib.vv_dsp_mfcc(_p(log_mel), _sz(log_mel.shape[0]), _sz(log_mel.shape[1]), _sz(n_coeffs), C.c_int(dct_type),
                                   C.c_float(lifter), _p(out))
         return st, out[:, :n_coeffs]
+
+    def wav_read(self, path):
+        """vv_dsp_wav_read (src/audio/wav.c:288-370) -> float32 [channels, samples]"""
+        class Info(C.Structure):
+            _fields_ = [("num_samples", _sz), ("num_channels", C.c_int), ("sample_rate", C.c_double), ("bit_depth", C.c_int),
+                        ("is_float", C.c_int)]
+        buf = C.POINTER(C.POINTER(C.c_float))()
+        info = Info()
+        st = self.lib.vv_dsp_wav_read(str(path).encode(), C.byref(buf), C.byref(info))
+        assert st == 0, st
+        out = np.stack([np.ctypeslib.as_array(buf[c], shape=(info.num_samples,)).copy() for c in range(info.num_channels)])
+        self.lib.vv_dsp_wav_free_buffer(C.byref(buf), info.num_channels)
+        return out
 
     def mfcc_plan_process(self, power, n_fft, n_mels, n_coeffs, sr, fmin, fmax, lifter, eps):
         """vv_dsp_mfcc_init -> vv_dsp_mfcc_process -> vv_dsp_mfcc_destroy (src/features/mel.c:333-461)"""

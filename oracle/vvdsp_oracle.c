@@ -25,6 +25,7 @@
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdint.h>
 
 typedef struct { float re, im; } orc_cpx;
 
@@ -556,5 +557,29 @@ int orc_mfcc(const float *log_mel, size_t frames, size_t n_mels, size_t n_coeffs
                 c[i] *= factor;
             }
     }
+    return 0;
+}
+
+/* src/audio/wav.c:458-521: interleaved little-endian samples -> planar float32 [channels][pitch].
+ * format 16 / 24 / 32 = signed PCM scaled by 1/2^15, 1/2^23, 1/2^31; format -32 = IEEE float32 copied. */
+int orc_pcm_to_planar(const void *interleaved, int format, size_t num_samples, size_t channels, float *planar, size_t pitch)
+{
+    const unsigned char *b = (const unsigned char *)interleaved;
+    if (!interleaved || !planar) return 1;
+    if (num_samples == 0 || channels == 0 || pitch < num_samples) return 2;
+    if (format != 16 && format != 24 && format != 32 && format != -32) return 3;
+    for (size_t s = 0; s < num_samples; ++s)
+        for (size_t c = 0; c < channels; ++c) {
+            const size_t i = s * channels + c;
+            float v;
+            if (format == -32) { memcpy(&v, b + 4 * i, 4); }
+            else if (format == 16) { int16_t q; memcpy(&q, b + 2 * i, 2); v = (float)q * (float)(1.0 / 32768.0); }
+            else if (format == 24) {
+                int32_t q = (int32_t)b[3 * i] | ((int32_t)b[3 * i + 1] << 8) | ((int32_t)b[3 * i + 2] << 16);
+                if (q & 0x800000) q |= (int32_t)0xFF000000;
+                v = (float)q * (float)(1.0 / 8388608.0);
+            } else { int32_t q; memcpy(&q, b + 4 * i, 4); v = (float)q * (float)(1.0 / 2147483648.0); }
+            planar[c * pitch + s] = v;
+        }
     return 0;
 }

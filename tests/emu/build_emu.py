@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "obj")
 
 def build(force=False):
     os.makedirs(OBJ, exist_ok=True)
-    host = [os.path.join(PKG, "csrc", "host", f) for f in ("window.c", "framing.c", "fft.c", "stft.c", "mel.c")]
+    host = [os.path.join(PKG, "csrc", "host", f) for f in ("window.c", "framing.c", "fft.c", "stft.c", "mel.c", "pcm.c")]
     cu = os.path.join(PKG, "csrc", "cuda", "vvb_cuda.cu")
     deps = host + [cu, os.path.join(HERE, "cuda_emu.h")]
     for d, _, fs in list(os.walk(INC)) + list(os.walk(os.path.join(PKG, "csrc", "cuda"))):

@@ -213,6 +213,42 @@ def check_mfcc(lib, oracle):
         assert got.shape == want.shape and got.tobytes() == want.tobytes()       # same log-mel in, same sums
 
 
+def check_pcm_decode(lib, oracle, golden_dir=None):
+    """vv_dsp_b200_pcm_to_planar against the oracle's restatement of the reference's WAV sample conversion: bit-exact
+    for every format, mono and stereo, extreme codes, and the config-1 voicebank samples."""
+    import ctypes as C
+    from vv_dsp_b200 import pcm_to_planar
+    rng = np.random.default_rng(3)
+    for fmt in (16, 24, 32, -32):
+        for channels in (1, 2, 3):
+            n = 4099
+            if fmt == -32:
+                raw = rng.uniform(-1, 1, n * channels).astype("<f4").tobytes()
+            elif fmt == 24:
+                v = rng.integers(-2**23, 2**23, n * channels, dtype=np.int64)
+                v[:4] = [-2**23, 2**23 - 1, -1, 0]
+                raw = b"".join(int(q & 0xFFFFFF).to_bytes(3, "little") for q in v)
+            else:
+                lim = 2 ** (fmt - 1)
+                v = rng.integers(-lim, lim, n * channels, dtype=np.int64)
+                v[:4] = [-lim, lim - 1, -1, 0]
+                raw = v.astype("<i2" if fmt == 16 else "<i4").tobytes()
+            got = pcm_to_planar(raw, fmt, channels, lib=lib)
+            assert got.tobytes() == oracle.pcm_to_planar(raw, fmt, channels).tobytes(), (fmt, channels)
+    if golden_dir is not None:
+        pcm = np.load(f"{golden_dir}/voicebank_aka_sa_pcm16.npz")["pcm"]
+        got = pcm_to_planar(pcm.astype("<i2").tobytes(), 16, 1, lib=lib)[0]
+        assert got.tobytes() == (pcm.astype(np.float32) / np.float32(32768.0)).tobytes()
+    buf = np.zeros(8, np.uint8)
+    out = np.zeros(8, np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)                                      # noqa: E731
+    f = lib.vv_dsp_b200_pcm_to_planar
+    assert f(None, 0, 16, 4, 1, vp(out), 0, 0, None) == 1 and f(vp(buf), 0, 16, 4, 1, None, 0, 0, None) == 1
+    assert f(vp(buf), 0, 8, 4, 1, vp(out), 0, 0, None) == 3 and f(vp(buf), 2, 16, 4, 1, vp(out), 0, 0, None) == 3
+    assert f(vp(buf), 0, 16, 0, 1, vp(out), 0, 0, None) == 2 and f(vp(buf), 0, 16, 4, 0, vp(out), 0, 0, None) == 2
+    assert f(vp(buf), 0, 16, 4, 1, vp(out), 0, 3, None) == 2
+
+
 def check_status_codes(lib):
     """Return codes of the reference boundary (SURVEY.md section 4 'lifecycle/validation')."""
     import ctypes as C

@@ -96,3 +96,8 @@ def test_accuracy_vs_truth(emu, oracle):
     for nfft in (256, 2048, 8192):
         mine, theirs = pc.check_accuracy_vs_truth(emu, oracle, nfft)
         assert mine < theirs
+
+
+def test_pcm_decode(emu, oracle):
+    import os
+    pc.check_pcm_decode(emu, oracle, os.path.join(os.path.dirname(__file__), "golden"))

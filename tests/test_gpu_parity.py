@@ -262,3 +262,8 @@ def test_stream_sharding_nccl():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "nccl stream sharding ok" in r.stdout
+
+
+def test_pcm_decode(lib, oracle):
+    import os
+    pc.check_pcm_decode(lib, oracle, os.path.join(os.path.dirname(__file__), "golden"))

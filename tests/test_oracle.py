@@ -269,3 +269,38 @@ def test_mfcc_oracle_against_reference(oracle, reference):
     _, w = oracle.mel_filterbank(512, 40, 16000.0, 0.0, 8000.0)
     st2, mine = oracle.mfcc(oracle.log_mel(p, w, 1e-10), 13, 22.0)
     assert st == st2 == 0 and mine.tobytes() == ref.tobytes()
+
+
+def _write_wav(path, raw, fmt, channels, rate=48000):
+    import struct
+    bits = abs(fmt)
+    tag = 3 if fmt < 0 else 1
+    block = channels * bits // 8
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, tag, channels, rate, rate * block,
+                                                                                 block, bits) + b"data" + struct.pack("<I", len(raw))
+    path.write_bytes(hdr + raw)
+
+
+def test_pcm_decode_oracle_against_reference(oracle, reference, tmp_path):
+    """orc_pcm_to_planar (src/audio/wav.c:458-521) is bit-exact against vv_dsp_wav_read of the same bytes, for every
+    sample format the reference reads, mono and interleaved stereo, including the extreme codes."""
+    if not hasattr(reference.lib, "vv_dsp_wav_read"):
+        pytest.skip("oracle/_ref was built without wav.c")
+    rng = np.random.default_rng(3)
+    for fmt in (16, 24, 32, -32):
+        for channels in (1, 2):
+            n = 1001
+            if fmt == -32:
+                raw = rng.uniform(-1, 1, n * channels).astype("<f4").tobytes()
+            elif fmt == 24:
+                v = rng.integers(-2**23, 2**23, n * channels, dtype=np.int64)
+                v[:4] = [-2**23, 2**23 - 1, -1, 0]
+                raw = b"".join(int(q & 0xFFFFFF).to_bytes(3, "little") for q in v)
+            else:
+                lim = 2 ** (fmt - 1)
+                v = rng.integers(-lim, lim, n * channels, dtype=np.int64)
+                v[:4] = [-lim, lim - 1, -1, 0]
+                raw = v.astype("<i2" if fmt == 16 else "<i4").tobytes()
+            path = tmp_path / f"t_{fmt}_{channels}.wav"
+            _write_wav(path, raw, fmt, channels)
+            assert oracle.pcm_to_planar(raw, fmt, channels).tobytes() == reference.wav_read(path).tobytes(), (fmt, channels)

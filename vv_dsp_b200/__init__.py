@@ -9,7 +9,7 @@ fails loudly when the CUDA library has not been built.
 """
 from .api import (  # noqa: F401
     CONVENTIONS, KINDS, WINDOWS, FftPlan, Library, Stft, VvDspError, default_library,
-    fetch_frame, get_num_frames, overlap_add, window, mel_filterbank, log_mel_spectrogram, mfcc, MfccPlan,
+    fetch_frame, get_num_frames, overlap_add, window, mel_filterbank, log_mel_spectrogram, mfcc, MfccPlan, pcm_to_planar,
 )
 
 __all__ = ["Stft", "FftPlan", "Library", "VvDspError", "default_library", "window", "get_num_frames",

@@ -84,6 +84,7 @@ class Library:
                                        C.POINTER(_vp)]),
         "vv_dsp_mfcc_process": (C.c_int, [_vp, _vp, _sz, _vp]),
         "vv_dsp_mfcc_destroy": (C.c_int, [_vp]),
+        "vv_dsp_b200_pcm_to_planar": (C.c_int, [_vp, C.c_int, C.c_int, _sz, _sz, _vp, C.c_int, _sz, _vp]),
         "vv_dsp_b200_version": (C.c_char_p, []),
         "vv_dsp_b200_last_error": (C.c_char_p, []),
         "vv_dsp_b200_kernel_launches": (C.c_ulonglong, []),
@@ -208,6 +209,28 @@ def log_mel_spectrogram(power, weights, log_epsilon, lib: Library | None = None)
     st = lib.vv_dsp_compute_log_mel_spectrogram(_ptr(power), power.shape[0], power.shape[1], _ptr(weights), weights.shape[0],
                                                 log_epsilon, _ptr(out))
     _check(lib, st, "vv_dsp_compute_log_mel_spectrogram")
+    return out
+
+
+def pcm_to_planar(raw, fmt, channels, out=None, stream=0, lib: Library | None = None):
+    """vv_dsp_b200_pcm_to_planar: interleaved little-endian samples (bytes / numpy uint8 / torch CUDA uint8) of
+    format 16 / 24 / 32 (PCM) or -32 (float32) -> float32 [channels, samples] (numpy, or torch when out is)."""
+    lib = lib or default_library()
+    dev_in = _is_device(raw)
+    if not dev_in:
+        raw = np.frombuffer(bytes(raw), np.uint8) if not isinstance(raw, np.ndarray) else np.ascontiguousarray(raw).view(np.uint8)
+    nbytes = int(raw.numel()) if dev_in else int(raw.size)
+    n = nbytes // (abs(fmt) // 8) // max(channels, 1)
+    if out is None:
+        if dev_in:
+            import torch
+            out = torch.empty((channels, n), device=raw.device, dtype=torch.float32)
+        else:
+            out = np.empty((channels, n), np.float32)
+    pitch = int(out.stride(0)) if _is_device(out) else n
+    st = lib.vv_dsp_b200_pcm_to_planar(_ptr(raw), DEVICE if dev_in else HOST, fmt, n, channels, _ptr(out),
+                                       DEVICE if _is_device(out) else HOST, pitch, stream)
+    _check(lib, st, "vv_dsp_b200_pcm_to_planar")
     return out
 
 

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 INC = os.path.join(ROOT, "include")
 LIB = os.path.join(PKG, "lib", "libvvdsp_b200.so")
 OBJ = os.path.join(PKG, "lib", "obj")
-HOST_SRCS = [os.path.join(PKG, "csrc", "host", f) for f in ("window.c", "framing.c", "fft.c", "stft.c", "mel.c")]
+HOST_SRCS = [os.path.join(PKG, "csrc", "host", f) for f in ("window.c", "framing.c", "fft.c", "stft.c", "mel.c", "pcm.c")]
 CUDA_SRCS = [os.path.join(PKG, "csrc", "cuda", "vvb_cuda.cu")]
 CUDA_DEPS = [os.path.join(PKG, "csrc", "cuda", f) for f in
              ("vvb_fft_core.cuh", "vvb_stft_kernels.cuh", "vvb_direct_kernels.cuh")]

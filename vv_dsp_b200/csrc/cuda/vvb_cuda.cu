@@ -734,6 +734,24 @@ extern "C" int vvb_mfcc(const float* d_logmel, size_t frames, size_t n_mels, siz
     return 0;
 }
 
+extern "C" int vvb_pcm_to_planar(const void* d_interleaved, int format, size_t num_samples, size_t channels, float* d_planar,
+                                 size_t pitch, void* stream)
+{
+    if (!d_interleaved || !d_planar) return fail(1, "vvb_pcm_to_planar", "null");
+    if (num_samples == 0 || channels == 0) return 0;
+    if (channels > 0x7fffffffu) return fail(2, "vvb_pcm_to_planar", "size");
+#ifndef VVB_EMU
+    if (int st = vvb_device_ready()) return st;
+#endif
+    PcmArgs a;
+    a.in = (const unsigned char*)d_interleaved; a.format = format; a.num_samples = (long long)num_samples; a.channels = (int)channels;
+    a.out = d_planar; a.pitch = (long long)pitch;
+    const long long total = (long long)(num_samples * channels);
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)rt_num_sms() * 16);
+    VVB_LAUNCH(pcm_to_planar_kernel, grid, 256, 0, stream, a);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- FP32 peak probe */
 /* Measures the FP32 FMA throughput the roofline is quoted against: 16 independent dependent-FMA
  * chains per thread, scalar FFMA or packed FFMA2.  Diagnostics only (bench.py's roofline_fp32). */

@@ -409,4 +409,39 @@ __global__ void __launch_bounds__(256) mfcc_kernel(const MfccArgs a)
     }
 }
 
+/* ------------------------------------------------------------------ PCM decode */
+/* interleaved little-endian WAV samples -> planar float32, the reference's src/audio/wav.c:458-521:
+ * (float)code * 2^-15 / 2^-23 / 2^-31 (int -> float rounds to nearest even like the C cast, the scale is a
+ * power of two, so the result is exact to the bit); format -32 copies IEEE float32.  One thread per output
+ * sample, consecutive threads along time: stores are coalesced, loads too for mono. */
+struct PcmArgs {
+    const unsigned char* in; int format; long long num_samples; int channels;
+    float* out; long long pitch;
+};
+
+__global__ void pcm_to_planar_kernel(const PcmArgs a)
+{
+    const long long total = a.num_samples * a.channels;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long s = idx % a.num_samples;
+        const int c = (int)(idx / a.num_samples);
+        const long long i = s * a.channels + c;
+        float v;
+        if (a.format == -32) {
+            v = reinterpret_cast<const float*>(a.in)[i];
+        } else if (a.format == 16) {
+            v = __fmul_rn((float)reinterpret_cast<const short*>(a.in)[i], 1.0f / 32768.0f);
+        } else if (a.format == 24) {
+            const unsigned char* b = a.in + 3 * i;
+            int q = (int)b[0] | ((int)b[1] << 8) | ((int)b[2] << 16);
+            if (q & 0x800000) q |= (int)0xFF000000;
+            v = __fmul_rn((float)q, 1.0f / 8388608.0f);
+        } else {
+            v = __fmul_rn((float)reinterpret_cast<const int*>(a.in)[i], 1.0f / 2147483648.0f);
+        }
+        a.out[c * a.pitch + s] = v;
+    }
+}
+
 }  // namespace vvb
