@@ -335,6 +335,72 @@ def check_accuracy_vs_truth(lib, oracle, nfft):
     return mine, theirs
 
 
+def check_bluestein(lib, oracle, sizes):
+    """Sizes served by the chirp-z path (no Stockham kernel, 32 <= n <= 2048).  The reference serves them with an O(n^2)
+    float32 DFT whose own error grows with n (measured here: 2.5e-5 at n=400, 6e-5 at 1000, 1.5e-4 at 2000 of max|X|),
+    so the yardstick is float64 truth: the CUDA result must be within 3e-6 of it, and within the triangle bound
+    (own error + the oracle's error) of the oracle.  Frame counts and zero regions stay bit-exact."""
+    report = {}
+    rng = np.random.default_rng(21)
+    for nfft, hop in sizes:
+        n = nfft + hop * 7 + 13
+        x = np.stack([noise(70 + nfft + i, n) for i in range(2)])
+        for win in ("hann", "hamming"):
+            w = oracle.window(win, nfft)[1]
+            with Stft(nfft, hop, win, lib=lib) as h:
+                for conv in ("valid", "center", "spectrogram"):
+                    s = h.batch_forward(x, "complex", conv)
+                    assert s.shape[1] == oracle.num_frames(n, nfft, hop, conv), conv
+                s = h.batch_forward(x, "complex", "valid")
+                p = h.batch_forward(x, "power", "valid")
+                F = s.shape[1]
+                truth = np.stack([stft_truth_f64(x[i], w, nfft, hop, F) for i in range(2)])
+                ref = np.stack([oracle.stft(x[i], nfft, hop, win) for i in range(2)])
+                mx = np.abs(truth).max()
+                mine, theirs = np.abs(s - truth).max() / mx, np.abs(ref - truth).max() / mx
+                assert mine < 3e-6, (nfft, win, mine)
+                assert np.abs(s - ref).max() / mx <= mine + theirs + 1e-7
+                assert np.abs(p - np.abs(truth) ** 2).max() <= 6e-6 * mx * mx
+                # synthesis: float64 overlap-add of irfft(spec) * w, divided by sum(w^2) where > 1e-12
+                y = h.batch_inverse(ref, n, True)
+                raw = h.batch_inverse(ref, n, False)
+                acc = np.zeros((2, n + nfft)); norm = np.zeros(n + nfft)
+                for f in range(F):
+                    fr = np.fft.irfft(ref[:, f].astype(np.complex128), nfft, axis=-1) * w.astype(np.float64)
+                    acc[:, f * hop:f * hop + nfft] += fr
+                    norm[f * hop:f * hop + nfft] += w.astype(np.float64) ** 2
+                acc, norm = acc[:, :n], norm[:n]
+                assert np.abs(raw - acc).max() <= 3e-6 * np.abs(acc).max()
+                cov = (F - 1) * hop + nfft
+                assert np.all(y[:, cov:] == 0) and np.all(raw[:, cov:] == 0)
+                if 2 * hop <= nfft:
+                    good = norm > 1e-3
+                    yt = np.where(good, acc / np.where(good, norm, 1), 0)
+                    assert np.abs(y - yt)[:, good].max() <= 2e-5 * np.abs(yt).max()
+                    own = h.batch_inverse(s, n, True)
+                    assert rel_l2(own[:, nfft:n - nfft], x[:, nfft:n - nfft]) <= ROUNDTRIP_REL_L2
+                    oref = np.stack([oracle.istft(ref[i], nfft, hop, n, win) for i in range(2)])
+                    assert rel_l2(y[:, nfft:n - nfft], oref[:, nfft:n - nfft]) <= 2e-4     # the oracle's inverse DFT error dominates
+        report[nfft] = (float(mine), float(theirs))
+        # plan API
+        z = (rng.uniform(-1, 1, (3, nfft)) + 1j * rng.uniform(-1, 1, (3, nfft))).astype(np.complex64)
+        xr = rng.uniform(-1, 1, (3, nfft)).astype(np.float32)
+        f = FftPlan(nfft, 0, +1, lib=lib).execute_batch(z)
+        b = FftPlan(nfft, 0, -1, lib=lib).execute_batch(z)
+        r = FftPlan(nfft, 1, +1, lib=lib).execute_batch(xr)
+        c = FftPlan(nfft, 2, -1, lib=lib).execute_batch(r)
+        z64 = z.astype(np.complex128)
+        assert np.abs(f - np.fft.fft(z64, axis=-1)).max() <= 3e-6 * np.abs(np.fft.fft(z64, axis=-1)).max()
+        assert np.abs(b - np.fft.ifft(z64, axis=-1)).max() <= 3e-6 * np.abs(np.fft.ifft(z64, axis=-1)).max()
+        rt = np.fft.rfft(xr.astype(np.float64), axis=-1)
+        assert np.abs(r - rt).max() <= 3e-6 * np.abs(rt).max()
+        assert np.abs(c - xr).max() < 5e-6
+        assert np.array_equal(f[1], FftPlan(nfft, 0, +1, lib=lib).execute(z[1]))
+        fo = oracle.fft_c2c(z[0], +1)
+        assert np.abs(f[0] - fo).max() <= np.abs(f[0] - np.fft.fft(z64[0])).max() + np.abs(fo - np.fft.fft(z64[0])).max() + 1e-6
+    return report
+
+
 def check_golden_slices(lib, golden):
     """GPU/emulator output against slices of the REAL reference's output (tests/golden/)."""
     for c in golden["cases"]:

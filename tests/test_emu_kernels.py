@@ -101,3 +101,17 @@ def test_accuracy_vs_truth(emu, oracle):
 def test_pcm_decode(emu, oracle):
     import os
     pc.check_pcm_decode(emu, oracle, os.path.join(os.path.dirname(__file__), "golden"))
+
+
+def test_bluestein_sizes(emu, oracle):
+    report = pc.check_bluestein(emu, oracle, [(400, 160), (33, 11), (96, 24), (1000, 250)])
+    print("error vs float64 truth (mine, reference):", report)
+
+
+def test_bluestein_unfused_and_direct_paths(emu, oracle, monkeypatch):
+    """the multi-kernel chirp-z pipeline and the O(n^2) kernels stay selectable (read when a plan is created)"""
+    monkeypatch.setenv("VVB_BLUESTEIN_UNFUSED", "1")
+    pc.check_bluestein(emu, oracle, [(400, 160), (100, 25)])
+    monkeypatch.delenv("VVB_BLUESTEIN_UNFUSED")
+    monkeypatch.setenv("VVB_NO_BLUESTEIN", "1")
+    pc.check_bluestein(emu, oracle, [(100, 25)])

@@ -267,3 +267,17 @@ def test_stream_sharding_nccl():
 def test_pcm_decode(lib, oracle):
     import os
     pc.check_pcm_decode(lib, oracle, os.path.join(os.path.dirname(__file__), "golden"))
+
+
+def test_bluestein_sizes(lib, oracle):
+    report = pc.check_bluestein(lib, oracle, [(400, 160), (33, 11), (96, 24), (480, 120), (1000, 250), (1536, 384), (2000, 500), (2047, 512), (64, 16)])
+    print("error vs float64 truth (mine, reference):", report)
+
+
+def test_bluestein_unfused_and_direct_paths(lib, oracle, monkeypatch):
+    """the multi-kernel chirp-z pipeline and the O(n^2) kernels stay selectable (read when a plan is created)"""
+    monkeypatch.setenv("VVB_BLUESTEIN_UNFUSED", "1")
+    pc.check_bluestein(lib, oracle, [(400, 160), (100, 25)])
+    monkeypatch.delenv("VVB_BLUESTEIN_UNFUSED")
+    monkeypatch.setenv("VVB_NO_BLUESTEIN", "1")
+    pc.check_bluestein(lib, oracle, [(100, 25)])

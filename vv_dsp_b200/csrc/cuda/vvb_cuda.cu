@@ -196,7 +196,29 @@ template <class C> static constexpr size_t smem_c2c() { return sizeof(float) * (
 
 static bool fast_size(size_t m) { return m == 128 || m == 256 || m == 512 || m == 1024 || m == 2048 || m == 4096; }
 
+/* Bluestein plan for a size without a Stockham kernel (see vvb_direct_kernels.cuh): chirp table, spectrum of the
+ * wrapped conjugate chirp, two power-of-two C2C engines and a work buffer grown on demand. */
+struct Chirp {
+    size_t n = 0, M = 0;
+    float2* d_chirp = nullptr;       /* exp(-j pi i^2 / n), i < n */
+    float2* d_bspec = nullptr;       /* FFT_M of the wrapped conjugate chirp */
+    float2* d_bspec_m = nullptr;     /* the same divided by M (fused kernel: inverse scale folded in) */
+    float* d_tables = nullptr;       /* Tables<C> blob of the M-point plan (fused kernel) */
+    bool fused = true;
+    vvb_fft_engine* fwd = nullptr;   /* C2C size M forward */
+    vvb_fft_engine* bwd = nullptr;   /* C2C size M backward (scaled 1/M) */
+    float2* d_work = nullptr;
+    size_t work_elems = 0;
+};
+static bool chirp_size(size_t n) { return n >= 32 && n <= 2048 && getenv("VVB_NO_BLUESTEIN") == nullptr; }
+static void chirp_destroy(Chirp* c);
+static int chirp_create(size_t n, Chirp** out);
+static int chirp_reserve(Chirp* c, size_t transforms, size_t* chunk);
+static int chirp_convolve(Chirp* c, size_t count, void* stream);
+static int chirp_fused(Chirp* c, ChirpFusedArgs a, int sms, void* stream);
+
 struct vvb_engine {
+    Chirp* chirp = nullptr;          /* sizes served by the Bluestein path */
     size_t nfft = 0, hop = 0;
     bool fast = false;
     int sms = 0;
@@ -260,6 +282,7 @@ extern "C" int vvb_engine_create(size_t nfft, size_t hop, const float* window, v
         make_wtab(t, nfft);
         st = upload(&e->d_win, w);
         if (!st) st = upload((float**)&e->d_wtab, t);
+        if (!st && chirp_size(nfft)) st = chirp_create(nfft, &e->chirp);
     }
     if (st) { vvb_engine_destroy(e); return st; }
     *out = e;
@@ -270,6 +293,7 @@ extern "C" void vvb_engine_destroy(vvb_engine* e)
 {
     if (!e) return;
     vvb_free(e->d_tables); vvb_free(e->d_tables_m); vvb_free(e->d_win); vvb_free(e->d_wtab); vvb_free(e->d_scratch);
+    chirp_destroy(e->chirp);
     delete e;
 }
 
@@ -384,6 +408,32 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
         default: return launch_forward<Cfg4096>(e, a, out_kind, stream);
         }
     }
+    if (e->chirp && e->chirp->fused) {
+        ChirpFusedArgs a;
+        memset(&a, 0, sizeof(a));
+        a.count = (long long)(batch * frames); a.mode = CHIRP_STFT_FWD; a.win = e->d_win;
+        a.x = d_x; a.x_pitch = (long long)x_pitch; a.n_sig = (long long)n; a.frames = (int)frames; a.hop = (int)e->hop;
+        a.pad_mode = pad_mode; a.out_kind = out_kind; a.out = d_out; a.out_pitch = (long long)out_pitch;
+        return chirp_fused(e->chirp, a, e->sms, stream);
+    }
+    if (e->chirp) {
+        Chirp* c = e->chirp;
+        const size_t count = batch * frames;
+        size_t chunk = 0;
+        if (int st = chirp_reserve(c, count, &chunk)) return st;
+        for (size_t g0 = 0; g0 < count; g0 += chunk) {
+            ChirpFwdArgs a;
+            a.x = d_x; a.x_pitch = (long long)x_pitch; a.n_sig = (long long)n;
+            a.frames = (int)frames; a.hop = (int)e->hop; a.nfft = (int)e->nfft; a.pad_mode = pad_mode; a.M = (int)c->M;
+            a.g0 = (long long)g0; a.count = (long long)std::min(chunk, count - g0);
+            a.win = e->d_win; a.chirp = c->d_chirp; a.work = c->d_work;
+            a.out_kind = out_kind; a.out = d_out; a.out_pitch = (long long)out_pitch;
+            VVB_LAUNCH(chirp_pre_stft_kernel, persistent_grid((a.count * a.M + 255) / 256, 8, e->sms), 256, 0, stream, a);
+            if (int st = chirp_convolve(c, (size_t)a.count, stream)) return st;
+            VVB_LAUNCH(chirp_post_stft_kernel, persistent_grid((a.count * (a.nfft / 2 + 1) + 255) / 256, 8, e->sms), 256, 0, stream, a);
+        }
+        return 0;
+    }
     DirFwdArgs a;
     a.x = d_x; a.x_pitch = (long long)x_pitch; a.n = (long long)n;
     a.batch = (int)batch; a.frames = (int)frames; a.hop = (int)e->hop; a.nfft = (int)e->nfft;
@@ -483,6 +533,31 @@ static int ensure_scratch(vvb_engine* e, size_t bytes)
     return st;
 }
 
+/* Bluestein synthesis of `count` frames: Hermitian half spectra -> real frames times `win` (nullptr: none) */
+static int chirp_inverse_frames(vvb_engine* e, const float2* d_spec, size_t count, size_t spec_pitch, float* d_frames,
+                                const float* win, void* stream)
+{
+    Chirp* c = e->chirp;
+    if (c->fused) {
+        ChirpFusedArgs a;
+        memset(&a, 0, sizeof(a));
+        a.count = (long long)count; a.mode = CHIRP_STFT_INV; a.win = win;
+        a.spec = d_spec; a.spec_pitch = (long long)spec_pitch; a.frames_out = d_frames;
+        return chirp_fused(c, a, e->sms, stream);
+    }
+    size_t chunk = 0;
+    if (int st = chirp_reserve(c, count, &chunk)) return st;
+    for (size_t g0 = 0; g0 < count; g0 += chunk) {
+        ChirpInvArgs a;
+        a.spec = d_spec; a.spec_pitch = (long long)spec_pitch; a.g0 = (long long)g0; a.count = (long long)std::min(chunk, count - g0);
+        a.nfft = (int)e->nfft; a.M = (int)c->M; a.win = win; a.chirp = c->d_chirp; a.work = c->d_work; a.frames_out = d_frames;
+        VVB_LAUNCH(chirp_pre_spec_kernel, persistent_grid((a.count * a.M + 255) / 256, 8, e->sms), 256, 0, stream, a);
+        if (int st = chirp_convolve(c, (size_t)a.count, stream)) return st;
+        VVB_LAUNCH(chirp_post_frames_kernel, persistent_grid((a.count * a.nfft + 255) / 256, 8, e->sms), 256, 0, stream, a);
+    }
+    return 0;
+}
+
 extern "C" int vvb_stft_inverse_frames(vvb_engine* e, const vvb_cpx* d_spec, size_t count, size_t spec_pitch,
                                        float* d_frames, void* stream)
 {
@@ -496,6 +571,7 @@ extern "C" int vvb_stft_inverse_frames(vvb_engine* e, const vvb_cpx* d_spec, siz
         a.frames = (int)count; a.hop = (int)e->hop; a.y = d_frames; a.tables = e->d_tables;
         return dispatch_inverse<false>(e, a, 1, stream);
     }
+    if (e->chirp) return chirp_inverse_frames(e, reinterpret_cast<const float2*>(d_spec), count, spec_pitch, d_frames, e->d_win, stream);
     DirInvArgs a;
     a.spec = reinterpret_cast<const float2*>(d_spec); a.spec_pitch = (long long)spec_pitch;
     a.count = (long long)count; a.nfft = (int)e->nfft; a.frames_out = d_frames; a.win = e->d_win; a.wtab = e->d_wtab;
@@ -539,11 +615,15 @@ extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t bat
     /* direct path: synthesis frames to HBM scratch, then the stand-alone overlap-add kernel */
     const size_t count = batch * frames;
     if (int st = ensure_scratch(e, count * e->nfft * sizeof(float))) return st;
-    DirInvArgs d;
-    d.spec = reinterpret_cast<const float2*>(d_spec); d.spec_pitch = (long long)spec_pitch;
-    d.count = (long long)count; d.nfft = (int)e->nfft; d.frames_out = e->d_scratch; d.win = e->d_win; d.wtab = e->d_wtab;
-    const long long total = (long long)count * e->nfft;
-    VVB_LAUNCH(stft_inverse_direct_kernel, persistent_grid((total + 127) / 128, 16, e->sms), 128, 0, stream, d);
+    if (e->chirp) {
+        if (int st = chirp_inverse_frames(e, reinterpret_cast<const float2*>(d_spec), count, spec_pitch, e->d_scratch, e->d_win, stream)) return st;
+    } else {
+        DirInvArgs d;
+        d.spec = reinterpret_cast<const float2*>(d_spec); d.spec_pitch = (long long)spec_pitch;
+        d.count = (long long)count; d.nfft = (int)e->nfft; d.frames_out = e->d_scratch; d.win = e->d_win; d.wtab = e->d_wtab;
+        const long long total = (long long)count * e->nfft;
+        VVB_LAUNCH(stft_inverse_direct_kernel, persistent_grid((total + 127) / 128, 16, e->sms), 128, 0, stream, d);
+    }
     OlaArgs o;
     o.frames_in = e->d_scratch; o.batch = (int)batch; o.frames = (int)frames; o.hop = (int)e->hop; o.nfft = (int)e->nfft;
     o.y = d_y; o.y_pitch = (long long)y_pitch; o.n_out = (long long)n_out; o.inv_norm = d_inv_norm;
@@ -560,6 +640,7 @@ struct vvb_fft_engine {
     float* d_tables = nullptr;       /* C2C fast: Tables<C> blob with M = n */
     float2* d_wtab = nullptr;        /* direct C2C */
     vvb_engine* real = nullptr;      /* R2C / C2R: STFT engine with a boxcar window, hop = n */
+    Chirp* chirp = nullptr;          /* C2C sizes served by the Bluestein path */
 };
 
 extern "C" int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine** out)
@@ -591,6 +672,7 @@ extern "C" int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine
         } else {
             make_wtab(blob, n);
             st = upload((float**)&e->d_wtab, blob);
+            if (!st && chirp_size(n)) st = chirp_create(n, &e->chirp);
         }
     } else {
         std::vector<float> ones(n, 1.0f);
@@ -605,6 +687,7 @@ extern "C" void vvb_fft_engine_destroy(vvb_fft_engine* e)
 {
     if (!e) return;
     vvb_free(e->d_tables); vvb_free(e->d_wtab); vvb_engine_destroy(e->real);
+    chirp_destroy(e->chirp);
     delete e;
 }
 
@@ -639,6 +722,27 @@ extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, si
             default: return launch_c2c<Cfg4096>(e, a, stream);
             }
         }
+        if (e->chirp && e->chirp->fused) {      /* in place is fine: a team reads its whole transform before it writes */
+            ChirpFusedArgs a;
+            memset(&a, 0, sizeof(a));
+            a.count = (long long)batch; a.mode = CHIRP_C2C; a.cin = (const float2*)d_in; a.cout = (float2*)d_out; a.inverse = e->dir < 0;
+            return chirp_fused(e->chirp, a, e->sms, stream);
+        }
+        if (e->chirp) {
+            Chirp* c = e->chirp;
+            size_t chunk = 0;
+            if (int st = chirp_reserve(c, batch, &chunk)) return st;
+            for (size_t g0 = 0; g0 < batch; g0 += chunk) {
+                ChirpC2CArgs a;
+                a.in = (const float2*)d_in + g0 * e->n; a.out = (float2*)d_out + g0 * e->n;
+                a.count = (long long)std::min(chunk, batch - g0); a.n = (int)e->n; a.M = (int)c->M; a.inverse = e->dir < 0;
+                a.chirp = c->d_chirp; a.work = c->d_work;
+                VVB_LAUNCH(chirp_pre_c2c_kernel, persistent_grid((a.count * a.M + 255) / 256, 8, e->sms), 256, 0, stream, a);
+                if (int st = chirp_convolve(c, (size_t)a.count, stream)) return st;
+                VVB_LAUNCH(chirp_post_c2c_kernel, persistent_grid((a.count * a.n + 255) / 256, 8, e->sms), 256, 0, stream, a);
+            }
+            return 0;
+        }
         /* the direct kernel reads every input of a transform for every output: out must not alias in */
         DirC2CArgs a;
         a.in = (const float2*)d_in; a.out = (float2*)d_out; a.batch = (long long)batch; a.n = (int)e->n;
@@ -652,6 +756,122 @@ extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, si
     if (e->type == 1)   /* R2C: one frame per transform, boxcar window, complex half spectrum */
         return vvb_stft_forward(e->real, (const float*)d_in, batch, e->n, e->n, 1, PAD_ZERO, OUT_COMPLEX, d_out, bins, stream);
     return vvb_stft_inverse_frames(e->real, (const vvb_cpx*)d_in, batch, bins, (float*)d_out, stream);   /* C2R */
+}
+
+/* ---------------------------------------------------------------------- Bluestein plumbing */
+static void chirp_destroy(Chirp* c)
+{
+    if (!c) return;
+    vvb_free(c->d_chirp); vvb_free(c->d_bspec); vvb_free(c->d_bspec_m); vvb_free(c->d_tables); vvb_free(c->d_work);
+    vvb_fft_engine_destroy(c->fwd); vvb_fft_engine_destroy(c->bwd);
+    delete c;
+}
+
+static int chirp_create(size_t n, Chirp** out)
+{
+    *out = nullptr;
+    Chirp* c = new (std::nothrow) Chirp();
+    if (!c) return fail(4, "chirp_create", "oom");
+    c->n = n;
+    c->M = 128;
+    while (c->M < 2 * n - 1) c->M *= 2;
+    const size_t M = c->M;
+    /* chirp in double with the exponent reduced mod 2n; spectrum of the wrapped conjugate chirp by a direct
+     * double-precision DFT (M * (2n-1) terms, once per plan) */
+    std::vector<double> cr(n), ci(n), twr(M), twi(M);
+    std::vector<float> chirp(2 * n), bspec(2 * M);
+    for (size_t i = 0; i < n; ++i) {
+        const double ang = M_PI * (double)((i * i) % (2 * n)) / (double)n;
+        cr[i] = cos(ang); ci[i] = -sin(ang);
+        chirp[2 * i] = (float)cr[i]; chirp[2 * i + 1] = (float)ci[i];
+    }
+    for (size_t j = 0; j < M; ++j) { const double ang = 2.0 * M_PI * (double)j / (double)M; twr[j] = cos(ang); twi[j] = -sin(ang); }
+    for (size_t k = 0; k < M; ++k) {
+        double sr = cr[0], si = -ci[0];                      /* b[0] = conj(c[0]) = 1 */
+        for (size_t i = 1; i < n; ++i) {
+            /* b[i] = b[M-i] = conj(c[i]):  b[i] (W^{ki} + W^{-ki}) = 2 b[i] cos(2 pi k i / M) */
+            const double w = 2.0 * twr[(k * i) % M];
+            sr += cr[i] * w; si += -ci[i] * w;
+        }
+        bspec[2 * k] = (float)sr; bspec[2 * k + 1] = (float)si;
+    }
+    int st = upload((float**)&c->d_chirp, chirp);
+    if (!st) st = upload((float**)&c->d_bspec, bspec);
+    c->fused = getenv("VVB_BLUESTEIN_UNFUSED") == nullptr;
+    if (!st && c->fused) {
+        std::vector<float> bm(bspec), blob;
+        for (auto& v : bm) v = (float)((double)v / (double)M);
+        st = upload((float**)&c->d_bspec_m, bm);
+        switch (M) {
+        case 128: build_tables<Cfg128>(blob, nullptr); break;
+        case 256: build_tables<Cfg256>(blob, nullptr); break;
+        case 512: build_tables<Cfg512>(blob, nullptr); break;
+        case 1024: build_tables<Cfg1024>(blob, nullptr); break;
+        case 2048: build_tables<Cfg2048>(blob, nullptr); break;
+        default: build_tables<Cfg4096>(blob, nullptr); break;
+        }
+        if (!st) st = upload(&c->d_tables, blob);
+    }
+    if (!st) st = vvb_fft_engine_create(M, 0, +1, &c->fwd);
+    if (!st) st = vvb_fft_engine_create(M, 0, -1, &c->bwd);
+    if (st) { chirp_destroy(c); return st; }
+    *out = c;
+    return 0;
+}
+
+/* work buffer for up to `transforms` transforms, bounded at 256 MB: *chunk = transforms per pass */
+static int chirp_reserve(Chirp* c, size_t transforms, size_t* chunk)
+{
+    const size_t cap = ((size_t)256 << 20) / (c->M * sizeof(float2));
+    size_t want = std::min(transforms, std::max<size_t>(cap, 1));
+    if (want == 0) want = 1;
+    if (c->work_elems < want * c->M) {
+        vvb_free(c->d_work); c->d_work = nullptr; c->work_elems = 0;
+        if (int st = vvb_malloc((void**)&c->d_work, want * c->M * sizeof(float2))) return st;
+        c->work_elems = want * c->M;
+    }
+    *chunk = c->work_elems / c->M;
+    return 0;
+}
+
+/* work <- IFFT_M(FFT_M(work) * bspec), in place, `count` transforms */
+static int chirp_convolve(Chirp* c, size_t count, void* stream)
+{
+    if (int st = vvb_fft_exec(c->fwd, c->d_work, c->d_work, count, stream)) return st;
+    VVB_LAUNCH(chirp_mul_kernel, persistent_grid(((long long)count * (long long)c->M + 255) / 256, 8, rt_num_sms()), 256, 0, stream,
+               c->d_work, c->d_bspec, (long long)count, (int)c->M);
+    return vvb_fft_exec(c->bwd, c->d_work, c->d_work, count, stream);
+}
+
+template <class C, int MODE> static int launch_chirp_fused_m(const ChirpFusedArgs& a, int sms, void* stream)
+{
+    constexpr int G = Teams<C>::G;
+    static int per_sm = -1;
+    auto kern = chirp_fused_kernel<C, G, MODE>;
+    const size_t smem = smem_c2c<C>();
+    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
+    if (per_sm == 0) return fail(4, "chirp_fused_kernel", "does not fit on this device");
+    VVB_LAUNCH(kern, persistent_grid((a.count + G - 1) / G, per_sm, sms), C::T * G, smem, stream, a);
+    return 0;
+}
+template <class C> static int launch_chirp_fused(const ChirpFusedArgs& a, int sms, void* stream)
+{
+    if (a.mode == CHIRP_STFT_FWD) return launch_chirp_fused_m<C, CHIRP_STFT_FWD>(a, sms, stream);
+    if (a.mode == CHIRP_STFT_INV) return launch_chirp_fused_m<C, CHIRP_STFT_INV>(a, sms, stream);
+    return launch_chirp_fused_m<C, CHIRP_C2C>(a, sms, stream);
+}
+
+static int chirp_fused(Chirp* c, ChirpFusedArgs a, int sms, void* stream)
+{
+    a.n = (int)c->n; a.chirp = c->d_chirp; a.bspec_over_m = c->d_bspec_m; a.tables = c->d_tables;
+    switch (c->M) {
+    case 128: return launch_chirp_fused<Cfg128>(a, sms, stream);
+    case 256: return launch_chirp_fused<Cfg256>(a, sms, stream);
+    case 512: return launch_chirp_fused<Cfg512>(a, sms, stream);
+    case 1024: return launch_chirp_fused<Cfg1024>(a, sms, stream);
+    case 2048: return launch_chirp_fused<Cfg2048>(a, sms, stream);
+    default: return launch_chirp_fused<Cfg4096>(a, sms, stream);
+    }
 }
 
 /* ---------------------------------------------------------------------- log-mel */

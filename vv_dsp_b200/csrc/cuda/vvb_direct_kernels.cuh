@@ -145,6 +145,292 @@ __global__ void overlap_add_kernel(const OlaArgs a)
     }
 }
 
+/* ------------------------------------------------------------------ Bluestein */
+/* Sizes without a Stockham kernel, 32 <= n <= 2048, run as a chirp-z convolution on the power-of-two C2C kernel
+ * (the reference itself serves them with an O(n^2) DFT, src/spectral/fft_kiss.c:76-92,115, and uses the same
+ * identity on the CPU for its CZT, src/spectral/czt.c:126-160):
+ *     X[k] = c[k] * sum_i (x[i] c[i]) conj(c)[k-i],   c[i] = exp(-j pi i^2 / n)   (i^2 taken mod 2n on the host)
+ * i.e. pre-multiply by the chirp, zero-pad to M >= 2n-1, FFT_M, multiply by the precomputed FFT_M of the
+ * wrapped conjugate chirp, inverse FFT_M, post-multiply by the chirp.  These kernels are the element-wise
+ * stages around the two fft_c2c_kernel launches; `work` holds M complex values per transform. */
+struct ChirpFwdArgs {          /* STFT analysis: frame gather + window + chirp */
+    const float* x; long long x_pitch, n_sig;
+    int frames, hop, nfft, pad_mode, M;
+    long long g0, count;       /* flat (signal, frame) range [g0, g0 + count) */
+    const float* win; const float2* chirp; float2* work;
+    int out_kind; void* out; long long out_pitch;
+};
+
+__global__ void chirp_pre_stft_kernel(const ChirpFwdArgs a)
+{
+    const long long total = a.count * a.M;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % a.M);
+        float2 r = make_float2(0.f, 0.f);
+        if (i < a.nfft) {
+            const long long g = a.g0 + idx / a.M;
+            const long long b = g / a.frames;
+            const int f = (int)(g - b * a.frames);
+            long long start = (long long)f * a.hop;
+            if (a.pad_mode == PAD_REFLECT) start -= a.nfft / 2;
+            const float v = fetch_sample(a.x + b * a.x_pitch, a.n_sig, start + i, a.pad_mode) * a.win[i];
+            const float2 c = a.chirp[i];
+            r = make_float2(v * c.x, v * c.y);
+        }
+        a.work[idx] = r;
+    }
+}
+
+__global__ void chirp_mul_kernel(float2* work, const float2* bspec, long long count, int M)
+{
+    const long long total = count * M;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x)
+        work[idx] = cmul(work[idx], bspec[idx % M]);
+}
+
+__global__ void chirp_post_stft_kernel(const ChirpFwdArgs a)
+{
+    const int bins = a.nfft / 2 + 1;
+    const long long total = a.count * bins;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % bins);
+        const long long g = idx / bins;
+        float2 z = cmul(a.work[g * a.M + k], a.chirp[k]);
+        if (k == 0 || 2 * k == a.nfft) z.y = 0.0f;
+        const long long o = (a.g0 + g) * a.out_pitch + k;
+        if (a.out_kind == OUT_COMPLEX) reinterpret_cast<float2*>(a.out)[o] = z;
+        else if (a.out_kind == OUT_POWER) reinterpret_cast<float*>(a.out)[o] = z.x * z.x + z.y * z.y;
+        else reinterpret_cast<float*>(a.out)[o] = sqrtf(z.x * z.x + z.y * z.y);
+    }
+}
+
+struct ChirpInvArgs {          /* STFT synthesis: Hermitian half spectrum -> windowed real frame */
+    const float2* spec; long long spec_pitch;
+    long long g0, count; int nfft, M;
+    const float* win;          /* nullptr: no window (C2R) */
+    const float2* chirp; float2* work;
+    float* frames_out;         /* [..][nfft], indexed by the flat frame number */
+};
+
+/* Re(IDFT(X)) = Re(DFT(conj X)) / n: feed conj of the Hermitian extension through the forward transform */
+__global__ void chirp_pre_spec_kernel(const ChirpInvArgs a)
+{
+    const long long total = a.count * a.M;
+    const int n = a.nfft;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % a.M);
+        float2 r = make_float2(0.f, 0.f);
+        if (k < n) {
+            const float2* X = a.spec + (a.g0 + idx / a.M) * a.spec_pitch;
+            float2 v = (2 * k <= n) ? X[k] : make_float2(X[n - k].x, -X[n - k].y);
+            if (k == 0 || 2 * k == n) v.y = 0.0f;
+            r = cmul(make_float2(v.x, -v.y), a.chirp[k]);
+        }
+        a.work[idx] = r;
+    }
+}
+
+__global__ void chirp_post_frames_kernel(const ChirpInvArgs a)
+{
+    const int n = a.nfft;
+    const long long total = a.count * n;
+    const float invn = 1.0f / (float)n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % n);
+        const long long g = idx / n;
+        const float2 w = a.work[g * a.M + i], c = a.chirp[i];
+        float v = (w.x * c.x - w.y * c.y) * invn;
+        if (a.win) v *= a.win[i];
+        a.frames_out[(a.g0 + g) * n + i] = v;
+    }
+}
+
+struct ChirpC2CArgs { const float2* in; float2* out; long long count; int n, M, inverse; const float2* chirp; float2* work; };
+
+__global__ void chirp_pre_c2c_kernel(const ChirpC2CArgs a)
+{
+    const long long total = a.count * a.M;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % a.M);
+        float2 r = make_float2(0.f, 0.f);
+        if (i < a.n) {
+            float2 v = a.in[(idx / a.M) * a.n + i];
+            if (a.inverse) v.y = -v.y;
+            r = cmul(v, a.chirp[i]);
+        }
+        a.work[idx] = r;
+    }
+}
+
+__global__ void chirp_post_c2c_kernel(const ChirpC2CArgs a)
+{
+    const long long total = a.count * a.n;
+    const float invn = 1.0f / (float)a.n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % a.n);
+        float2 z = cmul(a.work[(idx / a.n) * a.M + k], a.chirp[k]);
+        if (a.inverse) z = make_float2(z.x * invn, -z.y * invn);
+        a.out[idx] = z;
+    }
+}
+
+/* The whole chirp-z transform in ONE kernel: a team (the same T = M/E threads and register layout as
+ * fft_c2c_kernel) loads its transform with the pre-multiplication fused in, runs the forward FFT_M in
+ * registers, multiplies by the chirp spectrum (1/M folded in), turns the result back into pass-1 order through
+ * its exchange buffer, runs the second FFT_M on re/im-swapped data (= the inverse) and applies the
+ * post-multiplication on the way out.  HBM sees the input samples and the n-point result only; the
+ * multi-kernel version above moved 8 x M complex values per transform through HBM (kept for sizes whose
+ * team does not fit, and as a cross-check: VVB_BLUESTEIN_UNFUSED=1). */
+enum { CHIRP_STFT_FWD = 0, CHIRP_STFT_INV = 1, CHIRP_C2C = 2 };
+struct ChirpFusedArgs {
+    long long count;                 /* transforms */
+    int n, mode;
+    const float2* chirp; const float2* bspec_over_m; const float* win;
+    const float* tables;             /* Tables<C> blob of the M-point C2C plan */
+    /* STFT_FWD */
+    const float* x; long long x_pitch, n_sig; int frames, hop, pad_mode, out_kind; void* out; long long out_pitch;
+    /* STFT_INV */
+    const float2* spec; long long spec_pitch; float* frames_out;
+    /* C2C */
+    const float2* cin; float2* cout; int inverse;
+};
+
+template <class C, int G, int MODE>
+__global__ void __launch_bounds__(C::T* G) chirp_fused_kernel(const ChirpFusedArgs a)
+{
+    using TB = Tables<C>;
+    using L = LastPass<C>;
+    constexpr int M = C::M, E = C::E, T = C::T;
+#ifdef VVB_EMU
+    float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float smem[];
+#endif
+    float2* s_tw2 = reinterpret_cast<float2*>(smem);
+    float2* s_tw3 = s_tw2 + C::TW2;
+    float2* s_xb = s_tw3 + C::TW3;
+    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3));
+    __syncthreads();
+    const int team = threadIdx.x / T, t = threadIdx.x % T;
+    float2* xb = s_xb + team * C::XBUF;
+    const int n = a.n;
+    const float invn = 1.0f / (float)n;
+    const long long groups = (a.count + G - 1) / G;
+    for (long long group = blockIdx.x; group < groups; group += gridDim.x) {
+        const long long id = group * G + team;
+        const bool active = id < a.count;
+        float2 v[E];
+        {
+            /* phase 1: every global load of this transform is issued before any of them is used */
+            constexpr int R = C::R1, NQ = E / R, STRIDE = M / R;
+            if constexpr (MODE == CHIRP_STFT_FWD) {
+                const long long b = active ? id / a.frames : 0;
+                const int f = (int)(id - b * a.frames);
+                const float* xs = a.x + b * a.x_pitch;
+                const long long start = (long long)f * a.hop - (a.pad_mode == PAD_REFLECT ? n / 2 : 0);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = t + T * q + r * STRIDE;
+                        v[q * R + r].x = (active && i < n) ? fetch_sample(xs, a.n_sig, start + i, a.pad_mode) : 0.0f;
+                    }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = t + T * q + r * STRIDE;
+                        float2 s = make_float2(0.f, 0.f);
+                        if (i < n) {
+                            const float2 c = __ldg(a.chirp + i);
+                            const float val = v[q * R + r].x * __ldg(a.win + i);
+                            s = make_float2(val * c.x, val * c.y);
+                        }
+                        v[q * R + r] = s;
+                    }
+            } else {
+                const float2* src = (MODE == CHIRP_STFT_INV) ? a.spec + (active ? id : 0) * a.spec_pitch : a.cin + (active ? id : 0) * n;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = t + T * q + r * STRIDE;
+                        const int from = (MODE == CHIRP_STFT_INV && 2 * i > n) ? n - i : i;      /* Hermitian extension */
+                        v[q * R + r] = (active && i < n) ? __ldg(src + from) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = t + T * q + r * STRIDE;
+                        float2 h = v[q * R + r];
+                        if constexpr (MODE == CHIRP_STFT_INV) {
+                            /* feed conj(Xfull): the mirrored half is already a conjugate, the lower half gets one here */
+                            if (2 * i <= n) h.y = -h.y;
+                            if (i == 0 || 2 * i == n) h.y = 0.0f;
+                        } else if (a.inverse) h.y = -h.y;
+                        v[q * R + r] = (i < n) ? cmul(h, __ldg(a.chirp + i)) : make_float2(0.f, 0.f);
+                    }
+            }
+        }
+        team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+        /* times the chirp spectrum, parked in natural order, re-read in pass-1 order with re/im swapped */
+#pragma unroll
+        for (int q = 0; q < L::NQ; ++q)
+#pragma unroll
+            for (int r = 0; r < L::R; ++r) {
+                const int k = t + T * q + r * L::NS;
+                xb[C::pad(k)] = cmul(v[q * L::R + ct_bitrev(r, L::R)], __ldg(a.bspec_over_m + k));
+            }
+        team_sync<T>(team);
+        {
+            constexpr int R = C::R1, NQ = E / R, STRIDE = M / R;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float2 z = xb[C::pad(t + T * q + r * STRIDE)];
+                    v[q * R + r] = make_float2(z.y, z.x);
+                }
+        }
+        team_sync<T>(team);
+        team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < L::NQ; ++q)
+#pragma unroll
+                for (int r = 0; r < L::R; ++r) {
+                    const int k = t + T * q + r * L::NS;
+                    const bool wanted = (MODE == CHIRP_STFT_FWD) ? (2 * k <= n) : (k < n);
+                    if (!wanted) continue;
+                    const float2 zs = v[q * L::R + ct_bitrev(r, L::R)];
+                    float2 z = cmul(make_float2(zs.y, zs.x), __ldg(a.chirp + k));       /* un-swap, post-chirp */
+                    if constexpr (MODE == CHIRP_STFT_FWD) {
+                        if (k == 0 || 2 * k == n) z.y = 0.0f;
+                        const long long o = id * a.out_pitch + k;
+                        if (a.out_kind == OUT_COMPLEX) reinterpret_cast<float2*>(a.out)[o] = z;
+                        else if (a.out_kind == OUT_POWER) reinterpret_cast<float*>(a.out)[o] = z.x * z.x + z.y * z.y;
+                        else reinterpret_cast<float*>(a.out)[o] = sqrtf(z.x * z.x + z.y * z.y);
+                    } else if constexpr (MODE == CHIRP_STFT_INV) {
+                        float val = z.x * invn;
+                        if (a.win) val *= __ldg(a.win + k);
+                        a.frames_out[id * n + k] = val;
+                    } else {
+                        a.cout[id * n + k] = a.inverse ? make_float2(z.x * invn, -z.y * invn) : z;
+                    }
+                }
+        }
+        team_sync<T>(team);
+    }
+}
+
 /* ------------------------------------------------------------------ log-mel */
 /* out[f][m] = logf(sum_k power[f][k] W[m][k] + eps), the reference's src/features/mel.c:204-245, with the
  * filterbank stored sparsely (each triangular filter is non-zero on one contiguous bin range).
