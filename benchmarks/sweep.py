@@ -38,20 +38,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--nfft", type=int, nargs="*", default=None, help="restrict the sweep to these sizes")
+    ap.add_argument("--batch", type=int, nargs="*", default=None, help="batch sizes (default 64 512 4096; --quick 64 1024)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     cases = []
     for nfft in (args.nfft or (256, 512, 1024, 2048, 4096, 8192)):
-        for batch in ((64, 1024) if args.quick else (64, 512, 4096)):
+        for batch in (args.batch or ((64, 1024) if args.quick else (64, 512, 4096))):
             cases.append((nfft, nfft // 4, batch, 480_000, "config5"))
     if not args.nfft or 4096 in args.nfft:
         cases.append((4096, 1024, 1, 172_800_000 if not args.quick else 17_280_000, "config4 single stream"))
     for nfft, hop, B, n, tag in cases:
         F = 1 + (n - nfft) // hop
         bins = nfft // 2 + 1
-        if B * F * bins * 8 > 60e9:
+        if B * F * bins * 12 + B * n * 8 > 150e9:      # spectra + power + signals + output must fit 180 GB
             continue
         x = torch.rand((B, n), device=dev) * 2 - 1
         spec = torch.empty((B, F, bins), device=dev, dtype=torch.complex64)
