@@ -408,6 +408,49 @@ template <class C> VVB_DEV void team_fft_regtw(float2 (&v)[C::E], float2* xb, co
     fft_reg<32, 0>(v);
 }
 
+/* The same for any two-pass configuration (M = R1 * R2, T = M / E threads, E / R2 sub-transforms per thread in
+ * pass 2).  Sub-transform q of thread t is column j = t + T q of the R1 x R2 decomposition and needs
+ * W_M^{r j} = W_M^{r t} * W_M^{r T q}: powers of the per-thread base times a compile-time rotation. */
+template <class C> VVB_DEV TwBase load_tw_base2(const float2* tw2_global, int t)
+{
+    static_assert(C::NP == 2 && C::R2 <= 32, "two-pass configuration");
+    TwBase b;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+        b.w[j] = ((1 << j) < C::R2) ? __ldg(tw2_global + ((1 << j) - 1) * C::R1 + t) : make_float2(1.f, 0.f);   /* r = 2^j, jm = t */
+    return b;
+}
+template <class C, int Q, int R> VVB_DEV float2 tw_power_q(const TwBase& b)
+{
+    if constexpr (Q == 0) {
+        return tw_power<R>(b);
+    } else {
+        constexpr int K = (R * C::T * Q) % C::M;
+        return cmul(tw_power<R>(b), make_float2(TwC<C::M, K>::c, -TwC<C::M, K>::s));
+    }
+}
+template <class C, int Q, int... Rs> VVB_DEV void apply_tw_powers_q(float2* v, const TwBase& b, iseq<Rs...>)
+{
+    ((v[Rs + 1] = cmul(v[Rs + 1], tw_power_q<C, Q, Rs + 1>(b))), ...);
+}
+template <class C, int... Qs> VVB_DEV void apply_tw_all_q(float2* v, const TwBase& b, iseq<Qs...>)
+{
+    (apply_tw_powers_q<C, Qs>(v + Qs * C::R2, b, typename make_iseq<C::R2 - 1>::type{}), ...);
+}
+template <class C> VVB_DEV void team_fft_regtw2(float2 (&v)[C::E], float2* xb, const TwBase& b, int t, int team)
+{
+    constexpr int R = C::R2, NQ = C::E / R, STRIDE = C::M / R;
+    stockham_pass<C, C::R1, 1, true, false>(v, xb, nullptr, t, team);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[q * R + r] = xb[C::pad(t + C::T * q + r * STRIDE)];
+    team_sync<C::T>(team);
+    apply_tw_all_q<C>(v, b, typename make_iseq<NQ>::type{});
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) fft_reg<R, 0>(&v[q * R]);
+}
+
 template <class C> struct LastPass {
     static constexpr int R = (C::NP == 2) ? C::R2 : C::R3;
     static constexpr int NS = C::M / R;

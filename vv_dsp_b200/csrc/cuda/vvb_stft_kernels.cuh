@@ -26,6 +26,10 @@
 #include "vvb_fft_core.cuh"
 #include <stdint.h>
 
+#ifndef VVB_FWD_TABLE_TWIDDLES
+#define VVB_FWD_TABLE_TWIDDLES 0      /* 1: the generic forward kernel loads twiddles / window from shared memory (A/B builds) */
+#endif
+
 namespace vvb {
 
 enum { OUT_COMPLEX = 0, OUT_POWER = 1, OUT_MAGNITUDE = 2 };
@@ -88,8 +92,11 @@ VVB_DEV void copy_table(float* dst, const float* src, int count)
 }
 
 /* ============================================================== forward (analysis) */
+template <class C, int OUT> VVB_DEV void split_and_store(const float2* xb, const float2* s_post, int t, void* out, long long row);
+template <class C, int OUT> VVB_DEV void split_and_store_rot(const float2* xb, float2 hw_t, int t, void* out, long long row);
+
 template <class C, int G, int OUT>
-__global__ void __launch_bounds__(C::T* G) stft_forward_kernel(const FwdArgs a)
+__global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_kernel(const FwdArgs a)
 {
     using TB = Tables<C>;
     constexpr int M = C::M, N = 2 * M, E = C::E, T = C::T;
@@ -110,6 +117,26 @@ __global__ void __launch_bounds__(C::T* G) stft_forward_kernel(const FwdArgs a)
     const int team = threadIdx.x / T, t = threadIdx.x % T;
     float2* xb = s_xb + team * C::XBUF;
     const float2* win2 = reinterpret_cast<const float2*>(s_win);
+    /* These kernels are bound by shared-memory wavefronts (ncu: LSU 85 % at fft_size 512), so what can be
+     * computed or kept in registers is: inter-pass twiddles as powers of a per-thread base (two-pass
+     * configurations), split twiddles as per-thread value x compile-time rotation, and the window in
+     * registers where E is small enough to keep two CTAs per SM. */
+    constexpr bool REGTW = (C::NP == 2) && !VVB_FWD_TABLE_TWIDDLES;
+    constexpr bool WINREG = (E <= 16) && !VVB_FWD_TABLE_TWIDDLES;
+    TwBase twb;
+    if constexpr (REGTW) twb = load_tw_base2<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);
+    const float2 hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);   /* t < T <= M/2 */
+    float2 wreg[WINREG ? E : 1];
+    if constexpr (WINREG) {
+        constexpr int R = C::R1, NQ = E / R, STRIDE = M / R;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) wreg[q * R + r] = win2[t + T * q + r * STRIDE];
+    }
+    auto win_at = [&](int slot, int i) -> float2 {
+        if constexpr (WINREG) { (void)i; return wreg[slot]; } else { (void)slot; return win2[i]; }
+    };
 
     for (int group = blockIdx.x; group < a.num_groups; group += gridDim.x) {
         const int b = group / a.groups_per_signal;
@@ -133,7 +160,7 @@ __global__ void __launch_bounds__(C::T* G) stft_forward_kernel(const FwdArgs a)
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const int i = t + T * q + r * STRIDE;
-                            const float2 s = __ldg(p2 + i), w = win2[i];
+                            const float2 s = __ldg(p2 + i), w = win_at(q * R + r, i);
                             v[q * R + r] = make_float2(s.x * w.x, s.y * w.y);
                         }
                 } else {
@@ -142,7 +169,7 @@ __global__ void __launch_bounds__(C::T* G) stft_forward_kernel(const FwdArgs a)
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const int i = t + T * q + r * STRIDE;
-                            const float2 w = win2[i];
+                            const float2 w = win_at(q * R + r, i);
                             v[q * R + r] = make_float2(__ldg(p + 2 * i) * w.x, __ldg(p + 2 * i + 1) * w.y);
                         }
                 }
@@ -152,7 +179,7 @@ __global__ void __launch_bounds__(C::T* G) stft_forward_kernel(const FwdArgs a)
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const int i = t + T * q + r * STRIDE;
-                        const float2 w = win2[i];
+                        const float2 w = win_at(q * R + r, i);
                         v[q * R + r] = make_float2(fetch_sample(xs, a.n, start + 2 * i, a.pad_mode) * w.x,
                                                    fetch_sample(xs, a.n, start + 2 * i + 1, a.pad_mode) * w.y);
                     }
@@ -163,34 +190,17 @@ __global__ void __launch_bounds__(C::T* G) stft_forward_kernel(const FwdArgs a)
         }
 
         /* ---- M-point complex FFT of z[i] = x[2i] + j x[2i+1] */
-        team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+        if constexpr (REGTW) team_fft_regtw2<C>(v, xb, twb, t, team);
+        else team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
         team_store_natural<C>(v, xb, t);
         team_sync<T>(team);
 
         /* ---- split step: X[k] = (Z[k] + conj Z[M-k])/2 - (j/2) W_N^k (Z[k] - conj Z[M-k]) */
         const long long row = ((long long)b * a.frames + f) * a.out_pitch;
-        auto emit = [&](int k, float xr, float xi) {
-            if constexpr (OUT == OUT_COMPLEX) reinterpret_cast<float2*>(a.out)[row + k] = make_float2(xr, xi);
-            else if constexpr (OUT == OUT_POWER) reinterpret_cast<float*>(a.out)[row + k] = xr * xr + xi * xi;
-            else reinterpret_cast<float*>(a.out)[row + k] = sqrtf(xr * xr + xi * xi);
-        };
-#pragma unroll
-        for (int i = 0; i < E / 2; ++i) {
-            const int k = t + T * i;                                  /* 0 .. M/2-1 */
-            const float2 A = xb[C::pad(k)];
-            const float2 Bc = xb[C::pad((M - k) & (M - 1))];
-            const float2 hw = s_post[k];                              /* (cos, sin)/2 */
-            const float sr = A.x + Bc.x, si = A.y - Bc.y;             /* A + conj(Bc) */
-            const float dr = A.x - Bc.x, di = A.y + Bc.y;             /* A - conj(Bc) */
-            const float gr = hw.y * dr - hw.x * di, gi = hw.y * di + hw.x * dr;
-            if (active) {
-                emit(k, 0.5f * sr - gr, 0.5f * si - gi);             /* X[k]   */
-                emit(M - k, 0.5f * sr + gr, -(0.5f * si + gi));      /* X[M-k] */
-            }
-        }
-        if (t == 0 && active) {                                       /* k = M/2: X = conj(Z[M/2]) */
-            const float2 A = xb[C::pad(M / 2)];
-            emit(M / 2, A.x, -A.y);
+        if constexpr (!VVB_FWD_TABLE_TWIDDLES && C::M <= 2048) {
+            if (active) split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, row);
+        } else {
+            if (active) split_and_store<C, OUT>(xb, s_post, t, a.out, row);
         }
         team_sync<T>(team);                                           /* xb is reused next group */
     }
