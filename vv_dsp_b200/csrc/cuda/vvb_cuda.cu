@@ -224,6 +224,7 @@ struct vvb_engine {
     int sms = 0;
     float* d_tables = nullptr;       /* fast: Tables<C> blob */
     float* d_tables_m = nullptr;     /* fft_size 512 / 1024: blob of the whole-warp config used by the marching ISTFT */
+    float* d_tables_p = nullptr;     /* fft_size 256 / 512 / 1024: twiddles of the N-point complex plan of istft_pair_kernel */
     float* d_win = nullptr;          /* direct: window */
     float2* d_wtab = nullptr;        /* direct: (cos,-sin)(2 pi j/n) */
     float* d_scratch = nullptr;      /* direct: synthesis frames */
@@ -277,6 +278,12 @@ extern "C" int vvb_engine_create(size_t nfft, size_t hop, const float* window, v
             if (nfft == 512) build_tables<Cfg256m>(blob, window, hop); else build_tables<Cfg512m>(blob, window, hop);
             st = upload(&e->d_tables_m, blob);
         }
+        if (!st && (nfft == 256 || nfft == 512 || nfft == 1024)) {
+            if (nfft == 256) build_tables<Cfg256m>(blob, nullptr);
+            else if (nfft == 512) build_tables<Cfg512m>(blob, nullptr);
+            else build_tables<Cfg1024>(blob, nullptr);
+            st = upload(&e->d_tables_p, blob);
+        }
     } else {
         std::vector<float> w(window, window + nfft), t;
         make_wtab(t, nfft);
@@ -292,7 +299,7 @@ extern "C" int vvb_engine_create(size_t nfft, size_t hop, const float* window, v
 extern "C" void vvb_engine_destroy(vvb_engine* e)
 {
     if (!e) return;
-    vvb_free(e->d_tables); vvb_free(e->d_tables_m); vvb_free(e->d_win); vvb_free(e->d_wtab); vvb_free(e->d_scratch);
+    vvb_free(e->d_tables); vvb_free(e->d_tables_m); vvb_free(e->d_tables_p); vvb_free(e->d_win); vvb_free(e->d_wtab); vvb_free(e->d_scratch);
     chirp_destroy(e->chirp);
     delete e;
 }
@@ -524,6 +531,43 @@ template <class C> static int launch_inv_march(vvb_engine* e, const InvArgs& a, 
     }
 }
 
+/* two frames per complex transform (fft_size 256 / 512 / 1024): C = one-warp plan with M = fft_size, CO = the real plan
+ * whose window tables are reused */
+template <class C> struct PairCfg;
+template <> struct PairCfg<Cfg256m> { static constexpr int G = 8, MINB = 3; };
+template <> struct PairCfg<Cfg512m> { static constexpr int G = 8, MINB = 2; };
+template <> struct PairCfg<Cfg1024> { static constexpr int G = 8, MINB = 1; };
+template <class C, class CO, int HS> static int launch_inv_pair_s(vvb_engine* e, const InvArgs& ia, long long batch, void* stream)
+{
+    constexpr int G = PairCfg<C>::G, MINB = PairCfg<C>::MINB;
+    static int per_sm = -1;
+    auto kern = istft_pair_kernel<C, HS, G, MINB>;
+    const size_t smem = sizeof(float) * 2 * (C::TW2 + C::TW3 + G * C::XBUF);
+    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, 32 * G, smem);
+    if (per_sm == 0) return fail(4, "istft_pair_kernel", "does not fit on this device");
+    if (batch > 0x7fffffffLL) return fail(2, "vvb_stft_inverse", "batch");
+    PairArgs a;
+    a.spec = ia.spec; a.spec_pitch = ia.spec_pitch; a.frames = ia.frames; a.num_items = (int)batch;
+    a.y = ia.y; a.y_pitch = ia.y_pitch; a.n_out = ia.n_out; a.inv_norm = ia.inv_norm;
+    a.tables = e->d_tables_p;
+    a.wsyn = e->d_tables + (ia.inv_norm ? Tables<CO>::WSYN_NORM : Tables<CO>::WSYN);
+    a.midnorm = e->d_tables + Tables<CO>::MIDNORM;
+    const long long total = batch * ((ia.frames + 1) / 2);
+    const long long want = (total + 8 * G - 1) / (8 * G);
+    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), 32 * G, smem, stream, a);
+    return 0;
+}
+template <class C, class CO> static int launch_inv_pair(vvb_engine* e, const InvArgs& a, long long batch, void* stream)
+{
+    if (e->hop % 32) return -1;
+    switch (e->hop / 32) {
+    case C::E / 8: return launch_inv_pair_s<C, CO, C::E / 8>(e, a, batch, stream);
+    case C::E / 4: return launch_inv_pair_s<C, CO, C::E / 4>(e, a, batch, stream);
+    case C::E / 2: return launch_inv_pair_s<C, CO, C::E / 2>(e, a, batch, stream);
+    default: return -1;
+    }
+}
+
 static int ensure_scratch(vvb_engine* e, size_t bytes)
 {
     if (e->scratch_bytes >= bytes) return 0;
@@ -598,6 +642,13 @@ extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t bat
         a.frames = (int)frames; a.hop = (int)e->hop;
         a.y = d_y; a.y_pitch = (long long)y_pitch; a.n_out = (long long)n_out;
         a.inv_norm = d_inv_norm; a.tables = e->d_tables;
+        if (e->d_tables_p && !getenv("VVB_NO_PAIR") && !getenv("VVB_NO_MARCH")) {
+            int r = -1;
+            if (e->nfft == 256) r = launch_inv_pair<Cfg256m, Cfg128>(e, a, (long long)batch, stream);
+            else if (e->nfft == 512) r = launch_inv_pair<Cfg512m, Cfg256>(e, a, (long long)batch, stream);
+            else if (e->nfft == 1024) r = launch_inv_pair<Cfg1024, Cfg512>(e, a, (long long)batch, stream);
+            if (r >= 0) return r;
+        }
         const bool y_aligned = ((uintptr_t)d_y % 8 == 0) && (y_pitch % 2 == 0);   /* 64-bit stores */
         if (y_aligned && !getenv("VVB_NO_MARCH")) {
             int r = -1;

@@ -869,6 +869,149 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
     }
 }
 
+/* ================================================= inverse, two frames per complex transform */
+/* fft_size N <= 1024: a warp turns TWO consecutive frames into one N-point COMPLEX transform,
+ *     Z = X_f + j X_{f+1}  (Hermitian extensions)   =>   IDFT_N(Z) = x_f + j x_{f+1},
+ * so there is no merge step and no merge twiddle, and the one-warp configurations with M = N apply
+ * (N = 256: 8.8.4, N = 512: 16.16.2, N = 1024: 32.32).  Thread t owns the samples i = t + 32 s of both
+ * frames (every output index of these configurations is congruent to t mod 32), the hop is HS slots of 32
+ * samples, and the overlap-add accumulator is E + HS registers rotated by 2 HS slots per pair, exactly as
+ * in istft_march_kernel: finished hop-blocks leave with coalesced 128-byte stores, no shared-memory slots,
+ * no CTA barriers.  Frames are added in ascending order.  The window table is the real-transform one
+ * (w / (N/2) [x 1/sum w^2]); the factor 1/2 that turns it into w / N is applied when it is loaded. */
+struct PairArgs {
+    const float2* spec; long long spec_pitch;
+    int frames, num_items;
+    float* y; long long y_pitch, n_out;
+    const float* inv_norm;           /* edge tables as in InvArgs, nullptr = raw sum */
+    const float* tables;             /* Tables<C> of the N-point complex plan (twiddles only) */
+    const float* wsyn;               /* N floats: synthesis window of the real plan (normalisation folded in when inv_norm) */
+    const float* midnorm;            /* hop floats: steady-state sum w^2 */
+};
+
+template <class C, int HS, int G, int MINB>
+__global__ void __launch_bounds__(32 * G, MINB) istft_pair_kernel(const PairArgs a)
+{
+    static_assert(C::T == 32, "one-warp complex transform of size fft_size");
+    using TB = Tables<C>;
+    using L = LastPass<C>;
+    constexpr int N = C::M, E = C::E, T = 32;
+    constexpr int HOP = 32 * HS, PERIOD = E / HS, EDGE = N - HOP, HALO_PAIRS = PERIOD / 2;
+    static_assert(E % HS == 0 && PERIOD >= 2 && L::NS % 32 == 0, "hop must divide fft_size");
+#ifdef VVB_EMU
+    float* smem = reinterpret_cast<float*>(vvb_emu::g_dyn_smem);
+#else
+    extern __shared__ __align__(16) float smem[];
+#endif
+    float2* s_tw2 = reinterpret_cast<float2*>(smem);
+    float2* s_tw3 = s_tw2 + C::TW2;
+    float2* s_xb = s_tw3 + C::TW3;
+    copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3));
+    __syncthreads();
+    const int team = threadIdx.x / T, t = threadIdx.x % T;
+    float2* xb = s_xb + team * C::XBUF;
+    const bool normalise = a.inv_norm != nullptr;
+    float w[E];                                                        /* w[s] for sample t + 32 s, already / N */
+#pragma unroll
+    for (int s2 = 0; s2 < E; ++s2) w[s2] = 0.5f * __ldg(a.wsyn + t + 32 * s2);
+
+    const int F = a.frames;
+    const int FP = (F + 1) / 2;                                        /* frame pairs per signal */
+    const long long total = (long long)a.num_items * FP;
+    const long long nteams = (long long)gridDim.x * G;
+    const long long quota = (total + nteams - 1) / nteams;
+    long long g0 = ((long long)blockIdx.x * G + team) * quota;
+    const long long g1 = min(total, g0 + quota);
+
+    while (g0 < g1) {
+        const int b = (int)(g0 / FP);
+        const int p_begin = (int)(g0 - (long long)b * FP);
+        const int p_end = (int)min((long long)FP, (long long)p_begin + (g1 - g0));
+        const int blk_begin = 2 * p_begin;                             /* hop-blocks [blk_begin, blk_end) are ours */
+        const int blk_end = (p_end == FP) ? F + PERIOD - 1 : 2 * p_end;
+        const int p0 = p_begin - min(HALO_PAIRS, p_begin);            /* halo pairs re-synthesised */
+        const float2* specb = a.spec + (long long)b * F * a.spec_pitch;
+        float* yb = a.y + (long long)b * a.y_pitch;
+        g0 += p_end - p_begin;
+
+        float acc[E + HS];
+#pragma unroll
+        for (int i = 0; i < E + HS; ++i) acc[i] = 0.f;
+
+#pragma unroll 1
+        for (int pair = p0; 2 * pair < blk_end; ++pair) {
+            const int f0 = 2 * pair;
+            if (pair < p_end) {                                        /* warp-uniform */
+                const bool have1 = f0 + 1 < F;
+                const float2* X1 = specb + (long long)f0 * a.spec_pitch;
+                const float2* X2 = X1 + (have1 ? a.spec_pitch : 0);
+                float2 v[E];
+                {
+                    constexpr int R = C::R1, NQ = E / R, STRIDE = N / R;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int i = t + T * q + r * STRIDE;
+                            const int k = (2 * i <= N) ? i : N - i;
+                            float2 x1 = __ldg(X1 + k), x2 = __ldg(X2 + k);
+                            if (!have1) x2 = make_float2(0.f, 0.f);
+                            if (2 * i > N) { x1.y = -x1.y; x2.y = -x2.y; }           /* Hermitian extension */
+                            if (k == 0 || 2 * k == N) { x1.y = 0.f; x2.y = 0.f; }    /* Re(IDFT): DC / Nyquist imag drop out */
+                            /* Z = x1 + j x2, stored re/im swapped so the forward machinery computes the inverse */
+                            v[q * R + r] = make_float2(x1.y + x2.x, x1.x - x2.y);
+                        }
+                }
+                team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+                /* v = (N x_{f+1}[i], N x_f[i]) for i = t + 32 (q + r NS/32) */
+#pragma unroll
+                for (int q = 0; q < L::NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < L::R; ++r) {
+                        const int sl = q + r * (L::NS / 32);
+                        const float2 z = v[q * L::R + ct_bitrev(r, L::R)];
+                        acc[sl] = fmaf(z.y, w[sl], acc[sl]);
+                    }
+#pragma unroll
+                for (int q = 0; q < L::NQ; ++q)
+#pragma unroll
+                    for (int r = 0; r < L::R; ++r) {
+                        const int sl = q + r * (L::NS / 32);
+                        const float2 z = v[q * L::R + ct_bitrev(r, L::R)];
+                        acc[sl + HS] = fmaf(z.x, w[sl], acc[sl + HS]);
+                    }
+            }
+            /* the two oldest hop-blocks are complete: blocks f0 (slots 0..HS-1) and f0+1 (slots HS..2HS-1) */
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int blk = f0 + h;
+                if (blk >= blk_begin && blk < blk_end) {
+                    const long long base = (long long)blk * HOP;
+                    const bool edge_blk = normalise && (blk < PERIOD - 1 || blk >= F);
+                    const float* edge = nullptr;
+                    if (edge_blk) edge = (blk >= F) ? a.inv_norm + EDGE + HOP + (long long)(blk - F) * HOP
+                                                    : a.inv_norm + (long long)blk * HOP;
+#pragma unroll
+                    for (int s2 = 0; s2 < HS; ++s2) {
+                        const int c = t + 32 * s2;
+                        float val = acc[h * HS + s2];
+                        if (edge_blk) val *= __ldg(edge + c) * __ldg(a.midnorm + c);
+                        if (base + c < a.n_out) yb[base + c] = val;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < E - HS; ++i) acc[i] = acc[i + 2 * HS];
+#pragma unroll
+            for (int i = E - HS; i < E + HS; ++i) acc[i] = 0.f;
+        }
+        if (p_end == FP) {                                             /* nothing covers [cov, n_out): zeros */
+            const long long cov = (long long)(F - 1) * HOP + N;
+            for (long long tt = cov + t; tt < a.n_out; tt += T) yb[tt] = 0.f;
+        }
+    }
+}
+
 /* ===================================================== batched complex FFT (plan API) */
 struct C2CArgs {
     const float2* in;
