@@ -62,8 +62,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in CUDA_SRCS:
         o = os.path.join(OBJ, os.path.basename(src) + ".o")
         if force or _stale(o, [src] + CUDA_DEPS + hdrs):
-            # --split-compile 0: ptxas works on the ~100 kernels of this translation unit on all host cores
-            _run([NVCC, *ARCH, "-std=c++17", "-O3", "-lineinfo", "--split-compile", "0", "-Xptxas", "-v" if verbose else "-warn-spills",
+            # VVB_NVCC_EXTRA: extra nvcc flags for A/B builds (e.g. "-DVVB_INV_BASETW=0")
+            extra = os.environ.get("VVB_NVCC_EXTRA", "").split()
+            _run([NVCC, *ARCH, "-std=c++17", "-O3", "-lineinfo", *extra, "-Xptxas", "-v" if verbose else "-warn-spills",
                   "-Xcompiler", "-fPIC", "-I" + INC, "-c", src, "-o", o], verbose)
         objs.append(o)
     if force or _stale(LIB, objs):

@@ -408,6 +408,22 @@ template <class C> VVB_DEV void team_fft_regtw(float2 (&v)[C::E], float2* xb, co
     fft_reg<32, 0>(v);
 }
 
+/* Variant that keeps no register state between transforms: the five bases are re-read from the shared-memory
+ * table (5 LDS.64 instead of 31) right where they are used, so they are live only during the twiddle phase. */
+template <class C> VVB_DEV void team_fft_basetw(float2 (&v)[C::E], float2* xb, const float2* s_tw2, int t, int team)
+{
+    static_assert(C::T == 32 && C::R1 == 32 && C::R2 == 32 && C::NP == 2, "32 x 32 one-warp transform");
+    stockham_pass<C, 32, 1, true, false>(v, xb, nullptr, t, team);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) v[r] = xb[C::pad(t + r * 32)];
+    team_sync<C::T>(team);
+    TwBase b;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) b.w[j] = s_tw2[((1 << j) - 1) * 32 + t];
+    apply_tw_powers(v, b, typename make_iseq<31>::type{});
+    fft_reg<32, 0>(v);
+}
+
 /* The same for any two-pass configuration (M = R1 * R2, T = M / E threads, E / R2 sub-transforms per thread in
  * pass 2).  Sub-transform q of thread t is column j = t + T q of the R1 x R2 decomposition and needs
  * W_M^{r j} = W_M^{r t} * W_M^{r T q}: powers of the per-thread base times a compile-time rotation. */
@@ -449,6 +465,31 @@ template <class C> VVB_DEV void team_fft_regtw2(float2 (&v)[C::E], float2* xb, c
     apply_tw_all_q<C>(v, b, typename make_iseq<NQ>::type{});
 #pragma unroll
     for (int q = 0; q < NQ; ++q) fft_reg<R, 0>(&v[q * R]);
+}
+
+/* two-pass transform with the bases re-read from the shared-memory table at the point of use (no register state
+ * between transforms); three-pass configurations fall through to the table version.  Measured: a gain only where
+ * the kernel is bound by shared-memory wavefronts (marching ISTFT); the chirp-z and plan C2C kernels are not and
+ * got slower with it (nfft=400 STFT 5.4 -> 7.7 ms), so they keep the table twiddles. */
+template <class C> VVB_DEV void team_fft_auto(float2 (&v)[C::E], float2* xb, const float2* s_tw2, const float2* s_tw3, int t, int team)
+{
+    if constexpr (C::NP == 2 && C::R2 <= 32) {
+        constexpr int R = C::R2, NQ = C::E / R, STRIDE = C::M / R;
+        stockham_pass<C, C::R1, 1, true, false>(v, xb, nullptr, t, team);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[q * R + r] = xb[C::pad(t + C::T * q + r * STRIDE)];
+        team_sync<C::T>(team);
+        TwBase b;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) b.w[j] = ((1 << j) < R) ? s_tw2[((1 << j) - 1) * C::R1 + t] : make_float2(1.f, 0.f);
+        apply_tw_all_q<C>(v, b, typename make_iseq<NQ>::type{});
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) fft_reg<R, 0>(&v[q * R]);
+    } else {
+        team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+    }
 }
 
 template <class C> struct LastPass {

@@ -26,6 +26,9 @@
 #include "vvb_fft_core.cuh"
 #include <stdint.h>
 
+#ifndef VVB_INV_BASETW
+#define VVB_INV_BASETW 1              /* marching ISTFT, 32 x 32: 5 twiddle bases from shared memory + computed powers */
+#endif
 #ifndef VVB_FWD_TABLE_TWIDDLES
 #define VVB_FWD_TABLE_TWIDDLES 0      /* 1: the generic forward kernel loads twiddles / window from shared memory (A/B builds) */
 #endif
@@ -820,6 +823,7 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
                 team_sync<T>(team);                                    /* all reads of the staged X are done */
                 prefetch(frame + 1, off_next, bulk_next);
                 if constexpr (REGTW) team_fft_regtw<C>(v, xb, twb, t, team);
+                else if constexpr (VVB_INV_BASETW && C::T == 32 && C::R1 == 32 && C::R2 == 32 && C::NP == 2) team_fft_basetw<C>(v, xb, s_tw2, t, team);
                 else team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
                 /* v[q*RL + r] is sample pair i = t + T*(q + NQ*r): accumulate into that slot */
 #pragma unroll
@@ -962,7 +966,8 @@ __global__ void __launch_bounds__(32 * G, MINB) istft_pair_kernel(const PairArgs
                             v[q * R + r] = make_float2(x1.y + x2.x, x1.x - x2.y);
                         }
                 }
-                team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+                if constexpr (VVB_INV_BASETW && C::R1 == 32 && C::R2 == 32 && C::NP == 2) team_fft_basetw<C>(v, xb, s_tw2, t, team);
+                else team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
                 /* v = (N x_{f+1}[i], N x_f[i]) for i = t + 32 (q + r NS/32) */
 #pragma unroll
                 for (int q = 0; q < L::NQ; ++q)
