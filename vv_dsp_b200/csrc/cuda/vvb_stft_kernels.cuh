@@ -26,6 +26,9 @@
 #include "vvb_fft_core.cuh"
 #include <stdint.h>
 
+#ifndef VVB_FWD_BASETW
+#define VVB_FWD_BASETW 0              /* marching STFT, 32 x 32: 1 = re-read the twiddle bases per frame instead of keeping them in registers */
+#endif
 #ifndef VVB_INV_BASETW
 #define VVB_INV_BASETW 1              /* marching ISTFT, 32 x 32: 5 twiddle bases from shared memory + computed powers */
 #endif
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
     for (int r = 0; r < E; ++r) win[r] = __ldg(reinterpret_cast<const float2*>(a.tables + TB::WIN) + t + T * r);
     constexpr bool REGTW = (C::T == 32 && C::NP == 2 && C::R1 == 32 && C::R2 == 32);
     TwBase twb;
-    if constexpr (REGTW) twb = load_tw_base<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);
+    if constexpr (REGTW && !VVB_FWD_BASETW) twb = load_tw_base<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);
     const float2 hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);   /* (cos, sin)(2 pi t/N)/2, t < T <= M/2 */
 
     const int F = a.frames;
@@ -459,7 +462,8 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
                 team_fft_regtw<C>(v, xb, twb, t, team);
                 split_shuffle_store<C, OUT>(v, hw_t, t, a.out, ((long long)b * F + frame) * a.out_pitch);
             } else if constexpr (REGTW) {
-                team_fft_regtw<C>(v, xb, twb, t, team);
+                if constexpr (VVB_FWD_BASETW) team_fft_basetw<C>(v, xb, s_tw2, t, team);
+                else team_fft_regtw<C>(v, xb, twb, t, team);
                 team_store_natural<C>(v, xb, t);
                 team_sync<T>(team);
                 split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, ((long long)b * F + frame) * a.out_pitch);
