@@ -26,6 +26,9 @@
 #include "vvb_fft_core.cuh"
 #include <stdint.h>
 
+#ifndef VVB_FWD_HALF_SPLIT
+#define VVB_FWD_HALF_SPLIT 1          /* marching STFT, 32 x 32: publish only the 16 slots the partner lane needs */
+#endif
 #ifndef VVB_FWD_BASETW
 #define VVB_FWD_BASETW 0              /* marching STFT, 32 x 32: 1 = re-read the twiddle bases per frame instead of keeping them in registers */
 #endif
@@ -317,6 +320,40 @@ VVB_DEV void split_math(float2 A, float2 Bc, float2 hw, float2& x0, float2& x1)
     x0 = __ffma2_rn(splat(0.5f), sm, make_float2(-g.x, -g.y));
     x1 = __ffma2_rn(make_float2(0.5f, -0.5f), sm, make_float2(g.x, -g.y));
 }
+/* ---- split step that exchanges only what the partner needs (one-warp 32 x 32 transforms).
+ * After the last pass lane t holds column t, Z[t + 32 r] in v[r].  Bin k = t + 32 i (i < 16) pairs with
+ * M - k = (32 - t) + 32 (31 - i): lane 32 - t, slot 31 - i >= 16.  So a lane only has to publish its slots 16..31 and
+ * to read 16 partner values; the A operand is already in its own registers.  16 STS.64 + 16 LDS.64 per frame
+ * instead of 32 + 32: 64 shared-memory wavefronts fewer, in a kernel that sits at 86 % of that peak. */
+template <class C, int OUT, int I> VVB_DEV void split_pair_half(const float2 (&v)[C::E], const float2* xb, float2 hw_t, int t, void* out, long long row)
+{
+    constexpr int M = C::M, T = C::T;
+    const int k = t + T * I;
+    const float2 A = v[I];
+    float2 Bc = xb[C::pad((M - k) & (M - 1))];
+    if constexpr (I == 0) { if (t == 0) Bc = A; }                      /* k = 0 pairs with itself (slot 0 is not published) */
+    constexpr float cr = TwC<2 * C::E, I>::c, sr = TwC<2 * C::E, I>::s;
+    float2 x0, x1;
+    split_math(A, Bc, cmul(hw_t, make_float2(cr, sr)), x0, x1);
+    emit_bin<OUT>(out, row + k, x0);
+    emit_bin<OUT>(out, row + M - k, x1);
+}
+template <class C, int OUT, int... Is> VVB_DEV void split_pairs_half(const float2 (&v)[C::E], const float2* xb, float2 hw_t, int t, void* out, long long row, iseq<Is...>)
+{
+    (split_pair_half<C, OUT, Is>(v, xb, hw_t, t, out, row), ...);
+}
+/* publish slots 16..31, then split; the caller syncs the team before xb is reused */
+template <class C, int OUT> VVB_DEV void split_and_store_half(const float2 (&v)[C::E], float2* xb, float2 hw_t, int t, int team, void* out, long long row)
+{
+    static_assert(C::T == 32 && C::E == 32 && C::R2 == 32 && C::NP == 2, "column layout of the 32 x 32 transform");
+    constexpr int M = C::M;
+#pragma unroll
+    for (int r = 16; r < 32; ++r) xb[C::pad(t + 32 * r)] = v[r];
+    team_sync<C::T>(team);
+    split_pairs_half<C, OUT>(v, xb, hw_t, t, out, row, typename make_iseq<16>::type{});
+    if (t == 0) emit_bin<OUT>(out, row + M / 2, make_float2(v[16].x, -v[16].y));       /* k = M/2: X = conj(Z[M/2]) */
+}
+
 template <class C, int OUT, int R2> VVB_DEV void split_shfl_pair(const float2 (&v)[C::E], float2 hw_t, int t, int src, void* out, long long row)
 {
     constexpr int R = 2 * R2, M = C::M;                                /* even slot */
@@ -464,9 +501,13 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
             } else if constexpr (REGTW) {
                 if constexpr (VVB_FWD_BASETW) team_fft_basetw<C>(v, xb, s_tw2, t, team);
                 else team_fft_regtw<C>(v, xb, twb, t, team);
-                team_store_natural<C>(v, xb, t);
-                team_sync<T>(team);
-                split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+                if constexpr (VVB_FWD_HALF_SPLIT) {
+                    split_and_store_half<C, OUT>(v, xb, hw_t, t, team, a.out, ((long long)b * F + frame) * a.out_pitch);
+                } else {
+                    team_store_natural<C>(v, xb, t);
+                    team_sync<T>(team);
+                    split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+                }
                 team_sync<T>(team);                                    /* xb is reused by the next frame */
             } else {
                 team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
