@@ -27,7 +27,7 @@
 #include <stdint.h>
 
 #ifndef VVB_FWD_HALF_SPLIT
-#define VVB_FWD_HALF_SPLIT 1          /* marching STFT, 32 x 32: publish only the 16 slots the partner lane needs */
+#define VVB_FWD_HALF_SPLIT 1          /* forward kernels: publish only the half column the partner thread needs */
 #endif
 #ifndef VVB_FWD_BASETW
 #define VVB_FWD_BASETW 0              /* marching STFT, 32 x 32: 1 = re-read the twiddle bases per frame instead of keeping them in registers */
@@ -101,6 +101,77 @@ VVB_DEV void copy_table(float* dst, const float* src, int count)
 }
 
 /* ============================================================== forward (analysis) */
+template <int OUT> VVB_DEV void emit_bin(void* out, long long idx, float2 x)
+{
+    if constexpr (OUT == OUT_COMPLEX) reinterpret_cast<float2*>(out)[idx] = x;
+    else if constexpr (OUT == OUT_POWER) reinterpret_cast<float*>(out)[idx] = x.x * x.x + x.y * x.y;
+    else reinterpret_cast<float*>(out)[idx] = sqrtf(x.x * x.x + x.y * x.y);
+}
+/* X[k] = sm/2 - g, X[M-k] = conj(sm/2 + g) with sm = A + conj(Bc), g = ((sin + j cos)/2) (A - conj(Bc)) */
+VVB_DEV void split_math(float2 A, float2 Bc, float2 hw, float2& x0, float2& x1)
+{
+    const float2 sm = __fadd2_rn(A, make_float2(Bc.x, -Bc.y));
+    const float2 df = __fadd2_rn(A, make_float2(-Bc.x, Bc.y));
+    const float2 g = cmul(df, make_float2(hw.y, hw.x));
+    x0 = __ffma2_rn(splat(0.5f), sm, make_float2(-g.x, -g.y));
+    x1 = __ffma2_rn(make_float2(0.5f, -0.5f), sm, make_float2(g.x, -g.y));
+}
+/* ---- split step that exchanges only what the partner needs.
+ * After the last pass thread t of a team holds its whole column, Z[t + T i] for every i < E, in
+ * v[(i % NQ) * R + i / NQ] (NQ, R: sub-transforms and radix of the last pass).  Bin k = t + T i (i < E/2) pairs with
+ * M - k = (T - t) + T (E - 1 - i): thread T - t, column index E - 1 - i >= E/2.  So a thread only has to publish the
+ * upper half of its column and to read E/2 partner values; the A operand is already in its own registers.
+ * E/2 STS.64 + E/2 LDS.64 per frame instead of E + E: at fft_size 2048 that is 64 shared-memory wavefronts fewer,
+ * in a kernel that sits at 86 % of that peak.  ROT: twiddle = per-thread value x compile-time rotation; otherwise
+ * it is read from the shared-memory table (fft_size 8192, where computing it was measured slower). */
+template <class C, int I> VVB_DEV constexpr int column_slot()
+{
+    using L = LastPass<C>;
+    return (I % L::NQ) * L::R + ct_bitrev(I / L::NQ, L::R);
+}
+template <class C, int OUT, bool ROT, int I>
+VVB_DEV void split_pair_half(const float2 (&v)[C::E], const float2* xb, float2 hw_t, const float2* s_post, int t, void* out, long long row)
+{
+    constexpr int M = C::M, T = C::T;
+    const int k = t + T * I;
+    const float2 A = v[column_slot<C, I>()];
+    float2 Bc = xb[C::pad((M - k) & (M - 1))];
+    if constexpr (I == 0) { if (t == 0) Bc = A; }                      /* k = 0 pairs with itself (slot 0 is not published) */
+    float2 hw;
+    if constexpr (ROT) {
+        constexpr float cr = TwC<2 * C::E, I>::c, sr = TwC<2 * C::E, I>::s;
+        hw = cmul(hw_t, make_float2(cr, sr));
+    } else {
+        hw = s_post[k];
+    }
+    float2 x0, x1;
+    split_math(A, Bc, hw, x0, x1);
+    emit_bin<OUT>(out, row + k, x0);
+    emit_bin<OUT>(out, row + M - k, x1);
+}
+template <class C, int OUT, bool ROT, int... Is>
+VVB_DEV void split_pairs_half(const float2 (&v)[C::E], const float2* xb, float2 hw_t, const float2* s_post, int t, void* out, long long row, iseq<Is...>)
+{
+    (split_pair_half<C, OUT, ROT, Is>(v, xb, hw_t, s_post, t, out, row), ...);
+}
+template <class C, int... Is> VVB_DEV void publish_upper_half(const float2 (&v)[C::E], float2* xb, int t, iseq<Is...>)
+{
+    ((xb[C::pad(t + C::T * (C::E / 2 + Is))] = v[column_slot<C, C::E / 2 + Is>()]), ...);
+}
+/* publish the upper half of the column, then split; the caller syncs the team before xb is reused */
+template <class C, int OUT, bool ROT>
+VVB_DEV void split_and_store_half(const float2 (&v)[C::E], float2* xb, float2 hw_t, const float2* s_post, int t, int team, void* out, long long row)
+{
+    constexpr int M = C::M, E = C::E;
+    publish_upper_half<C>(v, xb, t, typename make_iseq<E / 2>::type{});
+    team_sync<C::T>(team);
+    split_pairs_half<C, OUT, ROT>(v, xb, hw_t, s_post, t, out, row, typename make_iseq<E / 2>::type{});
+    if (t == 0) {                                                      /* k = M/2 = T E/2: X = conj(Z[M/2]) */
+        const float2 A = v[column_slot<C, E / 2>()];
+        emit_bin<OUT>(out, row + M / 2, make_float2(A.x, -A.y));
+    }
+}
+
 template <class C, int OUT> VVB_DEV void split_and_store(const float2* xb, const float2* s_post, int t, void* out, long long row);
 template <class C, int OUT> VVB_DEV void split_and_store_rot(const float2* xb, float2 hw_t, int t, void* out, long long row);
 
@@ -201,15 +272,27 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
         /* ---- M-point complex FFT of z[i] = x[2i] + j x[2i+1] */
         if constexpr (REGTW) team_fft_regtw2<C>(v, xb, twb, t, team);
         else team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
-        team_store_natural<C>(v, xb, t);
-        team_sync<T>(team);
 
         /* ---- split step: X[k] = (Z[k] + conj Z[M-k])/2 - (j/2) W_N^k (Z[k] - conj Z[M-k]) */
         const long long row = ((long long)b * a.frames + f) * a.out_pitch;
-        if constexpr (!VVB_FWD_TABLE_TWIDDLES && C::M <= 2048) {
-            if (active) split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, row);
+        if constexpr (VVB_FWD_HALF_SPLIT && !VVB_FWD_TABLE_TWIDDLES) {
+            publish_upper_half<C>(v, xb, t, typename make_iseq<E / 2>::type{});
+            team_sync<T>(team);
+            if (active) {
+                split_pairs_half<C, OUT, (C::M <= 2048)>(v, xb, hw_t, s_post, t, a.out, row, typename make_iseq<E / 2>::type{});
+                if (t == 0) {
+                    const float2 A = v[column_slot<C, E / 2>()];
+                    emit_bin<OUT>(a.out, row + M / 2, make_float2(A.x, -A.y));
+                }
+            }
         } else {
-            if (active) split_and_store<C, OUT>(xb, s_post, t, a.out, row);
+            team_store_natural<C>(v, xb, t);
+            team_sync<T>(team);
+            if constexpr (!VVB_FWD_TABLE_TWIDDLES && C::M <= 2048) {
+                if (active) split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, row);
+            } else {
+                if (active) split_and_store<C, OUT>(xb, s_post, t, a.out, row);
+            }
         }
         team_sync<T>(team);                                           /* xb is reused next group */
     }
@@ -305,55 +388,6 @@ VVB_DEV void split_and_store_rot(const float2* xb, float2 hw_t, int t, void* out
  * paired with itself (r <-> 32 - r): all lanes run the same register-only code on their own column and
  * only lane 0 stores.  This replaces a natural-order store (32 STS.64), 32 paired LDS.64 and two team
  * barriers per frame by 32 SHFL -- the kernel is bound by shared-memory/LSU wavefronts. */
-template <int OUT> VVB_DEV void emit_bin(void* out, long long idx, float2 x)
-{
-    if constexpr (OUT == OUT_COMPLEX) reinterpret_cast<float2*>(out)[idx] = x;
-    else if constexpr (OUT == OUT_POWER) reinterpret_cast<float*>(out)[idx] = x.x * x.x + x.y * x.y;
-    else reinterpret_cast<float*>(out)[idx] = sqrtf(x.x * x.x + x.y * x.y);
-}
-/* X[k] = sm/2 - g, X[M-k] = conj(sm/2 + g) with sm = A + conj(Bc), g = ((sin + j cos)/2) (A - conj(Bc)) */
-VVB_DEV void split_math(float2 A, float2 Bc, float2 hw, float2& x0, float2& x1)
-{
-    const float2 sm = __fadd2_rn(A, make_float2(Bc.x, -Bc.y));
-    const float2 df = __fadd2_rn(A, make_float2(-Bc.x, Bc.y));
-    const float2 g = cmul(df, make_float2(hw.y, hw.x));
-    x0 = __ffma2_rn(splat(0.5f), sm, make_float2(-g.x, -g.y));
-    x1 = __ffma2_rn(make_float2(0.5f, -0.5f), sm, make_float2(g.x, -g.y));
-}
-/* ---- split step that exchanges only what the partner needs (one-warp 32 x 32 transforms).
- * After the last pass lane t holds column t, Z[t + 32 r] in v[r].  Bin k = t + 32 i (i < 16) pairs with
- * M - k = (32 - t) + 32 (31 - i): lane 32 - t, slot 31 - i >= 16.  So a lane only has to publish its slots 16..31 and
- * to read 16 partner values; the A operand is already in its own registers.  16 STS.64 + 16 LDS.64 per frame
- * instead of 32 + 32: 64 shared-memory wavefronts fewer, in a kernel that sits at 86 % of that peak. */
-template <class C, int OUT, int I> VVB_DEV void split_pair_half(const float2 (&v)[C::E], const float2* xb, float2 hw_t, int t, void* out, long long row)
-{
-    constexpr int M = C::M, T = C::T;
-    const int k = t + T * I;
-    const float2 A = v[I];
-    float2 Bc = xb[C::pad((M - k) & (M - 1))];
-    if constexpr (I == 0) { if (t == 0) Bc = A; }                      /* k = 0 pairs with itself (slot 0 is not published) */
-    constexpr float cr = TwC<2 * C::E, I>::c, sr = TwC<2 * C::E, I>::s;
-    float2 x0, x1;
-    split_math(A, Bc, cmul(hw_t, make_float2(cr, sr)), x0, x1);
-    emit_bin<OUT>(out, row + k, x0);
-    emit_bin<OUT>(out, row + M - k, x1);
-}
-template <class C, int OUT, int... Is> VVB_DEV void split_pairs_half(const float2 (&v)[C::E], const float2* xb, float2 hw_t, int t, void* out, long long row, iseq<Is...>)
-{
-    (split_pair_half<C, OUT, Is>(v, xb, hw_t, t, out, row), ...);
-}
-/* publish slots 16..31, then split; the caller syncs the team before xb is reused */
-template <class C, int OUT> VVB_DEV void split_and_store_half(const float2 (&v)[C::E], float2* xb, float2 hw_t, int t, int team, void* out, long long row)
-{
-    static_assert(C::T == 32 && C::E == 32 && C::R2 == 32 && C::NP == 2, "column layout of the 32 x 32 transform");
-    constexpr int M = C::M;
-#pragma unroll
-    for (int r = 16; r < 32; ++r) xb[C::pad(t + 32 * r)] = v[r];
-    team_sync<C::T>(team);
-    split_pairs_half<C, OUT>(v, xb, hw_t, t, out, row, typename make_iseq<16>::type{});
-    if (t == 0) emit_bin<OUT>(out, row + M / 2, make_float2(v[16].x, -v[16].y));       /* k = M/2: X = conj(Z[M/2]) */
-}
-
 template <class C, int OUT, int R2> VVB_DEV void split_shfl_pair(const float2 (&v)[C::E], float2 hw_t, int t, int src, void* out, long long row)
 {
     constexpr int R = 2 * R2, M = C::M;                                /* even slot */
@@ -502,7 +536,7 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
                 if constexpr (VVB_FWD_BASETW) team_fft_basetw<C>(v, xb, s_tw2, t, team);
                 else team_fft_regtw<C>(v, xb, twb, t, team);
                 if constexpr (VVB_FWD_HALF_SPLIT) {
-                    split_and_store_half<C, OUT>(v, xb, hw_t, t, team, a.out, ((long long)b * F + frame) * a.out_pitch);
+                    split_and_store_half<C, OUT, true>(v, xb, hw_t, s_post, t, team, a.out, ((long long)b * F + frame) * a.out_pitch);
                 } else {
                     team_store_natural<C>(v, xb, t);
                     team_sync<T>(team);
@@ -511,11 +545,17 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
                 team_sync<T>(team);                                    /* xb is reused by the next frame */
             } else {
                 team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
-                team_store_natural<C>(v, xb, t);
-                team_sync<T>(team);
                 /* computed split twiddles help at fft_size 4096 (2.94 -> 2.86 ms) and hurt at 8192 (3.24 -> 3.75 ms) */
-                if constexpr (C::M <= 2048) split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, ((long long)b * F + frame) * a.out_pitch);
-                else split_and_store<C, OUT>(xb, s_post, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+                /* (fft_size 8192 with power / magnitude output is the one case measured slower with the half exchange:
+                 * 2.46 -> 2.58 ms, while its complex output gains 8 %) */
+                if constexpr (VVB_FWD_HALF_SPLIT && !(C::M == 4096 && OUT != OUT_COMPLEX)) {
+                    split_and_store_half<C, OUT, (C::M <= 2048)>(v, xb, hw_t, s_post, t, team, a.out, ((long long)b * F + frame) * a.out_pitch);
+                } else {
+                    team_store_natural<C>(v, xb, t);
+                    team_sync<T>(team);
+                    if constexpr (C::M <= 2048) split_and_store_rot<C, OUT>(xb, hw_t, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+                    else split_and_store<C, OUT>(xb, s_post, t, a.out, ((long long)b * F + frame) * a.out_pitch);
+                }
                 team_sync<T>(team);                                    /* xb is reused by the next frame */
             }
         }
