@@ -836,8 +836,10 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
     /* split-step twiddle of this thread: (cos, sin)(2 pi t / N) / 2; its bins k = t + T r differ from it
      * by the compile-time rotation 2 pi r / (2E) */
     const float2 hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);   /* t < T <= M/2 */
-    /* (computed inter-pass twiddles, as in the forward kernel, push this kernel from 242 to 255 registers
-     * and into spills -- 2.25 vs 2.12 ms measured -- because of the 64-register accumulator: tables here) */
+    /* Twiddle bases held in registers across frames, as in the forward kernel, push this kernel from 242 to 255
+     * registers and into spills (2.25 vs 2.12 ms measured) because of the 64-register accumulator.  The 32 x 32
+     * configuration instead re-reads the five bases from shared memory every frame (team_fft_basetw below):
+     * they are live only during the twiddle phase, 26 of the 31 LDS.64 disappear, 2.02 -> 1.91 ms. */
     constexpr bool REGTW = false;
     TwBase twb;
     if constexpr (REGTW) twb = load_tw_base<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);
