@@ -91,6 +91,42 @@ def check_batch_inverse(lib, oracle, nfft, hop, win, n, batch=2):
             assert np.allclose(short[0][m], refshort[m], rtol=0, atol=5e-5 * max(np.abs(refshort).max(), 1e-30))
 
 
+def check_inverse_few_frames(lib, oracle, sizes, frame_counts=(1, 2, 3, 4, 5, 9)):
+    """ISTFT of very short signals (1..9 frames: every range is head + tail, odd and even pair counts) and of outputs longer
+    than the frames cover, raw and normalised, against the oracle.  Normalised values are compared where the window-sum
+    is above 1e-2 (below that the reference's own divide amplifies float32 rounding without bound)."""
+    worst = 0.0
+    for nfft, hop in sizes:
+        w = oracle.window("hann", nfft)[1].astype(np.float64)
+        with Stft(nfft, hop, "hann", lib=lib) as h:
+            for F in frame_counts:
+                n = (F - 1) * hop + nfft
+                x = np.stack([noise(3 + F + i, n) for i in range(3)])
+                spec = np.stack([oracle.stft(x[i], nfft, hop) for i in range(3)])
+                assert spec.shape[1] == F
+                for extra in (0, 7, nfft):
+                    nn = np.zeros(n + extra + nfft)
+                    for f in range(F):
+                        nn[f * hop:f * hop + nfft] += w * w
+                    good = np.broadcast_to(nn[:n + extra] > 1e-2, (3, n + extra))
+                    for norm in (False, True):
+                        if norm and 2 * hop > nfft:
+                            continue
+                        y = h.batch_inverse(spec, n + extra, norm)
+                        ref = np.stack([oracle.istft(spec[i], nfft, hop, n + extra, "hann", normalise=norm) for i in range(3)])
+                        assert np.all(y[:, n:] == 0)                                  # nothing covers: exactly zero
+                        if norm:
+                            err = np.abs((y - ref)[good]).max() / max(np.abs(ref[good]).max(), 1e-30)
+                        else:
+                            err = np.abs(y - ref).max() / max(np.abs(ref).max(), 1e-30)
+                        worst = max(worst, float(err))
+                        # the reference's twiddle recurrence is 2.3e-5 / 4.3e-5 of max|X| off at fft_size 4096 / 8192
+                        # (SURVEY.md section 8c) and the divide by a window-sum of 1e-2 amplifies that up to 100 times
+                        tol = 1e-4 if (nfft <= 2048 or not norm) else 5e-3
+                        assert err < tol, (nfft, hop, F, extra, norm, err)
+    return worst
+
+
 def check_spectrogram(lib, oracle, nfft, hop, win, n):
     x = noise(77 + nfft, n)
     with Stft(nfft, hop, win, lib=lib) as h:

@@ -115,3 +115,7 @@ def test_bluestein_unfused_and_direct_paths(emu, oracle, monkeypatch):
     monkeypatch.delenv("VVB_BLUESTEIN_UNFUSED")
     monkeypatch.setenv("VVB_NO_BLUESTEIN", "1")
     pc.check_bluestein(emu, oracle, [(100, 25)])
+
+
+def test_inverse_few_frames(emu, oracle):
+    pc.check_inverse_few_frames(emu, oracle, [(256, 64), (512, 256), (1024, 128), (2048, 512)], (1, 2, 3, 5))

@@ -281,3 +281,7 @@ def test_bluestein_unfused_and_direct_paths(lib, oracle, monkeypatch):
     monkeypatch.delenv("VVB_BLUESTEIN_UNFUSED")
     monkeypatch.setenv("VVB_NO_BLUESTEIN", "1")
     pc.check_bluestein(lib, oracle, [(100, 25)])
+
+
+def test_inverse_few_frames(lib, oracle):
+    pc.check_inverse_few_frames(lib, oracle, [(256, 64), (256, 32), (256, 128), (512, 128), (512, 256), (1024, 256), (1024, 128), (1024, 512), (2048, 512), (4096, 1024), (8192, 2048)], (1, 2, 3, 4, 5, 9))
