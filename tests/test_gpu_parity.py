@@ -285,3 +285,28 @@ def test_bluestein_unfused_and_direct_paths(lib, oracle, monkeypatch):
 
 def test_inverse_few_frames(lib, oracle):
     pc.check_inverse_few_frames(lib, oracle, [(256, 64), (256, 32), (256, 128), (512, 128), (512, 256), (1024, 256), (1024, 128), (1024, 512), (2048, 512), (4096, 1024), (8192, 2048)], (1, 2, 3, 4, 5, 9))
+
+
+def test_mel_chain_device_buffers(lib, oracle):
+    """device-resident signals / outputs of the log-mel and MFCC chains give the same bits as the host-buffer path,
+    on a caller-provided stream, with strided (pitched) signal rows"""
+    import torch
+    from vv_dsp_b200 import Stft, mel_filterbank
+    nfft, hop, n_mels = 2048, 512, 80
+    _, w = mel_filterbank(nfft, n_mels, 48000.0, 0.0, 24000.0, lib=lib)
+    x = np.stack([noise(200 + i, 40000) for i in range(6)])
+    s = torch.cuda.Stream()
+    big = torch.zeros((6, 40960), device="cuda")
+    big[:, :40000] = torch.from_numpy(x).cuda()
+    xd = big[:, :40000]                                        # row pitch 40960 != n
+    torch.cuda.synchronize()
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        lm_host = h.batch_logmel(x, w)
+        mf_host = h.batch_mfcc(x, w, 13, lifter=22.0)
+        h.set_stream(s.cuda_stream)
+        lm_dev = h.batch_logmel(xd, w)
+        mf_dev = h.batch_mfcc(xd, w, 13, lifter=22.0)
+        s.synchronize()
+        assert lm_dev.is_cuda and mf_dev.is_cuda
+        assert lm_dev.cpu().numpy().tobytes() == lm_host.tobytes()
+        assert mf_dev.cpu().numpy().tobytes() == mf_host.tobytes()
