@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(256) logmel_kernel(const MelArgs a)
  * for lane = frame.  `stages` tile buffers form a ring: thread 0 issues the copy for tile it+stages-1 right
  * after the CTA has finished tile it-1, so stages-1 tiles (>= 128 KB at the headline shape) are in flight per
  * SM while the warps reduce the current one.
- * Work split: a thread owns TWO frames (r and r + R/2: two independent sums that share every weight) and one
- * of 8*64/R band slots.  The host has cut every filter into groups of four taps and dealt whole filters to
+ * Work split: a thread owns FPT frames (1: 16 warps per CTA, the default; 2: rows r and r + R/2, two independent
+ * sums that share every weight, 8 warps) and one of the 16 / 32 / 64 / 128 band slots of its tile shape.  The host has cut every filter into groups of four taps and dealt whole filters to
  * slots, longest first (mel.c), so a slot is one flat list of groups: no per-band inner loop, nothing to
  * diverge on inside a warp, and the loads of group g+1 (descriptor, four weights, eight power values) are
  * issued before the sums of group g.  Summation order per band is unchanged: ascending bins, separate
@@ -529,10 +529,10 @@ constexpr int MEL_TMA_MAX_MELS = 512;
 
 struct MelGroup { int4 d; float4 w; float p0[4], p1[4]; };
 
-template <int R> __global__ void __launch_bounds__(256) logmel_tma_kernel(const MelArgs a, const int stages, const int stage_floats,
+template <int R, int FPT> __global__ void __launch_bounds__(256 * (2 / FPT)) logmel_tma_kernel(const MelArgs a, const int stages, const int stage_floats,
                                                                            const int n_groups)
 {
-    constexpr int HALF = R / 2, SUB = 32 / HALF, NSLOT = 8 * SUB;
+    constexpr int HALF = R / FPT, SUB = 32 / HALF, NTHR = 256 * (2 / FPT), NSLOT = (NTHR / 32) * SUB;   /* FPT frames per thread */
     constexpr int VARIANT = (R == 32) ? 0 : (R == 16) ? 1 : (R == 8) ? 2 : 3;
     static_assert(NSLOT == (16 << VARIANT), "slot count must match the host-side tables");
 #ifdef VVB_EMU
@@ -549,7 +549,7 @@ template <int R> __global__ void __launch_bounds__(256) logmel_tma_kernel(const 
     float* sOut = ring + (size_t)stages * stage_floats;                 /* [R][n_mels | 1] */
     const int opitch = a.n_mels | 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r0 = lane & (HALF - 1), r1 = r0 + HALF, slot = warp * SUB + lane / HALF;
+    const int r0 = lane & (HALF - 1), r1 = (FPT == 2) ? r0 + HALF : r0, slot = warp * SUB + lane / HALF;
     const long long ntiles = (a.frames + R - 1) / R;
     const long long tile_floats = (long long)R * a.bins;
     const int* hdr = a.meta + 3 * a.n_mels;
@@ -574,7 +574,7 @@ template <int R> __global__ void __launch_bounds__(256) logmel_tma_kernel(const 
     {   /* the tables of this tile shape, once per CTA (the first tiles are already in flight) */
         const int4* gdesc = reinterpret_cast<const int4*>(a.meta + __ldg(hdr + 4 + VARIANT));
         const float4* gwq = reinterpret_cast<const float4*>(a.w + __ldg(hdr + 8));
-        for (int g = tid; g < n_groups; g += 256) {
+        for (int g = tid; g < n_groups; g += NTHR) {
             const int4 d = __ldg(gdesc + g);
             s_desc[g] = d;
             s_wq[g] = __ldg(gwq + d.y);                                 /* weights follow the slot order too */
@@ -593,7 +593,7 @@ template <int R> __global__ void __launch_bounds__(256) logmel_tma_kernel(const 
             mbar_wait(&bars[s], (unsigned)((it / stages) & 1));
         } else {
             const float* src = a.power + tile * tile_floats;
-            for (long long i = tid; i < (long long)nf * a.bins; i += 256) P[i] = __ldg(src + i);
+            for (long long i = tid; i < (long long)nf * a.bins; i += NTHR) P[i] = __ldg(src + i);
             __syncthreads();
         }
         const float* P0 = P + (size_t)r0 * a.bins;
@@ -604,7 +604,7 @@ template <int R> __global__ void __launch_bounds__(256) logmel_tma_kernel(const 
             q.d = s_desc[g];
             q.w = s_wq[g];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { q.p0[u] = P0[q.d.x + u]; q.p1[u] = P1[q.d.x + u]; }
+            for (int u = 0; u < 4; ++u) { q.p0[u] = P0[q.d.x + u]; if constexpr (FPT == 2) q.p1[u] = P1[q.d.x + u]; else q.p1[u] = 0.f; }
         };
         float acc0 = 0.f, acc1 = 0.f;
         auto reduce = [&](const MelGroup& q) {
@@ -617,7 +617,7 @@ template <int R> __global__ void __launch_bounds__(256) logmel_tma_kernel(const 
             }
             if (q.d.z & 8) {                                            /* last group of a filter */
                 sOut[r0 * opitch + q.d.w] = acc0;
-                sOut[r1 * opitch + q.d.w] = acc1;
+                if constexpr (FPT == 2) sOut[r1 * opitch + q.d.w] = acc1;
                 acc0 = 0.f; acc1 = 0.f;
             }
         };
@@ -632,7 +632,7 @@ template <int R> __global__ void __launch_bounds__(256) logmel_tma_kernel(const 
             }
         }
         __syncthreads();
-        for (int idx = tid; idx < nf * a.n_mels; idx += 256) {
+        for (int idx = tid; idx < nf * a.n_mels; idx += NTHR) {
             const int rr = idx / a.n_mels, mm = idx - rr * a.n_mels;
             a.out[(f0 + rr) * a.n_mels + mm] = logf(sOut[rr * opitch + mm] + a.eps);
         }
