@@ -679,12 +679,21 @@ __global__ void __launch_bounds__(256) mfcc_kernel(const MfccArgs a)
         }
         __syncthreads();
         if (lane < nf) {
+            /* two coefficients per pass share every x[n] load: two independent ordered chains per thread */
             const float* x = tile + lane * pitch;
-            for (int k = warp; k < a.n_coeffs; k += 8) {
-                const float* c = tab + k * a.n_mels;
-                float sum = 0.f;
-                for (int n = 0; n < a.n_mels; ++n) sum = __fadd_rn(sum, __fmul_rn(x[n], c[n]));
-                so[lane * opitch + k] = __fmul_rn(sum, __ldg(a.lifter + k));
+            for (int k = warp; k < a.n_coeffs; k += 16) {
+                const int k2 = k + 8;
+                const bool two = k2 < a.n_coeffs;
+                const float* c0 = tab + k * a.n_mels;
+                const float* c1 = tab + (two ? k2 : k) * a.n_mels;
+                float s0 = 0.f, s1 = 0.f;
+                for (int n = 0; n < a.n_mels; ++n) {
+                    const float xv = x[n];
+                    s0 = __fadd_rn(s0, __fmul_rn(xv, c0[n]));
+                    s1 = __fadd_rn(s1, __fmul_rn(xv, c1[n]));
+                }
+                so[lane * opitch + k] = __fmul_rn(s0, __ldg(a.lifter + k));
+                if (two) so[lane * opitch + k2] = __fmul_rn(s1, __ldg(a.lifter + k2));
             }
         }
         __syncthreads();
