@@ -298,8 +298,8 @@ def main():
         bytes_inv = B * (8 * FRAMES * BINS + 4 * N_SAMPLES)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_ncu_full_v6_packed_tma_kernels.csv
         # (same shape, same kernels): equal to the algorithmic bytes, i.e. no re-reads
-        NCU_TRAFFIC = {"istft_march_kernel": 7.872063e9 + 1.953476e9, "stft_march_kernel": 1.973042e9 + 7.786636e9}
-        dom = ("istft_march_kernel", inv_ms, bytes_inv) if inv_ms >= fwd_ms else ("stft_march_kernel", fwd_ms, bytes_fwd)
+        NCU_TRAFFIC = {"istft_ws_kernel": 7.872063e9 + 1.953476e9, "stft_march_kernel": 1.973042e9 + 7.786636e9}
+        dom = ("istft_ws_kernel", inv_ms, bytes_inv) if inv_ms >= fwd_ms else ("stft_march_kernel", fwd_ms, bytes_fwd)
         achieved = dom[2] / (dom[1] * 1e-3) / 1e9
         flops_dir = B * FRAMES * 5 * NFFT * 11                     # 5 N log2 N per frame per direction
         line = {

@@ -25,9 +25,10 @@
  * stream (vv_dsp_stft_set_stream) and returns; otherwise it returns after the
  * results are in host memory.
  *
- * Batched entry points need a power-of-two fft_size in [256, 8192] (the Stockham
- * kernels); other sizes return VV_DSP_ERROR_UNSUPPORTED here and are served by the
- * per-frame API.  There is no CPU fallback anywhere.
+ * Every fft_size >= 1 is served on the GPU: powers of two in [256, 8192] by the fused
+ * Stockham kernels (the throughput path), other sizes in [32, 4096] by the fused
+ * chirp-z kernel, the rest by direct-DFT kernels (correct, O(n^2) like the reference's
+ * path for those sizes).  There is no CPU fallback anywhere.
  */
 #ifndef VV_DSP_B200_H
 #define VV_DSP_B200_H
@@ -136,7 +137,7 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_mfcc(
  * Same conventions as vv_dsp_fft_execute (forward unscaled, backward 1/n, R2C Nyquist real, C2R =
  * Re of the inverse of the Hermitian extension).  DEVICE buffers: enqueued on `cuda_stream` (NULL = the
  * plan's stream) and not awaited; any HOST buffer: staged and synchronous.  in == out is allowed for C2C
- * with a power-of-two n in [128, 4096] only. */
+ * with n in [32, 4096] or a power of two up to 8192 (not for the direct-DFT sizes). */
 VV_DSP_NODISCARD vv_dsp_status vv_dsp_fft_execute_batch(const vv_dsp_fft_plan* plan, const void* in,
                                                         vv_dsp_mem_space in_space, void* out,
                                                         vv_dsp_mem_space out_space, size_t batch, void* cuda_stream);
@@ -157,6 +158,9 @@ const char* vv_dsp_b200_last_error(void);
 /* diagnostics: measured FP32 FMA throughput of the current device in TFLOP/s (scalar FFMA when packed == 0,
  * packed FFMA2 otherwise); the denominator of the FP32 side of the roofline */
 vv_dsp_status vv_dsp_b200_fp32_peak(int packed, double* tflops);
+/* diagnostics: the SM clock in MHz at this moment, measured on the device (SM cycles per nanosecond of the global
+ * timer over ~50 us) after everything queued on cuda_stream; synchronises that stream */
+vv_dsp_status vv_dsp_b200_sm_clock_mhz(void* cuda_stream, double* mhz);
 /* number of kernels this process has launched through the library (bench.py's gpu_launches) */
 unsigned long long vv_dsp_b200_kernel_launches(void);
 

@@ -27,6 +27,7 @@ const char* vvb_last_error(void);
 unsigned long long vvb_kernel_launches(void);
 int vvb_device_ready(void);   /* 0 when a usable sm_100-class device is current */
 int vvb_fp32_peak(int packed, double* tflops);   /* diagnostics: measured FFMA (0) / FFMA2 (1) throughput */
+int vvb_sm_clock_mhz(void* stream, double* mhz); /* diagnostics: SM clock right now (cycles per global-timer ns), after the work queued on stream */
 
 /* ---- memory / stream plumbing (device = the engine's device) */
 int vvb_malloc(void** dptr, size_t bytes);

@@ -170,6 +170,13 @@ static inline void emu_named_barrier(int id, int nthreads)
 {
     vvb_emu::barrier_wait(vvb_emu::g_cta->named[id], (unsigned)nthreads);
 }
+/* give the other fibres of the CTA a turn (spin-waits on shared-memory flags / mbarriers) */
+static inline void emu_yield()
+{
+    vvb_emu::Cta &c = *vvb_emu::g_cta;
+    vvb_emu::Fiber &f = c.fibers[c.current];
+    swapcontext(&f.ctx, &c.sched);
+}
 static inline float __shfl_sync(unsigned, float v, int src, int width = 32)
 {
     unsigned t = emu_linear_tid();

@@ -372,7 +372,7 @@ def check_accuracy_vs_truth(lib, oracle, nfft):
 
 
 def check_bluestein(lib, oracle, sizes):
-    """Sizes served by the chirp-z path (no Stockham kernel, 32 <= n <= 2048).  The reference serves them with an O(n^2)
+    """Sizes served by the chirp-z path (no Stockham kernel, 32 <= n <= 4096).  The reference serves them with an O(n^2)
     float32 DFT whose own error grows with n (measured here: 2.5e-5 at n=400, 6e-5 at 1000, 1.5e-4 at 2000 of max|X|),
     so the yardstick is float64 truth: the CUDA result must be within 3e-6 of it, and within the triangle bound
     (own error + the oracle's error) of the oracle.  Frame counts and zero regions stay bit-exact."""

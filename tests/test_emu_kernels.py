@@ -68,7 +68,7 @@ def test_spectrogram(emu, oracle):
 
 
 def test_fft_plans(emu, oracle):
-    pc.check_fft_plans(emu, oracle, [1, 2, 3, 8, 16, 100, 128, 256, 1024, 2048])
+    pc.check_fft_plans(emu, oracle, [1, 2, 3, 8, 16, 100, 128, 256, 1024, 2048, 8192])    # 8192: three-pass C2C, 256-thread team
 
 
 def test_fft_execute_batch(emu, oracle):

@@ -270,7 +270,8 @@ def test_pcm_decode(lib, oracle):
 
 
 def test_bluestein_sizes(lib, oracle):
-    report = pc.check_bluestein(lib, oracle, [(400, 160), (33, 11), (96, 24), (480, 120), (1000, 250), (1536, 384), (2000, 500), (2047, 512), (64, 16)])
+    report = pc.check_bluestein(lib, oracle, [(400, 160), (33, 11), (96, 24), (480, 120), (1000, 250), (1536, 384), (2000, 500), (2047, 512), (64, 16),
+                                              (3000, 750), (4095, 1365)])
     print("error vs float64 truth (mine, reference):", report)
 
 

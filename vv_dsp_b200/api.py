@@ -89,7 +89,10 @@ class Library:
         "vv_dsp_b200_last_error": (C.c_char_p, []),
         "vv_dsp_b200_kernel_launches": (C.c_ulonglong, []),
         "vv_dsp_b200_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+        "vv_dsp_b200_sm_clock_mhz": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     }
+    # entry points newer than round 1: absent from an old library variant loaded for an A/B measurement
+    OPTIONAL = {"vv_dsp_b200_sm_clock_mhz"}
 
     def __init__(self, path: str | None = None):
         path = path or DEFAULT_LIB
@@ -100,6 +103,8 @@ class Library:
         self.path = path
         self.dll = C.CDLL(path)
         for name, (res, args) in self.PROTOS.items():
+            if name in self.OPTIONAL and not hasattr(self.dll, name):
+                continue
             fn = getattr(self.dll, name)
             fn.restype = res
             fn.argtypes = args
@@ -119,6 +124,14 @@ class Library:
         st = self.dll.vv_dsp_b200_fp32_peak(int(packed), C.byref(v))
         if st != 0:
             raise VvDspError(st, "vv_dsp_b200_fp32_peak", self.last_error())
+        return float(v.value)
+
+    def sm_clock_mhz(self, cuda_stream=None) -> float:
+        """SM clock measured on the device right after the work queued on cuda_stream (synchronises it)"""
+        v = C.c_double(0.0)
+        st = self.dll.vv_dsp_b200_sm_clock_mhz(_vp(cuda_stream or 0), C.byref(v))
+        if st != 0:
+            raise VvDspError(st, "vv_dsp_b200_sm_clock_mhz", self.last_error())
         return float(v.value)
 
     def version(self) -> str:

@@ -18,9 +18,10 @@ INC = os.path.join(ROOT, "include")
 LIB = os.path.join(PKG, "lib", "libvvdsp_b200.so")
 OBJ = os.path.join(PKG, "lib", "obj")
 HOST_SRCS = [os.path.join(PKG, "csrc", "host", f) for f in ("window.c", "framing.c", "fft.c", "stft.c", "mel.c", "pcm.c")]
-CUDA_SRCS = [os.path.join(PKG, "csrc", "cuda", "vvb_cuda.cu")]
-CUDA_DEPS = [os.path.join(PKG, "csrc", "cuda", f) for f in
-             ("vvb_fft_core.cuh", "vvb_stft_kernels.cuh", "vvb_direct_kernels.cuh")]
+CUDA_DIR = os.path.join(PKG, "csrc", "cuda")
+# one kernel family per translation unit (vvb_tu_*.cu) + the C-ABI / runtime unit: compiled in parallel
+CUDA_SRCS = sorted(os.path.join(CUDA_DIR, f) for f in os.listdir(CUDA_DIR) if f.endswith(".cu"))
+CUDA_DEPS = sorted(os.path.join(CUDA_DIR, f) for f in os.listdir(CUDA_DIR) if f.endswith(".cuh"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -48,6 +49,8 @@ def _run(cmd, verbose):
         raise RuntimeError("build failed: " + " ".join(cmd[:3]) + " ...")
     if verbose and (r.stdout or r.stderr):
         print(r.stdout + r.stderr)
+    elif "warning" in (r.stdout + r.stderr).lower():       # e.g. ptxas -warn-spills
+        sys.stderr.write(f"[{os.path.basename(cmd[-3])}]\n" + r.stdout + r.stderr)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -59,14 +62,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if force or _stale(o, [src] + hdrs):
             _run(["gcc", "-std=c99", "-O2", "-fPIC", "-Wall", "-Wextra", "-I" + INC, "-c", src, "-o", o], verbose)
         objs.append(o)
+    # VVB_NVCC_EXTRA: extra nvcc flags for A/B builds (e.g. "-DVVB_INV_BASETW=0")
+    extra = os.environ.get("VVB_NVCC_EXTRA", "").split()
+    jobs = []
     for src in CUDA_SRCS:
         o = os.path.join(OBJ, os.path.basename(src) + ".o")
         if force or _stale(o, [src] + CUDA_DEPS + hdrs):
-            # VVB_NVCC_EXTRA: extra nvcc flags for A/B builds (e.g. "-DVVB_INV_BASETW=0")
-            extra = os.environ.get("VVB_NVCC_EXTRA", "").split()
-            _run([NVCC, *ARCH, "-std=c++17", "-O3", "-lineinfo", *extra, "-Xptxas", "-v" if verbose else "-warn-spills",
-                  "-Xcompiler", "-fPIC", "-I" + INC, "-c", src, "-o", o], verbose)
+            jobs.append([NVCC, *ARCH, "-std=c++17", "-O3", "-lineinfo", *extra, "-Xptxas", "-v" if verbose else "-warn-spills",
+                         "-Xcompiler", "-fPIC", "-I" + INC, "-c", src, "-o", o])
         objs.append(o)
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        workers = int(os.environ.get("VVB_BUILD_JOBS", str(min(len(jobs), os.cpu_count() or 4))))
+        with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+            list(pool.map(lambda c: _run(c, verbose), jobs))
     if force or _stale(LIB, objs):
         _run([NVCC, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *objs, "-lm"], verbose)
     return LIB

@@ -7,14 +7,10 @@
  * 4 (VV_DSP_ERROR_INTERNAL) and the host library fails loudly.
  * (-DVVB_EMU is the test-only emulator build under tests/emu/, see cuda_emu.h.)
  */
+#include "vvb_rt.cuh"
 #include "vvb_direct_kernels.cuh"
-#include "../../../include/vvb200_cuda.h"
 
-#include <atomic>
 #include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
 #include <new>
 #include <vector>
 
@@ -22,16 +18,17 @@ using namespace vvb;
 
 /* ------------------------------------------------------------------ error plumbing */
 static thread_local char g_err[512] = "";
-static std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> vvb::g_launches{0};
 
 extern "C" const char* vvb_last_error(void) { return g_err; }
 extern "C" unsigned long long vvb_kernel_launches(void) { return g_launches.load(); }
 
-static int fail(int code, const char* what, const char* detail)
+int vvb::rt_fail(int code, const char* what, const char* detail)
 {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, detail ? detail : "");
     return code;
 }
+static int fail(int code, const char* what, const char* detail) { return rt_fail(code, what, detail); }
 
 #ifdef VVB_EMU
 /* ---- emulator runtime: host memory stands in for HBM, streams are no-ops */
@@ -41,8 +38,7 @@ uint3_emu g_threadIdx, g_blockIdx;
 dim3 g_blockDim, g_gridDim;
 char* g_dyn_smem = nullptr;
 }
-#define CK(expr) do { if ((expr) != 0) return fail(4, #expr, "emu"); } while (0)
-static int rt_num_sms() { return 3; }
+int vvb::rt_num_sms() { return 3; }
 extern "C" int vvb_device_ready(void) { return 0; }
 extern "C" int vvb_malloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : fail(4, "malloc", "oom"); }
 extern "C" int vvb_free(void* p) { free(p); return 0; }
@@ -65,13 +61,9 @@ extern "C" int vvb_event_create(void** e) { *e = malloc(1); return 0; }
 extern "C" int vvb_event_destroy(void* e) { free(e); return 0; }
 extern "C" int vvb_event_record(void*, void*) { return 0; }
 extern "C" int vvb_stream_wait_event(void*, void*) { return 0; }
-#define VVB_LAUNCH(kern, grid, block, smem, stream, ...) \
-    do { g_launches++; vvb_emu::launch(dim3(grid), dim3(block), smem, [&] { kern(__VA_ARGS__); }); } while (0)
-template <class K> static int rt_blocks_per_sm(K, int, size_t) { return 1; }
 #else
 /* ---- CUDA runtime */
-#define CK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(4, #expr, cudaGetErrorString(e_)); } while (0)
-static int rt_num_sms()
+int vvb::rt_num_sms()
 {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -111,25 +103,6 @@ extern "C" int vvb_event_create(void** e) { cudaEvent_t ev; CK(cudaEventCreateWi
 extern "C" int vvb_event_destroy(void* e) { if (e) CK(cudaEventDestroy((cudaEvent_t)e)); return 0; }
 extern "C" int vvb_event_record(void* e, void* s) { CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s)); return 0; }
 extern "C" int vvb_stream_wait_event(void* s, void* e) { CK(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0)); return 0; }
-#define VVB_LAUNCH(kern, grid, block, smem, stream, ...) \
-    do { g_launches++; kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); CK(cudaGetLastError()); } while (0)
-/* opt in to the dynamic shared memory the kernel needs and ask how many CTAs fit per SM */
-template <class K> static int rt_blocks_per_sm(K kern, int threads, size_t smem)
-{
-    cudaError_t e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int nb = 0;
-    cudaError_t e2 = (e1 == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) : e1;
-    if (e2 != cudaSuccess || nb == 0) {
-        cudaFuncAttributes fa;
-        memset(&fa, 0, sizeof(fa));
-        cudaFuncGetAttributes(&fa, kern);
-        fprintf(stderr, "vvb: kernel does not fit: %s (threads %d, dyn smem %zu, regs %d, static smem %zu, maxThreadsPerBlock %d)\n",
-                cudaGetErrorString(e2), threads, smem, fa.numRegs, fa.sharedSizeBytes, fa.maxThreadsPerBlock);
-        cudaGetLastError();
-        return 0;
-    }
-    return nb;
-}
 #endif
 
 /* -------------------------------------------------------------------- plan tables */
@@ -179,22 +152,24 @@ template <class C> static void build_tables(std::vector<float>& blob, const floa
     }
 }
 
-/* the kernel configurations: M complex points = fft_size/2 for the real transforms */
-using Cfg128 = Cfg<128, 16, 16, 8>;
-using Cfg256 = Cfg<256, 16, 16, 16>;
-using Cfg256m = Cfg<256, 8, 8, 8, 4>;       /* T = 32: whole-warp team for the marching ISTFT (own table blob) */
-using Cfg512 = Cfg<512, 32, 32, 16>;
-using Cfg512m = Cfg<512, 16, 16, 16, 2>;    /* T = 32 */
-using Cfg1024 = Cfg<1024, 32, 32, 32>;
-using Cfg2048 = Cfg<2048, 32, 32, 8, 8>;      /* T = 64 (two warps per frame), E = 32 */
-using Cfg4096 = Cfg<4096, 32, 32, 16, 8>;     /* T = 128, E = 32 */
-template <class C> struct Teams { static constexpr int G = (C::T >= 256) ? 2 : 256 / C::T; };
-
-template <class C> static constexpr size_t smem_fwd() { return sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3 + C::POST + 1) + 2 * Teams<C>::G * C::XBUF); }
-template <class C> static size_t smem_inv(int hop, bool ola) { return smem_fwd<C>() + (ola ? sizeof(float) * 2 * (2 * C::M - hop) : 0); }
-template <class C> static constexpr size_t smem_c2c() { return sizeof(float) * (2 * (C::TW2 + C::TW3) + 2 * Teams<C>::G * C::XBUF); }
-
 static bool fast_size(size_t m) { return m == 128 || m == 256 || m == 512 || m == 1024 || m == 2048 || m == 4096; }
+/* plan-API C2C (and the chirp-z transform built on it) also has a 256-thread, three-pass 8192-point kernel */
+static bool fast_c2c_size(size_t n) { return fast_size(n) || n == 8192; }
+static void build_c2c_tables(size_t n, std::vector<float>& blob);
+
+/* twiddle tables of the n-point complex plan (no window) */
+static void build_c2c_tables(size_t n, std::vector<float>& blob)
+{
+    switch (n) {
+    case 128: build_tables<Cfg128>(blob, nullptr); break;
+    case 256: build_tables<Cfg256>(blob, nullptr); break;
+    case 512: build_tables<Cfg512>(blob, nullptr); break;
+    case 1024: build_tables<Cfg1024>(blob, nullptr); break;
+    case 2048: build_tables<Cfg2048>(blob, nullptr); break;
+    case 4096: build_tables<Cfg4096>(blob, nullptr); break;
+    default: build_tables<Cfg8192>(blob, nullptr); break;
+    }
+}
 
 /* Bluestein plan for a size without a Stockham kernel (see vvb_direct_kernels.cuh): chirp table, spectrum of the
  * wrapped conjugate chirp, two power-of-two C2C engines and a work buffer grown on demand. */
@@ -210,7 +185,7 @@ struct Chirp {
     float2* d_work = nullptr;
     size_t work_elems = 0;
 };
-static bool chirp_size(size_t n) { return n >= 32 && n <= 2048 && getenv("VVB_NO_BLUESTEIN") == nullptr; }
+static bool chirp_size(size_t n) { return n >= 32 && n <= 4096 && getenv("VVB_NO_BLUESTEIN") == nullptr; }   /* M = pow2 >= 2n-1 <= 8192 */
 static void chirp_destroy(Chirp* c);
 static int chirp_create(size_t n, Chirp** out);
 static int chirp_reserve(Chirp* c, size_t transforms, size_t* chunk);
@@ -306,85 +281,6 @@ extern "C" void vvb_engine_destroy(vvb_engine* e)
 
 extern "C" int vvb_engine_is_fast(const vvb_engine* e) { return e && e->fast; }
 
-static int persistent_grid(long long work, int per_sm, int sms)
-{
-    long long cap = (long long)(per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
-    long long g = work < cap ? work : cap;
-    return (int)(g < 1 ? 1 : g);
-}
-
-/* ------------------------------------------------------------------ forward launch */
-template <class C, int OUT> static int launch_forward_t(vvb_engine* e, FwdArgs a, void* stream)
-{
-    constexpr int G = Teams<C>::G;
-    a.groups_per_signal = (a.frames + G - 1) / G;
-    static int per_sm = -1;
-    auto kern = stft_forward_kernel<C, G, OUT>;
-    const size_t smem = smem_fwd<C>();
-    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
-    if (per_sm == 0) return fail(4, "stft_forward_kernel", "does not fit on this device");
-    const long long groups = (long long)a.groups_per_signal * (long long)(a.num_groups);   /* num_groups carries batch here */
-    if (groups > 0x7fffffffLL) return fail(2, "vvb_stft_forward", "batch*frames too large for one launch");
-    a.num_groups = (int)groups;
-    if (groups == 0) return 0;
-    VVB_LAUNCH(kern, persistent_grid(groups, per_sm, e->sms), C::T * G, smem, stream, a);
-    return 0;
-}
-template <class C> static int launch_forward(vvb_engine* e, const FwdArgs& a, int kind, void* stream)
-{
-    switch (kind) {
-    case OUT_COMPLEX: return launch_forward_t<C, OUT_COMPLEX>(e, a, stream);
-    case OUT_POWER: return launch_forward_t<C, OUT_POWER>(e, a, stream);
-    case OUT_MAGNITUDE: return launch_forward_t<C, OUT_MAGNITUDE>(e, a, stream);
-    default: return fail(3, "vvb_stft_forward", "bad out_kind");
-    }
-}
-
-/* team-marching kernels (whole-warp teams: fft_size 2048 / 4096 / 8192, hop = 2*T*S dividing fft_size).
- * G teams per CTA and CTAs per SM chosen per configuration: registers are partitioned per SM sub-partition
- * (16 K each), so 8 warps per SM may use 255 registers per thread but 9..12 warps cap at 168. */
-template <class C> struct March;
-template <> struct March<Cfg256m> { static constexpr int G = 8, MINB = 3; };    /* 256 thr, <= 80 regs */
-template <> struct March<Cfg512m> { static constexpr int G = 8, MINB = 2; };    /* 256 thr, <= 128 regs */
-template <> struct March<Cfg1024> { static constexpr int G = 8, MINB = 1; };   /* 256 thr, 232 regs, 1 CTA/SM */
-template <> struct March<Cfg2048> { static constexpr int G = 4, MINB = 1; };   /* 256 thr, 1 CTA/SM, up to 255 regs */
-template <> struct March<Cfg4096> { static constexpr int G = 2, MINB = 1; };   /* 256 thr, 1 CTA/SM, up to 255 regs */
-
-template <class C, int S, int OUT> static int launch_fwd_march_t(vvb_engine* e, FwdArgs a, void* stream)
-{
-    constexpr int G = March<C>::G, MINB = March<C>::MINB;
-    static int per_sm = -1;
-    auto kern = stft_march_kernel<C, S, G, MINB, OUT>;
-    const size_t smem = sizeof(float) * 2 * (C::TW2 + C::TW3 + C::POST + 1 + G * C::XBUF + G * (C::E / S + 1) * C::T * S) + 8 * G;
-    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
-    if (per_sm == 0) return fail(4, "stft_march_kernel", "does not fit on this device");
-    const long long total = (long long)a.num_groups * a.frames;  /* num_groups carries the batch */
-    const long long want = (total + 16 * G - 1) / (16 * G);      /* at least ~16 frames per team */
-    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), C::T * G, smem, stream, a);
-    return 0;
-}
-template <class C, int S> static int launch_fwd_march_s(vvb_engine* e, const FwdArgs& a, int kind, void* stream)
-{
-    switch (kind) {
-    case OUT_COMPLEX: return launch_fwd_march_t<C, S, OUT_COMPLEX>(e, a, stream);
-    case OUT_POWER: return launch_fwd_march_t<C, S, OUT_POWER>(e, a, stream);
-    case OUT_MAGNITUDE: return launch_fwd_march_t<C, S, OUT_MAGNITUDE>(e, a, stream);
-    default: return fail(3, "vvb_stft_forward", "bad out_kind");
-    }
-}
-/* returns -1 when this (fft_size, hop) has no marching kernel */
-template <class C> static int launch_fwd_march(vvb_engine* e, const FwdArgs& a, int kind, void* stream)
-{
-    const size_t unit = 2 * (size_t)C::T;                        /* samples per register slot of a team */
-    if (e->hop % unit) return -1;
-    switch (e->hop / unit) {
-    case C::E / 8: return launch_fwd_march_s<C, C::E / 8>(e, a, kind, stream);
-    case C::E / 4: return launch_fwd_march_s<C, C::E / 4>(e, a, kind, stream);
-    case C::E / 2: return launch_fwd_march_s<C, C::E / 2>(e, a, kind, stream);
-    default: return -1;
-    }
-}
-
 extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, size_t n, size_t x_pitch, size_t frames,
                                 int pad_mode, int out_kind, void* d_out, size_t out_pitch, void* stream)
 {
@@ -401,19 +297,12 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
         if (!getenv("VVB_NO_MARCH")) {           /* zero padding and centred reflect padding both */
             int r = -1;
             /* (at fft_size 512 / 1024 the 2-pass generic forward kernel is faster than a 3-pass marching one) */
-            if (e->nfft == 2048) r = launch_fwd_march<Cfg1024>(e, a, out_kind, stream);
-            else if (e->nfft == 4096) r = launch_fwd_march<Cfg2048>(e, a, out_kind, stream);
-            else if (e->nfft == 8192) r = launch_fwd_march<Cfg4096>(e, a, out_kind, stream);
+            if (e->nfft == 2048) r = tu_fwd_march_2048(e->hop, a, out_kind, e->sms, stream);
+            else if (e->nfft == 4096) r = tu_fwd_march_4096(e->hop, a, out_kind, e->sms, stream);
+            else if (e->nfft == 8192) r = tu_fwd_march_8192(e->hop, a, out_kind, e->sms, stream);
             if (r >= 0) return r;
         }
-        switch (e->nfft / 2) {
-        case 128: return launch_forward<Cfg128>(e, a, out_kind, stream);
-        case 256: return launch_forward<Cfg256>(e, a, out_kind, stream);
-        case 512: return launch_forward<Cfg512>(e, a, out_kind, stream);
-        case 1024: return launch_forward<Cfg1024>(e, a, out_kind, stream);
-        case 2048: return launch_forward<Cfg2048>(e, a, out_kind, stream);
-        default: return launch_forward<Cfg4096>(e, a, out_kind, stream);
-        }
+        return tu_fwd_generic((int)(e->nfft / 2), a, out_kind, e->sms, stream);
     }
     if (e->chirp && e->chirp->fused) {
         ChirpFusedArgs a;
@@ -452,122 +341,6 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
 }
 
 /* ------------------------------------------------------------------ inverse launch */
-template <class C, bool OLA> static int launch_inverse_t(vvb_engine* e, InvArgs a, long long batch, void* stream)
-{
-    constexpr int G = Teams<C>::G;
-    static int per_sm_cache[2] = {-1, -1};
-    static size_t smem_cache = 0;
-    auto kern = stft_inverse_kernel<C, G, OLA>;
-    const size_t smem = smem_inv<C>(a.hop, OLA);
-    int& per_sm = per_sm_cache[0];
-    if (per_sm < 0 || smem != smem_cache) { per_sm = rt_blocks_per_sm(kern, C::T * G, smem); smem_cache = smem; }
-    if (per_sm == 0) return fail(4, "stft_inverse_kernel", "does not fit on this device");
-    long long items;
-    if (OLA) {
-        /* split every signal into chunks of frames so the persistent grid has >= ~4 items per CTA;
-         * each chunk re-synthesises up to K-1 halo frames, so chunks are kept long (>= 16 rounds) */
-        const long long cap = (long long)per_sm * e->sms;
-        long long want = (4 * cap + batch - 1) / batch;                 /* chunks per signal wanted */
-        long long max_chunks = a.frames / (16 * G);
-        if (max_chunks < 1) max_chunks = 1;
-        if (want > max_chunks) want = max_chunks;
-        if (want < 1) want = 1;
-        long long cf = (a.frames + want - 1) / want;
-        cf = (cf + G - 1) / G * G;                                      /* whole rounds */
-        a.chunk_frames = (int)cf;
-        a.chunks_per_signal = (int)((a.frames + cf - 1) / cf);
-        items = batch * a.chunks_per_signal;
-    } else {
-        items = (a.frames + G - 1) / G;
-    }
-    if (items > 0x7fffffffLL) return fail(2, "vvb_stft_inverse", "too many work items");
-    a.num_items = (int)items;
-    if (items == 0) return 0;
-    VVB_LAUNCH(kern, persistent_grid(items, per_sm, e->sms), C::T * G, smem, stream, a);
-    return 0;
-}
-
-template <bool OLA> static int dispatch_inverse(vvb_engine* e, const InvArgs& a, long long batch, void* stream)
-{
-    switch (e->nfft / 2) {
-    case 128: return launch_inverse_t<Cfg128, OLA>(e, a, batch, stream);
-    case 256: return launch_inverse_t<Cfg256, OLA>(e, a, batch, stream);
-    case 512: return launch_inverse_t<Cfg512, OLA>(e, a, batch, stream);
-    case 1024: return launch_inverse_t<Cfg1024, OLA>(e, a, batch, stream);
-    case 2048: return launch_inverse_t<Cfg2048, OLA>(e, a, batch, stream);
-    default: return launch_inverse_t<Cfg4096, OLA>(e, a, batch, stream);
-    }
-}
-
-/* team-marching ISTFT: register-resident overlap-add (see istft_march_kernel) */
-template <class C> struct MarchInv : March<C> {};
-#ifdef VVB_INV_G12
-template <> struct MarchInv<Cfg1024> { static constexpr int G = 12, MINB = 1; };
-#endif
-template <class C, int S> static int launch_inv_march_s(vvb_engine* e, InvArgs a, long long batch, void* stream)
-{
-    constexpr int G = MarchInv<C>::G, MINB = MarchInv<C>::MINB;
-    static int per_sm = -1;
-    auto kern = istft_march_kernel<C, S, G, MINB>;
-    const size_t smem = sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3) + 2 * G * (C::XBUF + C::M + 2)) + 8 * G;
-    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
-    if (per_sm == 0) return fail(4, "istft_march_kernel", "does not fit on this device");
-    if (batch > 0x7fffffffLL) return fail(2, "vvb_stft_inverse", "batch");
-    a.num_items = (int)batch;                                   /* the kernel partitions batch*frames itself */
-    const long long total = batch * a.frames;
-    const long long want = (total + 16 * G - 1) / (16 * G);
-    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), C::T * G, smem, stream, a);
-    return 0;
-}
-template <class C> static int launch_inv_march(vvb_engine* e, const InvArgs& a, long long batch, void* stream)
-{
-    const size_t unit = 2 * (size_t)C::T;
-    if (e->hop % unit) return -1;
-    switch (e->hop / unit) {
-    case C::E / 8: return launch_inv_march_s<C, C::E / 8>(e, a, batch, stream);
-    case C::E / 4: return launch_inv_march_s<C, C::E / 4>(e, a, batch, stream);
-    case C::E / 2: return launch_inv_march_s<C, C::E / 2>(e, a, batch, stream);
-    default: return -1;
-    }
-}
-
-/* two frames per complex transform (fft_size 256 / 512 / 1024): C = one-warp plan with M = fft_size, CO = the real plan
- * whose window tables are reused */
-template <class C> struct PairCfg;
-template <> struct PairCfg<Cfg256m> { static constexpr int G = 8, MINB = 3; };
-template <> struct PairCfg<Cfg512m> { static constexpr int G = 8, MINB = 2; };
-template <> struct PairCfg<Cfg1024> { static constexpr int G = 8, MINB = 1; };
-template <class C, class CO, int HS> static int launch_inv_pair_s(vvb_engine* e, const InvArgs& ia, long long batch, void* stream)
-{
-    constexpr int G = PairCfg<C>::G, MINB = PairCfg<C>::MINB;
-    static int per_sm = -1;
-    auto kern = istft_pair_kernel<C, HS, G, MINB>;
-    const size_t smem = sizeof(float) * 2 * (C::TW2 + C::TW3 + G * C::XBUF);
-    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, 32 * G, smem);
-    if (per_sm == 0) return fail(4, "istft_pair_kernel", "does not fit on this device");
-    if (batch > 0x7fffffffLL) return fail(2, "vvb_stft_inverse", "batch");
-    PairArgs a;
-    a.spec = ia.spec; a.spec_pitch = ia.spec_pitch; a.frames = ia.frames; a.num_items = (int)batch;
-    a.y = ia.y; a.y_pitch = ia.y_pitch; a.n_out = ia.n_out; a.inv_norm = ia.inv_norm;
-    a.tables = e->d_tables_p;
-    a.wsyn = e->d_tables + (ia.inv_norm ? Tables<CO>::WSYN_NORM : Tables<CO>::WSYN);
-    a.midnorm = e->d_tables + Tables<CO>::MIDNORM;
-    const long long total = batch * ((ia.frames + 1) / 2);
-    const long long want = (total + 8 * G - 1) / (8 * G);
-    VVB_LAUNCH(kern, persistent_grid(want, per_sm, e->sms), 32 * G, smem, stream, a);
-    return 0;
-}
-template <class C, class CO> static int launch_inv_pair(vvb_engine* e, const InvArgs& a, long long batch, void* stream)
-{
-    if (e->hop % 32) return -1;
-    switch (e->hop / 32) {
-    case C::E / 8: return launch_inv_pair_s<C, CO, C::E / 8>(e, a, batch, stream);
-    case C::E / 4: return launch_inv_pair_s<C, CO, C::E / 4>(e, a, batch, stream);
-    case C::E / 2: return launch_inv_pair_s<C, CO, C::E / 2>(e, a, batch, stream);
-    default: return -1;
-    }
-}
-
 static int ensure_scratch(vvb_engine* e, size_t bytes)
 {
     if (e->scratch_bytes >= bytes) return 0;
@@ -613,7 +386,7 @@ extern "C" int vvb_stft_inverse_frames(vvb_engine* e, const vvb_cpx* d_spec, siz
         memset(&a, 0, sizeof(a));
         a.spec = reinterpret_cast<const float2*>(d_spec); a.spec_pitch = (long long)spec_pitch;
         a.frames = (int)count; a.hop = (int)e->hop; a.y = d_frames; a.tables = e->d_tables;
-        return dispatch_inverse<false>(e, a, 1, stream);
+        return tu_inv_generic((int)(e->nfft / 2), false, a, 1, e->sms, stream);
     }
     if (e->chirp) return chirp_inverse_frames(e, reinterpret_cast<const float2*>(d_spec), count, spec_pitch, d_frames, e->d_win, stream);
     DirInvArgs a;
@@ -643,10 +416,7 @@ extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t bat
         a.y = d_y; a.y_pitch = (long long)y_pitch; a.n_out = (long long)n_out;
         a.inv_norm = d_inv_norm; a.tables = e->d_tables;
         if (e->d_tables_p && !getenv("VVB_NO_PAIR") && !getenv("VVB_NO_MARCH")) {
-            int r = -1;
-            if (e->nfft == 256) r = launch_inv_pair<Cfg256m, Cfg128>(e, a, (long long)batch, stream);
-            else if (e->nfft == 512) r = launch_inv_pair<Cfg512m, Cfg256>(e, a, (long long)batch, stream);
-            else if (e->nfft == 1024) r = launch_inv_pair<Cfg1024, Cfg512>(e, a, (long long)batch, stream);
+            const int r = tu_inv_pair((int)e->nfft, e->hop, a, (long long)batch, e->sms, e->d_tables_p, e->d_tables, stream);
             if (r >= 0) return r;
         }
         const bool y_aligned = ((uintptr_t)d_y % 8 == 0) && (y_pitch % 2 == 0);   /* 64-bit stores */
@@ -654,14 +424,16 @@ extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t bat
             int r = -1;
             InvArgs am = a;
             am.tables = e->d_tables_m;
-            if (e->nfft == 512) r = launch_inv_march<Cfg256m>(e, am, (long long)batch, stream);
-            else if (e->nfft == 1024) r = launch_inv_march<Cfg512m>(e, am, (long long)batch, stream);
-            else if (e->nfft == 2048) r = launch_inv_march<Cfg1024>(e, a, (long long)batch, stream);
-            else if (e->nfft == 4096) r = launch_inv_march<Cfg2048>(e, a, (long long)batch, stream);
-            else if (e->nfft == 8192) r = launch_inv_march<Cfg4096>(e, a, (long long)batch, stream);
+            if (e->nfft == 512 || e->nfft == 1024) r = tu_inv_march_small((int)e->nfft, e->hop, am, (long long)batch, e->sms, stream);
+            else if (e->nfft == 2048) {
+                if (!getenv("VVB_NO_WS")) r = tu_inv_ws_2048(e->hop, a, (long long)batch, e->sms, stream);
+                if (r < 0) r = tu_inv_march_2048(e->hop, a, (long long)batch, e->sms, stream);
+            }
+            else if (e->nfft == 4096) r = tu_inv_march_4096(e->hop, a, (long long)batch, e->sms, stream);
+            else if (e->nfft == 8192) r = tu_inv_march_8192(e->hop, a, (long long)batch, e->sms, stream);
             if (r >= 0) return r;
         }
-        return dispatch_inverse<true>(e, a, (long long)batch, stream);
+        return tu_inv_generic((int)(e->nfft / 2), true, a, (long long)batch, e->sms, stream);
     }
     /* direct path: synthesis frames to HBM scratch, then the stand-alone overlap-add kernel */
     const size_t count = batch * frames;
@@ -708,17 +480,10 @@ extern "C" int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine
     e->n = n; e->type = type; e->dir = dir; e->sms = rt_num_sms();
     int st = 0;
     if (type == 0) {
-        e->fast_c2c = fast_size(n);
+        e->fast_c2c = fast_c2c_size(n);
         std::vector<float> blob;
         if (e->fast_c2c) {
-            switch (n) {
-            case 128: build_tables<Cfg128>(blob, nullptr); break;
-            case 256: build_tables<Cfg256>(blob, nullptr); break;
-            case 512: build_tables<Cfg512>(blob, nullptr); break;
-            case 1024: build_tables<Cfg1024>(blob, nullptr); break;
-            case 2048: build_tables<Cfg2048>(blob, nullptr); break;
-            default: build_tables<Cfg4096>(blob, nullptr); break;
-            }
+            build_c2c_tables(n, blob);
             st = upload(&e->d_tables, blob);
         } else {
             make_wtab(blob, n);
@@ -742,19 +507,6 @@ extern "C" void vvb_fft_engine_destroy(vvb_fft_engine* e)
     delete e;
 }
 
-template <class C> static int launch_c2c(vvb_fft_engine* e, C2CArgs a, void* stream)
-{
-    constexpr int G = Teams<C>::G;
-    static int per_sm = -1;
-    auto kern = fft_c2c_kernel<C, G>;
-    const size_t smem = smem_c2c<C>();
-    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
-    if (per_sm == 0) return fail(4, "fft_c2c_kernel", "does not fit on this device");
-    const long long groups = (a.batch + G - 1) / G;
-    VVB_LAUNCH(kern, persistent_grid(groups, per_sm, e->sms), C::T * G, smem, stream, a);
-    return 0;
-}
-
 extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, size_t batch, void* stream)
 {
     if (!e || !d_in || !d_out) return fail(1, "vvb_fft_exec", "null");
@@ -764,14 +516,7 @@ extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, si
         if (e->fast_c2c) {
             C2CArgs a;
             a.in = (const float2*)d_in; a.out = (float2*)d_out; a.batch = (int)batch; a.inverse = e->dir < 0; a.tables = e->d_tables;
-            switch (e->n) {
-            case 128: return launch_c2c<Cfg128>(e, a, stream);
-            case 256: return launch_c2c<Cfg256>(e, a, stream);
-            case 512: return launch_c2c<Cfg512>(e, a, stream);
-            case 1024: return launch_c2c<Cfg1024>(e, a, stream);
-            case 2048: return launch_c2c<Cfg2048>(e, a, stream);
-            default: return launch_c2c<Cfg4096>(e, a, stream);
-            }
+            return tu_c2c((int)e->n, a, e->sms, stream);
         }
         if (e->chirp && e->chirp->fused) {      /* in place is fine: a team reads its whole transform before it writes */
             ChirpFusedArgs a;
@@ -853,14 +598,7 @@ static int chirp_create(size_t n, Chirp** out)
         std::vector<float> bm(bspec), blob;
         for (auto& v : bm) v = (float)((double)v / (double)M);
         st = upload((float**)&c->d_bspec_m, bm);
-        switch (M) {
-        case 128: build_tables<Cfg128>(blob, nullptr); break;
-        case 256: build_tables<Cfg256>(blob, nullptr); break;
-        case 512: build_tables<Cfg512>(blob, nullptr); break;
-        case 1024: build_tables<Cfg1024>(blob, nullptr); break;
-        case 2048: build_tables<Cfg2048>(blob, nullptr); break;
-        default: build_tables<Cfg4096>(blob, nullptr); break;
-        }
+        build_c2c_tables(M, blob);
         if (!st) st = upload(&c->d_tables, blob);
     }
     if (!st) st = vvb_fft_engine_create(M, 0, +1, &c->fwd);
@@ -894,35 +632,10 @@ static int chirp_convolve(Chirp* c, size_t count, void* stream)
     return vvb_fft_exec(c->bwd, c->d_work, c->d_work, count, stream);
 }
 
-template <class C, int MODE> static int launch_chirp_fused_m(const ChirpFusedArgs& a, int sms, void* stream)
-{
-    constexpr int G = Teams<C>::G;
-    static int per_sm = -1;
-    auto kern = chirp_fused_kernel<C, G, MODE>;
-    const size_t smem = smem_c2c<C>();
-    if (per_sm < 0) per_sm = rt_blocks_per_sm(kern, C::T * G, smem);
-    if (per_sm == 0) return fail(4, "chirp_fused_kernel", "does not fit on this device");
-    VVB_LAUNCH(kern, persistent_grid((a.count + G - 1) / G, per_sm, sms), C::T * G, smem, stream, a);
-    return 0;
-}
-template <class C> static int launch_chirp_fused(const ChirpFusedArgs& a, int sms, void* stream)
-{
-    if (a.mode == CHIRP_STFT_FWD) return launch_chirp_fused_m<C, CHIRP_STFT_FWD>(a, sms, stream);
-    if (a.mode == CHIRP_STFT_INV) return launch_chirp_fused_m<C, CHIRP_STFT_INV>(a, sms, stream);
-    return launch_chirp_fused_m<C, CHIRP_C2C>(a, sms, stream);
-}
-
 static int chirp_fused(Chirp* c, ChirpFusedArgs a, int sms, void* stream)
 {
     a.n = (int)c->n; a.chirp = c->d_chirp; a.bspec_over_m = c->d_bspec_m; a.tables = c->d_tables;
-    switch (c->M) {
-    case 128: return launch_chirp_fused<Cfg128>(a, sms, stream);
-    case 256: return launch_chirp_fused<Cfg256>(a, sms, stream);
-    case 512: return launch_chirp_fused<Cfg512>(a, sms, stream);
-    case 1024: return launch_chirp_fused<Cfg1024>(a, sms, stream);
-    case 2048: return launch_chirp_fused<Cfg2048>(a, sms, stream);
-    default: return launch_chirp_fused<Cfg4096>(a, sms, stream);
-    }
+    return tu_chirp_fused(c->M, a, sms, stream);
 }
 
 /* ---------------------------------------------------------------------- log-mel */
@@ -931,11 +644,8 @@ static int chirp_fused(Chirp* c, ChirpFusedArgs a, int sms, void* stream)
 #endif
 template <int R> static int launch_logmel_tma(const MelArgs& a, int grid, size_t smem, int stages, int stage_floats, int n_groups, void* stream)
 {
-    static size_t opted = 0;                               /* largest dynamic shared-memory size opted in to so far */
-    if (smem > opted) {
-        if (rt_blocks_per_sm(logmel_tma_kernel<R, VVB_MEL_FPT>, 256 * (2 / VVB_MEL_FPT), smem) == 0) return fail(4, "logmel_tma_kernel", "does not fit on this device");
-        opted = smem;
-    }
+    static OccCache occ;                                   /* per device and dynamic shared-memory size */
+    if (occ.get(logmel_tma_kernel<R, VVB_MEL_FPT>, 256 * (2 / VVB_MEL_FPT), smem) == 0) return fail(4, "logmel_tma_kernel", "does not fit on this device");
     VVB_LAUNCH((logmel_tma_kernel<R, VVB_MEL_FPT>), grid, 256 * (2 / VVB_MEL_FPT), smem, stream, a, stages, stage_floats, n_groups);
     return 0;
 }
@@ -976,9 +686,9 @@ extern "C" int vvb_logmel(const float* d_power, size_t frames, size_t bins, size
             }
         }
     }
-    static int per_sm = -1;
+    static OccCache occ;
     const size_t smem = sizeof(float) * MEL_KC * 33;
-    if (per_sm < 0) per_sm = rt_blocks_per_sm(logmel_kernel, 256, smem);
+    const int per_sm = occ.get(logmel_kernel, 256, smem);
     if (per_sm == 0) return fail(4, "logmel_kernel", "does not fit on this device");
     VVB_LAUNCH(logmel_kernel, persistent_grid((long long)((frames + 31) / 32), per_sm, rt_num_sms()), 256, smem, stream, a);
     return 0;
@@ -997,13 +707,9 @@ extern "C" int vvb_mfcc(const float* d_logmel, size_t frames, size_t n_mels, siz
     MfccArgs a;
     a.logmel = d_logmel; a.frames = (long long)frames; a.n_mels = (int)n_mels; a.n_coeffs = (int)n_coeffs;
     a.table = d_table; a.lifter = d_lifter; a.out = d_out;
-    static size_t opted = 0;
-    static int per_sm = 1;
-    if (smem > opted) {
-        per_sm = rt_blocks_per_sm(mfcc_kernel, 256, smem);
-        if (per_sm == 0) return fail(4, "mfcc_kernel", "does not fit on this device");
-        opted = smem;
-    }
+    static OccCache occ;
+    const int per_sm = occ.get(mfcc_kernel, 256, smem);
+    if (per_sm == 0) return fail(4, "mfcc_kernel", "does not fit on this device");
     VVB_LAUNCH(mfcc_kernel, persistent_grid((long long)((frames + 31) / 32), per_sm, rt_num_sms()), 256, smem, stream, a);
     return 0;
 }
@@ -1075,6 +781,44 @@ extern "C" int vvb_fp32_peak(int packed, double* tflops)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *tflops = best;
+    return 0;
+#endif
+}
+
+/* ---------------------------------------------------------------- SM clock probe */
+/* One warp spins for ~50 us and reports SM cycles per nanosecond of the global timer: the SM clock the GPU is
+ * ACTUALLY running at that moment (nvidia-smi samples every 100 ms and misses short excursions).  Diagnostics
+ * for bench.py / benchmarks: lets a measurement say which clock it was taken at. */
+__global__ void sm_clock_probe_kernel(double* out, long long spin_cycles)
+{
+#ifndef VVB_EMU
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    const long long c0 = clock64();
+    long long c1 = c0;
+    while (c1 - c0 < spin_cycles) c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if (threadIdx.x == 0) out[0] = (g1 > g0) ? (double)(c1 - c0) / (double)(g1 - g0) * 1000.0 : 0.0;
+#else
+    (void)spin_cycles; out[0] = 0.0;
+#endif
+}
+
+extern "C" int vvb_sm_clock_mhz(void* stream, double* mhz)
+{
+    if (!mhz) return fail(1, "vvb_sm_clock_mhz", "null");
+#ifdef VVB_EMU
+    (void)stream; *mhz = 0.0; return 0;
+#else
+    if (int st = vvb_device_ready()) return st;
+    static thread_local double* d_out = nullptr;
+    static thread_local double* h_out = nullptr;
+    if (!d_out) { CK(cudaMalloc(&d_out, sizeof(double))); CK(cudaMallocHost(&h_out, sizeof(double))); }
+    sm_clock_probe_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_out, 100000);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_out, d_out, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    *mhz = *h_out;
     return 0;
 #endif
 }

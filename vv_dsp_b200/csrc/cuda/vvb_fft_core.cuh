@@ -306,6 +306,12 @@ VVB_DEV void cp_async_commit()
     asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
 }
+VVB_DEV void cp_async_wait_group1()      /* all but the most recently committed group have landed */
+{
+#ifndef VVB_EMU
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
 VVB_DEV void cp_async_wait_all()
 {
 #ifndef VVB_EMU
@@ -315,10 +321,22 @@ VVB_DEV void cp_async_wait_all()
 
 /* ---- TMA 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) completing on an mbarrier.
  * src, dst and bytes must be multiples of 16.  Issued by ONE thread. */
+/* (emulator: the 8-byte barrier word holds {phase bit, expected arrivals, pending arrivals}; a TMA copy is a memcpy
+ * followed by the arrival that expect_tx stands for, and a wait yields to the other fibres until the phase flips) */
+#ifdef VVB_EMU
+struct EmuMbar { unsigned phase; unsigned short expected, pending; };
+static_assert(sizeof(EmuMbar) == 8, "mbarrier word");
+inline void emu_mbar_arrive(unsigned long long* bar)
+{
+    EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+    if (--b->pending == 0) { b->phase ^= 1u; b->pending = b->expected; }
+}
+#endif
 VVB_DEV void mbar_init(unsigned long long* bar, unsigned count)
 {
 #ifdef VVB_EMU
-    *bar = 0;
+    EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+    b->phase = 0; b->expected = (unsigned short)count; b->pending = (unsigned short)count;
 #else
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory");
@@ -330,12 +348,25 @@ VVB_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
 #ifndef VVB_EMU
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+#else
+    (void)bar; (void)bytes;                       /* the arrival is performed by bulk_load's completion */
+#endif
+}
+/* plain arrival (release semantics at CTA scope): signals "my earlier shared-memory writes / reads are done" */
+VVB_DEV void mbar_arrive(unsigned long long* bar)
+{
+#ifdef VVB_EMU
+    emu_mbar_arrive(bar);
+#else
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
 #endif
 }
 VVB_DEV void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar)
 {
 #ifdef VVB_EMU
     memcpy(smem_dst, gsrc, bytes);
+    emu_mbar_arrive(bar);
 #else
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
@@ -343,9 +374,17 @@ VVB_DEV void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigne
                  ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
 #endif
 }
+/* wait until the phase with the given parity has completed (a fresh barrier: parity 1 passes at once) */
 VVB_DEV void mbar_wait(unsigned long long* bar, unsigned parity)
 {
-#ifndef VVB_EMU
+#ifdef VVB_EMU
+    const EmuMbar* b = reinterpret_cast<const EmuMbar*>(bar);
+    long spins = 0;
+    while ((b->phase & 1u) == (parity & 1u)) {
+        if (++spins > 50000000L) { fprintf(stderr, "vvb_emu: mbarrier wait never completes (block %u)\n", blockIdx.x); abort(); }
+        emu_yield();
+    }
+#else
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

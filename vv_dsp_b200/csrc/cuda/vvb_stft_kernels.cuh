@@ -35,6 +35,10 @@
 #ifndef VVB_INV_BASETW
 #define VVB_INV_BASETW 1              /* marching ISTFT, 32 x 32: 5 twiddle bases from shared memory + computed powers */
 #endif
+#ifndef VVB_INV_PAIRMERGE
+#define VVB_INV_PAIRMERGE 0           /* marching ISTFT, 32 x 32: merge bins k and M-k together (0 = every thread merges all its bins alone,
+                                         1 = partner values through warp shuffles, 2 = through the exchange buffer) */
+#endif
 #ifndef VVB_FWD_TABLE_TWIDDLES
 #define VVB_FWD_TABLE_TWIDDLES 0      /* 1: the generic forward kernel loads twiddles / window from shared memory (A/B builds) */
 #endif
@@ -798,6 +802,86 @@ template <class C, int... Rs> VVB_DEV void march_merge(float2 (&v)[C::E], const 
     (march_merge_one<C, Rs>(v, st, t, hw_t), ...);
 }
 
+/* ---- the same merge with every pair (k, M-k) formed ONCE (one-warp 32 x 32 transforms).
+ * Lane t owns column t of the first pass: bins k = t + 32 R in slot R.  The partner bin M - k = (32 - t) + 32 (31 - R)
+ * lives in lane 32 - t, slot 31 - R, so lane t forms Z[k] AND Z[M-k] for its lower slots R < 16 from one load of
+ * (X[k], X[M-k]) and one shared sum / difference / twiddle product (8 packed instructions per pair instead of 2 x 7,
+ * 32 staged loads per frame instead of 64), keeps Z[k] and hands Z[M-k] to lane 32 - t, which files it in slot 31 - R.
+ * Lane 16 is its own partner (the shuffle returns its own value); lane 0 owns the self-paired column 0, whose partner
+ * of slot R is slot 32 - R: it takes its own values one slot further up, and slot 16 (k = M/2) is conj X[M/2].
+ * MODE 1 moves the partner values with SHFL, MODE 2 through the team's exchange buffer at their natural position. */
+/* streaming 8-byte load of a spectrum bin straight from global memory (read once, not worth a place in L1) */
+VVB_DEV float2 load_bin_global(const float2* p)
+{
+#ifdef VVB_EMU
+    return *p;
+#else
+    return __ldcs(p);
+#endif
+}
+/* phase 1 of a pair: the two loads (GLOBAL: from the spectrum row in HBM / L2; otherwise from the staged copy) */
+template <class C, int R, bool GLOBAL> VVB_DEV void march_pair_load(float2 (&x)[C::E / 2], float2 (&y)[C::E / 2], const float2* st, int t)
+{
+    constexpr int M = C::M, T = C::T;
+    if constexpr (GLOBAL) { x[R] = load_bin_global(st + t + T * R); y[R] = load_bin_global(st + M - t - T * R); }
+    else { x[R] = st[t + T * R]; y[R] = st[M - t - T * R]; }
+}
+template <class C, int R> VVB_DEV void march_merge_pair_math(float2 (&v)[C::E], float2 (&zp)[C::E / 2], float2 x, float2 y, int t, float2 hw_t)
+{
+    if constexpr (R == 0) {
+        if (t == 0) { x.y = 0.f; y.y = 0.f; }                          /* Re(IDFT): DC / Nyquist imag drop out */
+    }
+    constexpr float cr = TwC<2 * C::E, R>::c, sr = TwC<2 * C::E, R>::s;
+    const float2 h = cmul(hw_t, make_float2(cr, sr));                 /* (cos, sin)(2 pi k/N)/2 */
+    const float2 sm = __fadd2_rn(x, make_float2(y.x, -y.y));          /* x + conj(y) */
+    const float2 df = __fadd2_rn(x, make_float2(-y.x, y.y));          /* x - conj(y) */
+    const float2 u = cmul(df, make_float2(-h.y, h.x));                /* (j/2) conj(W_N^k) * df */
+    v[R] = __ffma2_rn(splat(0.5f), make_float2(sm.y, sm.x), make_float2(u.y, u.x));                  /* Z[k]   as (Im, Re) */
+    zp[R] = __ffma2_rn(make_float2(-0.5f, 0.5f), make_float2(sm.y, sm.x), make_float2(u.y, -u.x));   /* Z[M-k] = conj(sm/2 - u) as (Im, Re) */
+}
+template <class C, bool GLOBAL, int... Rs> VVB_DEV void march_merge_pairs_compute(float2 (&v)[C::E], float2 (&zp)[C::E / 2], const float2* st, int t, float2 hw_t, iseq<Rs...>)
+{
+    float2 x[C::E / 2], y[C::E / 2];
+    (march_pair_load<C, Rs, GLOBAL>(x, y, st, t), ...);               /* all loads in flight before the first use */
+    (march_merge_pair_math<C, Rs>(v, zp, x[Rs], y[Rs], t, hw_t), ...);
+}
+template <class C, int MODE, bool GLOBAL = false> VVB_DEV void march_merge_pairs(float2 (&v)[C::E], const float2* st, float2* xb, int t, float2 hw_t)
+{
+    static_assert(C::T == 32 && C::E == 32, "one-warp 32 x 32 transforms");
+    constexpr int M = C::M, H = C::E / 2;
+    float2 zp[H];
+    const float2 nyq = GLOBAL ? load_bin_global(st + M / 2) : st[M / 2];   /* k = M/2 (lane 0, slot 16): Z = conj X[M/2] */
+    march_merge_pairs_compute<C, GLOBAL>(v, zp, st, t, hw_t, typename make_iseq<H>::type{});
+    if constexpr (MODE == 1) {
+        const int src = (32 - t) & 31;
+        float2 rc[H];
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+            rc[r].x = __shfl_sync(0xffffffffu, zp[r].x, src);
+            rc[r].y = __shfl_sync(0xffffffffu, zp[r].y, src);
+        }
+        const bool col0 = (t == 0);
+#pragma unroll
+        for (int r = 0; r < H - 1; ++r) {                              /* slot 31 - r <- partner's pair r (lane 0: its own pair r + 1) */
+            v[31 - r].x = col0 ? rc[r + 1].x : rc[r].x;
+            v[31 - r].y = col0 ? rc[r + 1].y : rc[r].y;
+        }
+        v[H].x = col0 ? -nyq.y : rc[H - 1].x;
+        v[H].y = col0 ? nyq.x : rc[H - 1].y;
+    } else {
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+            const int p = (M - t - 32 * r) & (M - 1);                  /* natural position of Z[M-k]; k = 0 has no partner slot */
+            if (r > 0 || t > 0) xb[C::pad(p)] = zp[r];
+        }
+        if (t == 0) xb[C::pad(M / 2)] = make_float2(-nyq.y, nyq.x);
+        __syncwarp();
+#pragma unroll
+        for (int r = H; r < 2 * H; ++r) v[r] = xb[C::pad(t + 32 * r)];
+        __syncwarp();                                                  /* all partner values read before pass 1 overwrites xb */
+    }
+}
+
 template <class C, int S, int G, int MINB>
 __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArgs a)
 {
@@ -906,7 +990,10 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
                 if (bulk_cur) { mbar_wait(bar, parity); parity ^= 1; } else cp_async_wait_all();
                 team_sync<T>(team);
                 /* merge straight into the pass-1 registers (see march_merge_one) */
-                march_merge<C>(v, stage + off_cur, t, hw_t, typename make_iseq<E>::type{});
+                if constexpr (VVB_INV_PAIRMERGE != 0 && C::T == 32 && C::E == 32)
+                    march_merge_pairs<C, VVB_INV_PAIRMERGE>(v, stage + off_cur, xb, t, hw_t);
+                else
+                    march_merge<C>(v, stage + off_cur, t, hw_t, typename make_iseq<E>::type{});
                 team_sync<T>(team);                                    /* all reads of the staged X are done */
                 prefetch(frame + 1, off_next, bulk_next);
                 if constexpr (REGTW) team_fft_regtw<C>(v, xb, twb, t, team);

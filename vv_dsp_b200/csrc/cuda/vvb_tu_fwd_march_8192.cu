@@ -1,0 +1,5 @@
+/* vvb_tu_fwd_march_8192.cu -- stft_march_kernel instantiations for fft_size 8192 (hop = N/8, N/4, N/2; three output kinds). */
+#include "vvb_launch_march.cuh"
+namespace vvb {
+int tu_fwd_march_8192(size_t hop, const FwdArgs& a, int kind, int sms, void* stream) { return launch_fwd_march<Cfg4096>(hop, a, kind, sms, stream); }
+}

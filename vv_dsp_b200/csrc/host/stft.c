@@ -68,6 +68,7 @@ const char* vv_dsp_b200_version(void) { return "vv-dsp_b200 0.1.0 (sm_100a)"; }
 const char* vv_dsp_b200_last_error(void) { return vvb_last_error(); }
 unsigned long long vv_dsp_b200_kernel_launches(void) { return vvb_kernel_launches(); }
 vv_dsp_status vv_dsp_b200_fp32_peak(int packed, double* tflops) { return map_status(vvb_fp32_peak(packed, tflops)); }
+vv_dsp_status vv_dsp_b200_sm_clock_mhz(void* cuda_stream, double* mhz) { return map_status(vvb_sm_clock_mhz(cuda_stream, mhz)); }
 
 /* ---------------------------------------------------------------- create / destroy */
 static void handle_free(vv_dsp_stft* h)
