@@ -149,6 +149,48 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def stream_config4(lib, n_gpus, seconds=3600, steps=10, warmup=3):
+    """BASELINE config 4: ONE 1-hour 48 kHz stream, nfft=4096 hop=1024 Hann, sharded by frame range over n_gpus GPUs
+    by the C library's multi-device handle (vv_dsp_stft_stream_*: peer-to-peer sample halos, one CUDA graph per
+    device and step).  Timed on the devices (CUDA events on every device's stream, slowest device); the sharded
+    result is compared bit for bit with the one-device result of the same stream."""
+    import numpy as np
+    from vv_dsp_b200 import StftStream
+    nfft, hop = 4096, 1024
+    n = 48000 * seconds
+    frames, bins = 1 + (n - nfft) // hop, nfft // 2 + 1
+    rng = np.random.default_rng(4)
+    x = np.tile(rng.uniform(-1, 1, 48000 * 30).astype(np.float32), seconds // 30 + 1)[:n]
+    out = {"workload": f"configs[3]: single {seconds}-s 48 kHz stream ({n} samples, {frames} frames), nfft={nfft} hop={hop} Hann, "
+                       f"STFT -> complex half spectra -> normalised ISTFT, frame-range sharded over {n_gpus} GPU(s), "
+                       f"(nfft-hop)-sample halos peer to peer",
+           "n_gpus": n_gpus, "steps": steps, "halo_bytes_per_boundary_and_direction": (nfft - hop) * 4}
+    with StftStream(nfft, hop, n, [0], lib=lib) as s1:
+        s1.upload(x)
+        ms1 = s1.time_roundtrip(warmup, steps)
+        y1 = s1.download()
+    lo, hi = nfft, n - nfft
+    out["roundtrip_rel_l2"] = float(np.linalg.norm((y1[lo:hi] - x[lo:hi]).astype(np.float64)) / np.linalg.norm(x[lo:hi].astype(np.float64)))
+    hbm_peak, _ = measured_peaks()
+    gbytes = 2 * (4 * n + 8 * frames * bins) / 1e9
+    out["ms_per_step_1gpu"] = ms1
+    out["hbm_frac_1gpu"] = gbytes / (ms1 * 1e-3) / hbm_peak
+    ms = ms1
+    if n_gpus > 1:
+        with StftStream(nfft, hop, n, list(range(n_gpus)), lib=lib) as s:
+            s.upload(x)
+            ms = s.time_roundtrip(warmup, steps)
+            out["bit_identical_to_unsharded"] = bool(np.array_equal(s.download(), y1))
+            out["devices"] = sorted({s.shard(d).device for d in range(n_gpus)})
+        out["strong_scaling_efficiency"] = ms1 / (n_gpus * ms)
+    out["ms_per_step"] = ms
+    out["value"] = n / (ms * 1e-3) / 1e6
+    out["unit"] = UNIT
+    out["algorithmic_GB_per_step"] = gbytes
+    out["hbm_frac_aggregate"] = gbytes / (ms * 1e-3) / (hbm_peak * n_gpus)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,6 +200,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="signals per GPU (default: the BASELINE shape)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream", action="store_true", help="skip the config-4 single-stream leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -175,8 +218,12 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("VVB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL_DEBUG is left as the launcher set it (the driver reads communicator ranks from it); NCCL logs to
+        # stderr / NCCL_DEBUG_FILE, stdout carries the one JSON line
         dist.init_process_group("nccl", device_id=dev)
+    # CPU-side rendezvous for the phases in which ONE rank drives every GPU (the config-4 stream leg): the other
+    # ranks must wait on the host, not inside an NCCL kernel on a GPU that rank 0 is using
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
 
     from vv_dsp_b200 import Stft, default_library
     lib = default_library()
@@ -292,6 +339,20 @@ def main():
             fp32_scalar, fp32_packed = lib.fp32_peak(False), lib.fp32_peak(True)
         except Exception:
             pass
+    # ---- config 4: one long stream over all GPUs, driven by rank 0 through the C library's multi-device handle
+    stream_line = None
+    if not args.no_stream:
+        del xh, yh, xh_np, yh_np
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                stream_line = stream_config4(lib, world)
+            except Exception as exc:                       # the headline line must still be printed
+                stream_line = {"error": f"{type(exc).__name__}: {exc}"}
+        if world > 1:
+            dist.barrier(group=cpu_group)
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
         bytes_fwd = B * (4 * N_SAMPLES + 8 * FRAMES * BINS)       # read samples once + write half spectra once
@@ -330,6 +391,8 @@ def main():
                     "api": "vv_dsp_stft_set_async(1); vv_dsp_stft_batch_forward(HOST signals -> DEVICE spectra); vv_dsp_stft_batch_inverse(DEVICE spectra -> HOST signals); vv_dsp_stft_synchronize()"},
             "gpu_launches": int(launches), "clocks": clocks, "roundtrip_rel_l2": err,
         }
+        if stream_line is not None:
+            line["stream_config4"] = stream_line
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             run, Bc, kind = cpu_reference(cores, target_seconds=12.0)

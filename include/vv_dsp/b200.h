@@ -108,6 +108,76 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_inverse(
 VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_istft(vv_dsp_stft* h, const vv_dsp_cpx* half_spectra, size_t frames,
                                                  vv_dsp_real* out, size_t n_out);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * ONE long stream sharded by frame range over several GPUs (BASELINE config 4).
+ *
+ * Shard d owns the valid frames [F d / G, F (d+1) / G) of the n-sample stream and the samples [f0 hop, f1 hop)
+ * (the last shard: up to n).  Frames of different shards interact only through the overlap of nfft - hop samples at
+ * a boundary, and both directions resolve it with a HALO that is (nfft - hop) samples long:
+ *   analysis   a shard's local signal is [left halo | owned samples | right halo]; the right halo lets its last
+ *              frames reach into the next shard's samples, the left halo makes it ALSO compute the K - 1 = nfft/hop - 1
+ *              frames before its own first frame.  Local spectra: [K - 1 halo frames | own frames][bins].
+ *   synthesis  the halo frames are synthesised only for their overlap into the shard's first nfft - hop samples
+ *              (exactly what a warp of the batched kernel does when its range starts mid-signal); nothing is
+ *              exchanged, every output sample is the same ascending-frame sum as in the unsharded call, and the
+ *              shards' outputs CONCATENATE to the bit-identical result of vv_dsp_stft_batch_inverse on the whole
+ *              stream.  A frame-wise modification of the spectra must be applied to the halo rows as well.
+ * The only communication is the two sample halos per boundary (nfft - hop floats each way, 12 KB at 4096 / 1024),
+ * copied device to device over NVLink.  Needs hop | fft_size, fft_size in {512 ... 8192} and hop in {N/8, N/4, N/2}.
+ * (Bit-identical to the unsharded call for fft_size >= 2048, where both run the same kernel; at 512 / 1024 the
+ * unsharded call pairs frames two per transform, so the two agree to rounding -- and any two shard counts bit for bit.)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Synthesis of one shard, building block of the multi-process flavour (one process per GPU, vv_dsp_b200/sharding.py):
+ * spectra = DEVICE [local_frames][fft_size/2+1] holding halo_frames (0 for the first shard, else fft_size/hop - 1) rows
+ * of the previous shard followed by the shard's own frames; out = DEVICE, n_out owned samples, normalised.
+ * Enqueued on the handle's stream.  The analysis of a shard is vv_dsp_stft_batch_forward (VALID) of its local signal. */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_shard_inverse(vv_dsp_stft* h, const vv_dsp_cpx* spectra, size_t local_frames,
+                                                         size_t halo_frames, int is_first, int is_last,
+                                                         vv_dsp_real* out, size_t n_out);
+/* the CUDA device a handle lives on (every entry point switches to it and back), and the stream it enqueues on */
+int vv_dsp_stft_device(const vv_dsp_stft* h);
+void* vv_dsp_stft_get_stream(const vv_dsp_stft* h);
+
+/* The single-process flavour: one handle drives `num_devices` GPUs (device_ids NULL = 0 .. num_devices-1; the same id
+ * may appear more than once, which shards the stream on one GPU).  All buffers are owned by the handle and resident
+ * on the devices; per step the library enqueues, on each device's own stream, the two halo copies from the
+ * neighbouring devices (peer to peer), the fused analysis kernel and the fused synthesis kernel -- replayed as one
+ * CUDA graph per device once the first step has run.  No call blocks except upload / download / synchronize. */
+typedef struct vv_dsp_stft_stream vv_dsp_stft_stream;
+typedef struct vv_dsp_stft_stream_shard {
+    int device;
+    size_t frame0, frame1;          /* own frames of the stream */
+    size_t sample0, sample1;        /* own samples of the stream */
+    size_t halo_frames;             /* leading rows of `spectra` that belong to the previous shard */
+    size_t left_halo, right_halo;   /* samples in front of / behind the owned samples in `signal` */
+    vv_dsp_real* signal;            /* DEVICE [left_halo + (sample1 - sample0) + right_halo] */
+    vv_dsp_cpx* spectra;            /* DEVICE [halo_frames + frame1 - frame0][fft_size/2+1] */
+    vv_dsp_real* output;            /* DEVICE [sample1 - sample0] */
+    void* cuda_stream;              /* the stream the shard's work is enqueued on */
+} vv_dsp_stft_stream_shard;
+
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_create(const vv_dsp_stft_params* params, size_t n, size_t num_devices,
+                                                         const int* device_ids, vv_dsp_stft_stream** out);
+vv_dsp_status vv_dsp_stft_stream_destroy(vv_dsp_stft_stream* s);
+size_t vv_dsp_stft_stream_num_frames(const vv_dsp_stft_stream* s);
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_get_shard(const vv_dsp_stft_stream* s, size_t d, vv_dsp_stft_stream_shard* out);
+/* host signal [n] -> the shards' owned samples (synchronous); the halos are filled by every analysis step */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_upload(vv_dsp_stft_stream* s, const vv_dsp_real* signal);
+/* halo exchange + analysis of every shard (COMPLEX spectra into the shards' buffers); enqueue only */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_forward(vv_dsp_stft_stream* s);
+/* normalised synthesis of every shard from its spectra buffer into its output buffer; enqueue only */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_inverse(vv_dsp_stft_stream* s);
+/* forward + inverse as ONE enqueue per device (a captured CUDA graph after the first call) */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_roundtrip(vv_dsp_stft_stream* s);
+vv_dsp_status vv_dsp_stft_stream_synchronize(vv_dsp_stft_stream* s);
+/* gather to host (synchronous): out [n] samples; spectra [num_frames][fft_size/2+1] without the halo rows */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_download(vv_dsp_stft_stream* s, vv_dsp_real* out);
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_download_spectra(vv_dsp_stft_stream* s, vv_dsp_cpx* spectra);
+/* device-timed benchmark of `steps` roundtrip steps after `warmup` untimed ones: every device's stream is timed with
+ * its own pair of CUDA events between two full synchronisations; *ms_per_step = the slowest device's time / steps */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_time_roundtrip(vv_dsp_stft_stream* s, size_t warmup, size_t steps, double* ms_per_step);
+
 /* STFT -> power -> mel filterbank -> log for a whole batch:
  * out[b][f][m] = logf(sum_k |X_bf[k]|^2 W[m][k] + log_epsilon), i.e. vv_dsp_compute_log_mel_spectrogram
  * applied to the power output of vv_dsp_stft_batch_forward.  filterbank_weights: HOST, dense

@@ -45,7 +45,22 @@ int vvb_stream_sync(void* stream);
 int vvb_event_create(void** ev);
 int vvb_event_destroy(void* ev);
 int vvb_event_record(void* ev, void* stream);
+int vvb_event_sync(void* ev);                    /* host waits for the recorded work */
 int vvb_stream_wait_event(void* stream, void* ev);
+
+/* ---- several devices in one process (frame-range sharding of one stream, csrc/host/stream.c) */
+int vvb_device_count(int* count);
+int vvb_get_device(int* device);
+int vvb_set_device(int device);
+int vvb_enable_peer_access(int device, int peer);   /* device may then read / write peer's memory; 0 also when already on or device == peer */
+int vvb_memcpy_peer(void* dst, int dst_device, const void* src, int src_device, size_t bytes, void* stream);
+int vvb_event_create_timing(void** ev);
+int vvb_event_elapsed_ms(void* ev_start, void* ev_end, float* ms);
+/* capture what is enqueued on `stream` between begin and end into an executable graph; 6 = not supported here */
+int vvb_graph_capture_begin(void* stream);
+int vvb_graph_capture_end(void* stream, void** graph_exec);
+int vvb_graph_launch(void* graph_exec, void* stream);
+int vvb_graph_destroy(void* graph_exec);
 
 /* ---- STFT engine.  window: nfft host floats (the analysis == synthesis window). */
 int vvb_engine_create(size_t nfft, size_t hop, const float* window, vvb_engine** out);
@@ -64,6 +79,15 @@ int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, size_t n, si
  * NULL for the raw (un-normalised) sum. */
 int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t batch, size_t frames, size_t spec_pitch,
                      float* d_y, size_t n_out, size_t y_pitch, const float* d_inv_norm, void* stream);
+
+/* One frame-range shard of a longer stream: d_spec [frames][spec_pitch] = halo_frames rows that belong to the previous
+ * shard (synthesised only for their overlap into this shard's samples) followed by the shard's own frames; d_y receives
+ * the n_out samples starting at the first own frame's position.  head_edge / tail_edge: the shard starts / ends at the
+ * true start / end of the stream (edge normalisation; the trailing nfft-hop samples are emitted only at the true end).
+ * Shards concatenate to the bit-identical result of vvb_stft_inverse on the whole stream.  6 if (nfft, hop) has no
+ * marching kernel. */
+int vvb_stft_inverse_shard(vvb_engine* e, const vvb_cpx* d_spec, size_t frames, size_t halo_frames, int head_edge,
+                           int tail_edge, size_t spec_pitch, float* d_y, size_t n_out, const float* d_inv_norm, void* stream);
 
 /* windowed synthesis frames without overlap-add: d_frames [count][nfft] =
  * Re(IDFT(spec)/nfft) * w  (what vv_dsp_stft_reconstruct adds into out_add). */

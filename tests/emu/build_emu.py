@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "obj")
 
 def build(force=False):
     os.makedirs(OBJ, exist_ok=True)
-    host = [os.path.join(PKG, "csrc", "host", f) for f in ("window.c", "framing.c", "fft.c", "stft.c", "mel.c", "pcm.c")]
+    host = [os.path.join(PKG, "csrc", "host", f) for f in ("window.c", "framing.c", "fft.c", "stft.c", "stream.c", "mel.c", "pcm.c")]
     cudir = os.path.join(PKG, "csrc", "cuda")
     cus = sorted(os.path.join(cudir, f) for f in os.listdir(cudir) if f.endswith(".cu"))
     deps = host + cus + [os.path.join(HERE, "cuda_emu.h")]

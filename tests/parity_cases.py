@@ -9,7 +9,7 @@ relative L2 <= 1e-5; frame counts, padding and indexing bit-exact.
 import numpy as np
 
 from _util import ATOL, ROUNDTRIP_REL_L2, RTOL, noise, rel_l2, spectra_close, stft_truth_f64
-from vv_dsp_b200 import FftPlan, Stft
+from vv_dsp_b200 import StftStream, FftPlan, Stft
 from vv_dsp_b200.api import VvDspError
 
 
@@ -124,6 +124,21 @@ def check_inverse_few_frames(lib, oracle, sizes, frame_counts=(1, 2, 3, 4, 5, 9)
                         #  and the divide by a window-sum of 1e-2 amplifies that up to 100 times
                         tol = 1e-4 if (nfft <= 2048 or not norm) else 5e-3
                         assert err < tol, (nfft, hop, F, extra, norm, err)
+                        # ... so the binding check for this library is float64 truth at the north-star bound:
+                        # overlap-add of irfft(spec) * w in double, divided by the double window-sum
+                        acc = np.zeros((3, n + extra + nfft))
+                        for f in range(F):
+                            acc[:, f * hop:f * hop + nfft] += np.fft.irfft(spec[:, f].astype(np.complex128), nfft, axis=-1) * w
+                        acc = acc[:, :n + extra]
+                        if norm:
+                            truth = np.where(good, acc / np.where(nn[:n + extra] > 1e-2, nn[:n + extra], 1.0), 0.0)
+                            terr = np.abs((y - truth)[good]).max() / max(np.abs(truth[good]).max(), 1e-30)
+                            # a sample is divided by a window-sum >= 1e-2, which amplifies the float32 rounding of
+                            # the synthesis (~2e-7 of max|x|) by up to 100
+                            assert terr < 5e-5, ("truth", nfft, hop, F, extra, terr)
+                        else:
+                            terr = np.abs(y - acc).max() / max(np.abs(acc).max(), 1e-30)
+                            assert terr < 1e-5, ("truth", nfft, hop, F, extra, terr)
     return worst
 
 
@@ -417,6 +432,8 @@ def check_bluestein(lib, oracle, sizes):
                     assert rel_l2(own[:, nfft:n - nfft], x[:, nfft:n - nfft]) <= ROUNDTRIP_REL_L2
                     oref = np.stack([oracle.istft(ref[i], nfft, hop, n, win) for i in range(2)])
                     assert rel_l2(y[:, nfft:n - nfft], oref[:, nfft:n - nfft]) <= 2e-4     # the oracle's inverse DFT error dominates
+                    # binding check beside the widened tolerance: float64 truth of the same spectra, relative L2
+                    assert rel_l2(y[:, nfft:n - nfft], yt[:, nfft:n - nfft]) <= ROUNDTRIP_REL_L2
         report[nfft] = (float(mine), float(theirs))
         # plan API
         z = (rng.uniform(-1, 1, (3, nfft)) + 1j * rng.uniform(-1, 1, (3, nfft))).astype(np.complex64)
@@ -463,6 +480,8 @@ def check_golden_slices(lib, golden):
                 # and hold this library to the true signal at the north-star bound
                 tol = 5e-5 if nfft <= 2048 else 4e-4
                 assert np.abs(y[n // 2: n // 2 + 256] - ref).max() <= tol * max(np.abs(ref).max(), 1e-30), key
+                # binding check beside the widened tolerance: the true signal, max-norm, at the north-star scale
+                assert np.abs(y[n // 2: n // 2 + 256] - x[n // 2: n // 2 + 256]).max() <= 1e-5 * np.abs(x).max(), key
                 if 2 * hop <= nfft:   # with less overlap the Hann window-sum has near-zeros: ill-conditioned divide
                     assert rel_l2(y[n // 2: n // 2 + 256], x[n // 2: n // 2 + 256]) <= ROUNDTRIP_REL_L2, key
 
@@ -482,3 +501,112 @@ def check_config1_voicebank(lib, golden):
     err = rel_l2(y[1024:-1024], wav[1024:-1024])
     assert err <= ROUNDTRIP_REL_L2, err
     return err
+
+
+def check_reconstruct_non_hermitian(lib, oracle, sizes=((256, 64), (2048, 512), (100, 30), (8, 4))):
+    """vv_dsp_stft_reconstruct with a spectrum that is NOT Hermitian (a caller edited only bins 0..n/2, or anything
+    else): the reference adds Re(IDFT(X)) * w (src/spectral/stft.c:95-110); here the host forms the Hermitian part
+    (X[k] + conj X[n-k]) / 2 first.  Same arbitrary input to both sides."""
+    rng = np.random.default_rng(99)
+    for nfft, hop in sizes:
+        for case in ("random", "lower_half_only", "imag_dc_nyquist"):
+            X = (rng.uniform(-1, 1, nfft) + 1j * rng.uniform(-1, 1, nfft)).astype(np.complex64)
+            if case == "lower_half_only":
+                x = rng.uniform(-1, 1, nfft).astype(np.float32)
+                X = np.fft.fft(x).astype(np.complex64)
+                X[nfft // 2 + 1:] = 0                                   # upper half wiped: a common caller shortcut
+            elif case == "imag_dc_nyquist":
+                X = np.fft.fft(rng.uniform(-1, 1, nfft)).astype(np.complex64)
+                X[0] += 3j
+                X[nfft // 2] -= 2j
+            with Stft(nfft, hop, "hann", lib=lib) as h:
+                out = np.full(nfft, 0.25, np.float32); nrm = np.full(nfft, 0.5, np.float32)
+                h.reconstruct(X, out, nrm)
+            a, b = oracle.reconstruct(X, nfft, hop, "hann")
+            w = oracle.window("hann", nfft)[1].astype(np.float64)
+            truth = np.fft.ifft(X.astype(np.complex128)).real * w
+            scale = max(np.abs(truth).max(), 1e-30)
+            assert np.abs((out - 0.25) - truth).max() <= 1e-5 * scale, (nfft, case)              # float64 truth
+            assert np.abs((out - 0.25) - a).max() <= 5e-5 * scale + 1e-7, (nfft, case)           # the reference's result
+            assert np.array_equal(nrm, np.float32(0.5) + b), (nfft, case)                        # norm_add += w*w, float32
+
+
+def check_async_many_chunks(lib, oracle, nfft=256, hop=64, n=4000, batch=150):
+    """Stream-ordered host mode with MORE chunks than the dependency ring holds (64): the analysis call leaves its
+    spectra in HBM chunk by chunk, the synthesis call that follows must wait for every one of them.  Caller sets
+    VVB_STAGE_TARGET_BYTES small enough that a chunk is one signal (test hook read at handle creation)."""
+    import torch
+    x = np.stack([noise(500 + i, n) for i in range(batch)])
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        F = h.num_frames(n, "valid")
+        ref_spec = h.batch_forward(x, "complex", "valid")             # synchronous reference run
+        ref_y = h.batch_inverse(ref_spec, n, True)
+        xh = torch.from_numpy(x).pin_memory()
+        yh = torch.empty((batch, n), dtype=torch.float32).pin_memory()
+        for rep in range(3):
+            spec = torch.zeros((batch, F, h.bins), device="cuda", dtype=torch.complex64)
+            yh.zero_()
+            torch.cuda.synchronize()
+            h.set_async(True)
+            h.batch_forward(xh.numpy(), "complex", "valid", out=spec)
+            h.batch_inverse(spec, n, True, out=yh.numpy())
+            h.synchronize()
+            h.set_async(False)
+            assert np.array_equal(spec.cpu().numpy(), ref_spec), rep
+            assert np.array_equal(yh.numpy(), ref_y), rep
+
+
+def check_staged_chunks_equal_single(lib, nfft, hop, n=3000, batch=9):
+    """host-staged calls split into many chunks == the same call in one chunk (sizes with per-engine scratch buffers
+    included: their chunks must not overlap in time).  Caller sets VVB_STAGE_TARGET_BYTES for the chunked handle."""
+    x = np.stack([noise(900 + nfft + i, n) for i in range(batch)])
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        spec = h.batch_forward(x, "complex", "valid")
+        y = h.batch_inverse(spec, n, True)
+        for rep in range(3):
+            assert np.array_equal(h.batch_forward(x, "complex", "valid"), spec)
+            assert np.array_equal(h.batch_inverse(spec, n, True), y)
+    return spec, y
+
+
+def check_stream_sharding(lib, nfft, hop, n, shard_counts=(1, 2, 3, 5), win="hann", device=0):
+    """vv_dsp_stft_stream (one stream, frame-range shards with sample halos) against the UNSHARDED batched calls:
+    spectra and the normalised ISTFT must be bit-identical for every shard count -- the shards re-synthesise the
+    nfft/hop - 1 frames in front of their range instead of exchanging partial sums.  All shards on one device here
+    (peer copies degenerate to device copies), so the whole path runs on a 1-GPU box and in the emulator."""
+    x = noise(4242 + nfft, n)
+    with Stft(nfft, hop, win, lib=lib) as h:
+        spec = h.batch_forward(x[None], "complex", "valid")[0]
+        y = h.batch_inverse(spec[None], n, True)[0]
+    first = None
+    for g in shard_counts:
+        with StftStream(nfft, hop, n, [device] * g, win, lib=lib) as s:
+            assert s.frames == spec.shape[0]
+            cover = 0
+            for d in range(g):
+                sh = s.shard(d)
+                assert sh.frame0 == s.frames * d // g and sh.frame1 == s.frames * (d + 1) // g        # SURVEY.md 8e
+                assert sh.sample0 == sh.frame0 * hop and sh.sample1 == (n if d == g - 1 else sh.frame1 * hop)
+                assert sh.halo_frames == (0 if d == 0 else nfft // hop - 1)
+                assert sh.left_halo == (0 if d == 0 else nfft - hop) and sh.right_halo == (0 if d == g - 1 else nfft - hop)
+                cover += sh.sample1 - sh.sample0
+            assert cover == n
+            s.upload(x)
+            s.forward(); s.inverse(); s.synchronize()
+            assert np.array_equal(s.download_spectra(), spec), (nfft, hop, g, "spectra")
+            # fft_size >= 2048: shards and the unsharded call run the same marching kernel -> bit-identical.  Below, the
+            # unsharded call pairs frames (two per complex transform), a shard does not: equal to rounding, and the
+            # shard counts must still agree bit for bit among themselves.
+            same = (lambda a, b: np.array_equal(a, b)) if nfft >= 2048 else \
+                   (lambda a, b: np.abs(a - b)[nfft:-nfft].max() <= 2e-6 * np.abs(b).max())
+            got = s.download()
+            assert same(got, y), (nfft, hop, g, "istft")
+            if first is None:
+                first = got
+            assert np.array_equal(got, first), (nfft, hop, g, "shard counts disagree")
+            for _ in range(3):                                    # first call plain, later ones replay the captured graphs
+                s.roundtrip()
+            s.synchronize()
+            assert np.array_equal(s.download(), first), (nfft, hop, g, "roundtrip")
+            assert s.time_roundtrip(1, 2) >= 0.0
+    return y, x

@@ -119,3 +119,20 @@ def test_bluestein_unfused_and_direct_paths(emu, oracle, monkeypatch):
 
 def test_inverse_few_frames(emu, oracle):
     pc.check_inverse_few_frames(emu, oracle, [(256, 64), (512, 256), (1024, 128), (2048, 512)], (1, 2, 3, 5))
+
+
+def test_reconstruct_non_hermitian(emu, oracle):
+    pc.check_reconstruct_non_hermitian(emu, oracle)
+
+
+def test_staged_chunks_do_not_overlap(emu, monkeypatch):
+    one = pc.check_staged_chunks_equal_single(emu, 100, 30, n=900, batch=5)
+    monkeypatch.setenv("VVB_STAGE_TARGET_BYTES", str(8 * 1024))
+    many = pc.check_staged_chunks_equal_single(emu, 100, 30, n=900, batch=5)
+    import numpy as np
+    assert np.array_equal(one[0], many[0]) and np.array_equal(one[1], many[1])
+
+
+@pytest.mark.parametrize("nfft,hop", [(2048, 512), (4096, 1024), (512, 256), (1024, 128)])
+def test_stream_sharding_bit_identical(emu, nfft, hop):
+    pc.check_stream_sharding(emu, nfft, hop, nfft + hop * 45 + 17, shard_counts=(1, 2, 3))

@@ -311,3 +311,90 @@ def test_mel_chain_device_buffers(lib, oracle):
         assert lm_dev.is_cuda and mf_dev.is_cuda
         assert lm_dev.cpu().numpy().tobytes() == lm_host.tobytes()
         assert mf_dev.cpu().numpy().tobytes() == mf_host.tobytes()
+
+
+def test_reconstruct_non_hermitian(lib, oracle):
+    pc.check_reconstruct_non_hermitian(lib, oracle)
+
+
+def test_async_more_chunks_than_the_dependency_ring(lib, oracle, monkeypatch):
+    """150 one-signal chunks through the 64-entry dependency ring of the stream-ordered host mode"""
+    monkeypatch.setenv("VVB_STAGE_TARGET_BYTES", str(64 * 1024))
+    pc.check_async_many_chunks(lib, oracle)
+
+
+@pytest.mark.parametrize("nfft,hop", [(400, 160), (100, 30), (2048, 512), (3000, 750)])
+def test_staged_chunks_do_not_overlap(lib, nfft, hop, monkeypatch):
+    """multi-chunk host-staged calls (chirp-z / direct sizes share per-engine scratch) == single-chunk calls"""
+    one_spec, one_y = pc.check_staged_chunks_equal_single(lib, nfft, hop)
+    monkeypatch.setenv("VVB_STAGE_TARGET_BYTES", str(32 * 1024))
+    many_spec, many_y = pc.check_staged_chunks_equal_single(lib, nfft, hop)
+    assert np.array_equal(one_spec, many_spec) and np.array_equal(one_y, many_y)
+
+
+def test_device_calls_follow_torchs_current_stream(lib):
+    """No set_stream(): device-tensor calls are enqueued on torch's current stream, so they are ordered against the
+    torch ops that produce their inputs and consume their outputs (also on a side stream)."""
+    import torch
+    nfft, hop, n, B = 2048, 512, 48000, 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    base = torch.rand((B, n), device="cuda", generator=g) * 2 - 1
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        torch.cuda.synchronize()
+        want = h.batch_forward(base * 0.5, "complex", "valid")
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        for s in (torch.cuda.current_stream(), side):
+            with torch.cuda.stream(s):
+                big = torch.rand((4096, 4096), device="cuda")
+                for _ in range(20):
+                    big = big @ big * 1e-3                           # keeps the stream busy: the input below is late
+                x = base * 0.5                                        # produced on this stream
+                spec = h.batch_forward(x, "complex", "valid")
+                back = h.batch_inverse(spec, n, True)
+                err = (back - x)[:, nfft:-nfft].abs().max()          # consumed on this stream
+            torch.cuda.synchronize()
+            assert torch.equal(spec, want)
+            assert float(err) < 1e-5
+        # layout / dtype are checked instead of silently misread
+        with pytest.raises(TypeError):
+            h.batch_forward(base.double(), "complex", "valid")
+        with pytest.raises(ValueError):
+            h.batch_forward(base[:, ::2], "complex", "valid")
+        # a row pitch larger than the row is honoured: signals and spectra as views into wider buffers
+        wide = torch.zeros((B, n + 96), device="cuda"); wide[:, :n] = base * 0.5
+        wspec = torch.zeros((B, want.shape[1], h.bins + 3), device="cuda", dtype=torch.complex64)
+        h.batch_forward(wide[:, :n], "complex", "valid", out=wspec[:, :, :h.bins])
+        torch.cuda.synchronize()
+        assert torch.equal(wspec[:, :, :h.bins], want) and float(wspec[:, :, h.bins:].abs().max()) == 0.0
+        wy = torch.zeros((B, n + 10), device="cuda")
+        h.batch_inverse(wspec[:, :, :h.bins], n, True, out=wy[:, :n])
+        torch.cuda.synchronize()
+        assert float((wy[:, :n] - base * 0.5)[:, nfft:-nfft].abs().max()) < 1e-5 and float(wy[:, n:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("nfft,hop", [(4096, 1024), (2048, 512), (2048, 256), (8192, 4096), (1024, 256), (512, 64)])
+def test_stream_sharding_bit_identical(lib, nfft, hop):
+    """BASELINE config 4 in miniature: 1 / 2 / 3 / 5 / 8 shards == the unsharded result, bit for bit"""
+    y, x = pc.check_stream_sharding(lib, nfft, hop, nfft + hop * 997 + 123, shard_counts=(1, 2, 3, 5, 8))
+    assert rel_l2(y[nfft:-nfft], x[nfft:-nfft]) <= ROUNDTRIP_REL_L2
+
+
+def test_stream_sharding_over_all_visible_gpus(lib):
+    """the same on every GPU the box has (the driver's test box has one: then this is the 1-device case)"""
+    import torch
+    g = torch.cuda.device_count()
+    nfft, hop, n = 4096, 1024, 48000 * 60
+    x = noise(77, n)
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        spec = h.batch_forward(x[None], "complex", "valid")[0]
+        y = h.batch_inverse(spec[None], n, True)[0]
+    from vv_dsp_b200 import StftStream
+    with StftStream(nfft, hop, n, list(range(g)), lib=lib) as s:
+        s.upload(x)
+        for _ in range(3):
+            s.roundtrip()
+        s.synchronize()
+        assert np.array_equal(s.download_spectra(), spec)
+        assert np.array_equal(s.download(), y)
+        assert {s.shard(d).device for d in range(g)} == set(range(g))

@@ -90,9 +90,28 @@ class Library:
         "vv_dsp_b200_kernel_launches": (C.c_ulonglong, []),
         "vv_dsp_b200_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
         "vv_dsp_b200_sm_clock_mhz": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+        "vv_dsp_stft_shard_inverse": (C.c_int, [_vp, _vp, _sz, _sz, C.c_int, C.c_int, _vp, _sz]),
+        "vv_dsp_stft_device": (C.c_int, [_vp]),
+        "vv_dsp_stft_get_stream": (_vp, [_vp]),
+        "vv_dsp_stft_stream_create": (C.c_int, [C.POINTER(StftParams), _sz, _sz, C.POINTER(C.c_int), C.POINTER(_vp)]),
+        "vv_dsp_stft_stream_destroy": (C.c_int, [_vp]),
+        "vv_dsp_stft_stream_num_frames": (_sz, [_vp]),
+        "vv_dsp_stft_stream_get_shard": (C.c_int, [_vp, _sz, _vp]),
+        "vv_dsp_stft_stream_upload": (C.c_int, [_vp, _vp]),
+        "vv_dsp_stft_stream_forward": (C.c_int, [_vp]),
+        "vv_dsp_stft_stream_inverse": (C.c_int, [_vp]),
+        "vv_dsp_stft_stream_roundtrip": (C.c_int, [_vp]),
+        "vv_dsp_stft_stream_synchronize": (C.c_int, [_vp]),
+        "vv_dsp_stft_stream_download": (C.c_int, [_vp, _vp]),
+        "vv_dsp_stft_stream_download_spectra": (C.c_int, [_vp, _vp]),
+        "vv_dsp_stft_stream_time_roundtrip": (C.c_int, [_vp, _sz, _sz, C.POINTER(C.c_double)]),
     }
     # entry points newer than round 1: absent from an old library variant loaded for an A/B measurement
-    OPTIONAL = {"vv_dsp_b200_sm_clock_mhz"}
+    OPTIONAL = {"vv_dsp_b200_sm_clock_mhz", "vv_dsp_stft_shard_inverse", "vv_dsp_stft_device", "vv_dsp_stft_get_stream",
+                "vv_dsp_stft_stream_create", "vv_dsp_stft_stream_destroy", "vv_dsp_stft_stream_num_frames",
+                "vv_dsp_stft_stream_get_shard", "vv_dsp_stft_stream_upload", "vv_dsp_stft_stream_forward",
+                "vv_dsp_stft_stream_inverse", "vv_dsp_stft_stream_roundtrip", "vv_dsp_stft_stream_synchronize",
+                "vv_dsp_stft_stream_download", "vv_dsp_stft_stream_download_spectra", "vv_dsp_stft_stream_time_roundtrip"}
 
     def __init__(self, path: str | None = None):
         path = path or DEFAULT_LIB
@@ -300,6 +319,8 @@ class Stft:
         p = StftParams(self.nfft, self.hop, _win_id(window))
         st = self.lib.vv_dsp_stft_create(C.byref(p), C.byref(self._h))
         _check(self.lib, st, "vv_dsp_stft_create")
+        self._stream_pinned = False      # set_stream() called by the user: never rebind behind their back
+        self._bound_stream = None        # what the handle is bound to right now (None = its own stream)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -344,14 +365,42 @@ class Stft:
         return int(self.lib.vv_dsp_stft_num_frames(self._h, n, CONVENTIONS[convention]))
 
     def set_stream(self, cuda_stream):
-        """cuda_stream: a cudaStream_t as an integer.  None = the handle's own stream; 0 (the legacy default
-        stream, what torch reports for its default stream) is passed as cudaStreamLegacy (0x1), because the C
-        API reserves NULL for "the handle's own stream"."""
+        """Pin the handle to a stream.  cuda_stream: a cudaStream_t as an integer.  None = the handle's own stream
+        (and back to automatic binding, see _bind_torch_stream); 0 (the legacy default stream, what torch reports
+        for its default stream) is passed as cudaStreamLegacy (0x1), because the C API reserves NULL for "the
+        handle's own stream"."""
+        self._stream_pinned = cuda_stream is not None
+        self._set_stream_raw(cuda_stream)
+
+    def _set_stream_raw(self, cuda_stream):
         if cuda_stream is None:
             arg = None
         else:
             arg = _vp(int(cuda_stream) or 1)
         _check(self.lib, self.lib.vv_dsp_stft_set_stream(self._h, arg), "vv_dsp_stft_set_stream")
+        self._bound_stream = None if cuda_stream is None else (int(cuda_stream) or 1)
+
+    def _bind_torch_stream(self, tensor):
+        """Stream contract of the device path: calls whose buffers are torch CUDA tensors are enqueued on torch's
+        CURRENT stream of that device (like any torch op), so they are ordered after the ops that produced the
+        inputs and before the ops that consume the outputs -- unless the user pinned a stream with set_stream(),
+        in which case ordering against torch's streams is theirs to establish."""
+        if self._stream_pinned:
+            return
+        import torch
+        cur = int(torch.cuda.current_stream(tensor.device).cuda_stream) or 1
+        if cur != self._bound_stream:
+            self._set_stream_raw(cur)
+
+    @staticmethod
+    def _check_device_tensor(t, dtype_name, what):
+        """device tensors are handed to the C API as raw pointers: the layout has to be what it expects"""
+        import torch
+        want = {"float32": torch.float32, "complex64": torch.complex64}[dtype_name]
+        if t.dtype != want:
+            raise TypeError(f"{what}: expected a {dtype_name} CUDA tensor, got {t.dtype}")
+        if t.stride(-1) != 1:
+            raise ValueError(f"{what}: the innermost dimension must be contiguous (stride {t.stride(-1)})")
 
     def synchronize(self):
         _check(self.lib, self.lib.vv_dsp_stft_synchronize(self._h), "vv_dsp_stft_synchronize")
@@ -368,7 +417,7 @@ class Stft:
             signals = np.ascontiguousarray(signals, np.float32)
         assert signals.ndim == 2
         batch, n = int(signals.shape[0]), int(signals.shape[1])
-        pitch = int(signals.stride(0)) if dev_in else n
+        pitch = (int(signals.stride(0)) if batch > 1 else n) if dev_in else n
         frames = self.num_frames(n, convention)
         if out is None:
             if dev_in:
@@ -377,13 +426,45 @@ class Stft:
                                   dtype=torch.complex64 if kind == "complex" else torch.float32)
             else:
                 out = np.empty((batch, frames, self.bins), np.complex64 if kind == "complex" else np.float32)
+        spec_pitch = 0
+        if dev_in:
+            self._check_device_tensor(signals, "float32", "signals")
+        if _is_device(out):
+            self._check_device_tensor(out, "complex64" if kind == "complex" else "float32", "out")
+            assert tuple(out.shape) == (batch, frames, self.bins), (tuple(out.shape), (batch, frames, self.bins))
+            spec_pitch = self._spec_pitch(out)
+            self._bind_torch_stream(out)
+        elif dev_in:
+            self._bind_torch_stream(signals)
         nf = _sz(0)
         st = self.lib.vv_dsp_stft_batch_forward(self._h, _ptr(signals), DEVICE if dev_in else HOST, batch, n, pitch,
                                                 CONVENTIONS[convention], KINDS[kind], _ptr(out),
-                                                DEVICE if _is_device(out) else HOST, 0, C.byref(nf))
+                                                DEVICE if _is_device(out) else HOST, spec_pitch, C.byref(nf))
         _check(self.lib, st, "vv_dsp_stft_batch_forward")
         assert nf.value == frames
         return out
+
+    def _prepare_device_args(self, signals, out):
+        """dtype / layout checks and stream binding of the feature chains (dense float32 output)"""
+        if _is_device(signals):
+            self._check_device_tensor(signals, "float32", "signals")
+        if _is_device(out):
+            self._check_device_tensor(out, "float32", "out")
+            if not out.is_contiguous():
+                raise ValueError("out: must be contiguous")
+            self._bind_torch_stream(out)
+        elif _is_device(signals):
+            self._bind_torch_stream(signals)
+
+    def _spec_pitch(self, t):
+        """row pitch (elements) of a [batch, frames, bins] device tensor whose rows follow each other at one pitch;
+        0 = dense"""
+        if t.shape[1] > 1 and t.shape[0] > 1 and t.stride(0) != t.shape[1] * t.stride(1):
+            raise ValueError("spectra: frames of consecutive signals must follow each other at the row pitch")
+        p = int(t.stride(1)) if t.shape[1] > 1 else (int(t.stride(0)) if t.shape[0] > 1 else self.bins)
+        if p < self.bins:
+            raise ValueError("spectra: row pitch smaller than fft_size/2+1")
+        return 0 if p == self.bins else p
 
     def batch_logmel(self, signals, weights, log_epsilon=1e-10, convention="valid", out=None):
         """STFT -> power -> mel -> log: signals [batch, n] (numpy or torch CUDA), weights [n_mels, bins] numpy"""
@@ -393,7 +474,7 @@ class Stft:
         weights = np.ascontiguousarray(weights, np.float32)
         assert weights.shape[1] == self.bins
         batch, n = int(signals.shape[0]), int(signals.shape[1])
-        pitch = int(signals.stride(0)) if dev_in else n
+        pitch = (int(signals.stride(0)) if batch > 1 else n) if dev_in else n
         frames = self.num_frames(n, convention)
         if out is None:
             if dev_in:
@@ -401,6 +482,7 @@ class Stft:
                 out = torch.empty((batch, frames, weights.shape[0]), device=signals.device, dtype=torch.float32)
             else:
                 out = np.empty((batch, frames, weights.shape[0]), np.float32)
+        self._prepare_device_args(signals, out)
         nf = _sz(0)
         st = self.lib.vv_dsp_stft_batch_logmel(self._h, _ptr(signals), DEVICE if dev_in else HOST, batch, n, pitch,
                                                CONVENTIONS[convention], _ptr(weights), weights.shape[0], log_epsilon,
@@ -416,7 +498,7 @@ class Stft:
         weights = np.ascontiguousarray(weights, np.float32)
         assert weights.shape[1] == self.bins
         batch, n = int(signals.shape[0]), int(signals.shape[1])
-        pitch = int(signals.stride(0)) if dev_in else n
+        pitch = (int(signals.stride(0)) if batch > 1 else n) if dev_in else n
         frames = self.num_frames(n, convention)
         if out is None:
             if dev_in:
@@ -424,6 +506,7 @@ class Stft:
                 out = torch.empty((batch, frames, num_coeffs), device=signals.device, dtype=torch.float32)
             else:
                 out = np.empty((batch, frames, num_coeffs), np.float32)
+        self._prepare_device_args(signals, out)
         nf = _sz(0)
         st = self.lib.vv_dsp_stft_batch_mfcc(self._h, _ptr(signals), DEVICE if dev_in else HOST, batch, n, pitch,
                                              CONVENTIONS[convention], _ptr(weights), weights.shape[0], log_epsilon,
@@ -445,9 +528,35 @@ class Stft:
             else:
                 out = np.empty((batch, n_out), np.float32)
         keep = spectra if frames else None
-        st = self.lib.vv_dsp_stft_batch_inverse(self._h, _ptr(keep), DEVICE if dev_in else HOST, batch, frames, 0,
-                                                _ptr(out), DEVICE if _is_device(out) else HOST, n_out, 0, int(normalise))
+        spec_pitch = out_pitch = 0
+        if dev_in:
+            self._check_device_tensor(spectra, "complex64", "spectra")
+            spec_pitch = self._spec_pitch(spectra)
+        if _is_device(out):
+            self._check_device_tensor(out, "float32", "out")
+            assert out.ndim == 2 and int(out.shape[0]) == batch and int(out.shape[1]) == n_out
+            out_pitch = int(out.stride(0)) if batch > 1 else 0
+            self._bind_torch_stream(out)
+        elif dev_in:
+            self._bind_torch_stream(spectra)
+        st = self.lib.vv_dsp_stft_batch_inverse(self._h, _ptr(keep), DEVICE if dev_in else HOST, batch, frames, spec_pitch,
+                                                _ptr(out), DEVICE if _is_device(out) else HOST, n_out, out_pitch, int(normalise))
         _check(self.lib, st, "vv_dsp_stft_batch_inverse")
+        return out
+
+    def shard_inverse(self, spectra, halo_frames, is_first, is_last, n_out, out=None):
+        """Synthesis of one frame-range shard of a longer stream (include/vv_dsp/b200.h): spectra = CUDA tensor
+        [halo_frames + own frames, bins], out = CUDA tensor [n_out] (the shard's owned samples)."""
+        import torch
+        self._check_device_tensor(spectra, "complex64", "spectra")
+        assert spectra.ndim == 2 and spectra.shape[1] == self.bins and spectra.is_contiguous()
+        if out is None:
+            out = torch.empty(n_out, device=spectra.device, dtype=torch.float32)
+        self._check_device_tensor(out, "float32", "out")
+        self._bind_torch_stream(out)
+        st = self.lib.vv_dsp_stft_shard_inverse(self._h, _ptr(spectra), int(spectra.shape[0]), int(halo_frames), int(bool(is_first)),
+                                                int(bool(is_last)), _ptr(out), int(n_out))
+        _check(self.lib, st, "vv_dsp_stft_shard_inverse")
         return out
 
     def istft(self, half_spectra, n_out):
@@ -457,6 +566,82 @@ class Stft:
                                         half_spectra.shape[0], _ptr(out), n_out)
         _check(self.lib, st, "vv_dsp_stft_istft")
         return out
+
+
+# ----------------------------------------------------------------------------- one stream over several GPUs
+class StreamShard(C.Structure):
+    """vv_dsp_stft_stream_shard (include/vv_dsp/b200.h)"""
+    _fields_ = [("device", C.c_int), ("frame0", _sz), ("frame1", _sz), ("sample0", _sz), ("sample1", _sz),
+                ("halo_frames", _sz), ("left_halo", _sz), ("right_halo", _sz),
+                ("signal", _vp), ("spectra", _vp), ("output", _vp), ("cuda_stream", _vp)]
+
+
+class StftStream:
+    """vv_dsp_stft_stream: ONE long stream sharded by frame range over several GPUs of this process."""
+
+    def __init__(self, fft_size, hop_size, n, devices, window="hann", lib: Library | None = None):
+        self.lib = lib or default_library()
+        self.nfft, self.hop, self.n = int(fft_size), int(hop_size), int(n)
+        self.bins = self.nfft // 2 + 1
+        self.devices = list(devices)
+        self._s = _vp()
+        p = StftParams(self.nfft, self.hop, _win_id(window))
+        ids = (C.c_int * len(self.devices))(*self.devices)
+        st = self.lib.vv_dsp_stft_stream_create(C.byref(p), self.n, len(self.devices), ids, C.byref(self._s))
+        _check(self.lib, st, "vv_dsp_stft_stream_create")
+        self.frames = int(self.lib.vv_dsp_stft_stream_num_frames(self._s))
+
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s.value:
+            self.lib.vv_dsp_stft_stream_destroy(self._s)
+            self._s = _vp()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def shard(self, d) -> StreamShard:
+        sh = StreamShard()
+        _check(self.lib, self.lib.vv_dsp_stft_stream_get_shard(self._s, d, C.byref(sh)), "vv_dsp_stft_stream_get_shard")
+        return sh
+
+    def upload(self, signal):
+        signal = np.ascontiguousarray(signal, np.float32)
+        assert signal.size == self.n
+        _check(self.lib, self.lib.vv_dsp_stft_stream_upload(self._s, _ptr(signal)), "vv_dsp_stft_stream_upload")
+
+    def forward(self):
+        _check(self.lib, self.lib.vv_dsp_stft_stream_forward(self._s), "vv_dsp_stft_stream_forward")
+
+    def inverse(self):
+        _check(self.lib, self.lib.vv_dsp_stft_stream_inverse(self._s), "vv_dsp_stft_stream_inverse")
+
+    def roundtrip(self):
+        _check(self.lib, self.lib.vv_dsp_stft_stream_roundtrip(self._s), "vv_dsp_stft_stream_roundtrip")
+
+    def synchronize(self):
+        _check(self.lib, self.lib.vv_dsp_stft_stream_synchronize(self._s), "vv_dsp_stft_stream_synchronize")
+
+    def download(self):
+        out = np.empty(self.n, np.float32)
+        _check(self.lib, self.lib.vv_dsp_stft_stream_download(self._s, _ptr(out)), "vv_dsp_stft_stream_download")
+        return out
+
+    def download_spectra(self):
+        out = np.empty((self.frames, self.bins), np.complex64)
+        _check(self.lib, self.lib.vv_dsp_stft_stream_download_spectra(self._s, _ptr(out)), "vv_dsp_stft_stream_download_spectra")
+        return out
+
+    def time_roundtrip(self, warmup=3, steps=10) -> float:
+        """ms per forward + inverse step, CUDA events on every device's stream, slowest device"""
+        ms = C.c_double(0.0)
+        _check(self.lib, self.lib.vv_dsp_stft_stream_time_roundtrip(self._s, warmup, steps, C.byref(ms)),
+               "vv_dsp_stft_stream_time_roundtrip")
+        return float(ms.value)
 
 
 # ----------------------------------------------------------------------------- FFT plan

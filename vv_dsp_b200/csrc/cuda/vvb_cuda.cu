@@ -60,6 +60,18 @@ extern "C" int vvb_stream_sync(void*) { return 0; }
 extern "C" int vvb_event_create(void** e) { *e = malloc(1); return 0; }
 extern "C" int vvb_event_destroy(void* e) { free(e); return 0; }
 extern "C" int vvb_event_record(void*, void*) { return 0; }
+extern "C" int vvb_event_sync(void*) { return 0; }
+extern "C" int vvb_device_count(int* n) { *n = 1; return 0; }
+extern "C" int vvb_get_device(int* d) { *d = 0; return 0; }
+extern "C" int vvb_set_device(int) { return 0; }
+extern "C" int vvb_enable_peer_access(int, int) { return 0; }
+extern "C" int vvb_memcpy_peer(void* d, int, const void* s, int, size_t n, void*) { memcpy(d, s, n); return 0; }
+extern "C" int vvb_event_create_timing(void** e) { *e = malloc(1); return 0; }
+extern "C" int vvb_event_elapsed_ms(void*, void*, float* ms) { *ms = 0.f; return 0; }
+extern "C" int vvb_graph_capture_begin(void*) { return 6; }
+extern "C" int vvb_graph_capture_end(void*, void**) { return 6; }
+extern "C" int vvb_graph_launch(void*, void*) { return 6; }
+extern "C" int vvb_graph_destroy(void*) { return 0; }
 extern "C" int vvb_stream_wait_event(void*, void*) { return 0; }
 #else
 /* ---- CUDA runtime */
@@ -102,6 +114,45 @@ extern "C" int vvb_stream_sync(void* s) { CK(cudaStreamSynchronize((cudaStream_t
 extern "C" int vvb_event_create(void** e) { cudaEvent_t ev; CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); *e = ev; return 0; }
 extern "C" int vvb_event_destroy(void* e) { if (e) CK(cudaEventDestroy((cudaEvent_t)e)); return 0; }
 extern "C" int vvb_event_record(void* e, void* s) { CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s)); return 0; }
+extern "C" int vvb_event_sync(void* e) { CK(cudaEventSynchronize((cudaEvent_t)e)); return 0; }
+extern "C" int vvb_device_count(int* n) { CK(cudaGetDeviceCount(n)); return 0; }
+extern "C" int vvb_get_device(int* d) { CK(cudaGetDevice(d)); return 0; }
+extern "C" int vvb_set_device(int d) { CK(cudaSetDevice(d)); return 0; }
+extern "C" int vvb_enable_peer_access(int device, int peer)
+{
+    if (device == peer) return 0;
+    int can = 0, cur = 0;
+    CK(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return fail(6, "vvb_enable_peer_access", "devices are not peers");
+    CK(cudaGetDevice(&cur));
+    CK(cudaSetDevice(device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    cudaSetDevice(cur);
+    CK(e);
+    return 0;
+}
+extern "C" int vvb_memcpy_peer(void* d, int dd, const void* s, int sd, size_t n, void* st)
+{
+    CK(cudaMemcpyPeerAsync(d, dd, s, sd, n, (cudaStream_t)st)); return 0;
+}
+extern "C" int vvb_event_create_timing(void** e) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); *e = ev; return 0; }
+extern "C" int vvb_event_elapsed_ms(void* e0, void* e1, float* ms) { CK(cudaEventElapsedTime(ms, (cudaEvent_t)e0, (cudaEvent_t)e1)); return 0; }
+extern "C" int vvb_graph_capture_begin(void* st) { CK(cudaStreamBeginCapture((cudaStream_t)st, cudaStreamCaptureModeThreadLocal)); return 0; }
+extern "C" int vvb_graph_capture_end(void* st, void** exec)
+{
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    *exec = nullptr;
+    CK(cudaStreamEndCapture((cudaStream_t)st, &g));
+    cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    CK(e);
+    *exec = ge;
+    return 0;
+}
+extern "C" int vvb_graph_launch(void* exec, void* st) { CK(cudaGraphLaunch((cudaGraphExec_t)exec, (cudaStream_t)st)); return 0; }
+extern "C" int vvb_graph_destroy(void* exec) { if (exec) CK(cudaGraphExecDestroy((cudaGraphExec_t)exec)); return 0; }
 extern "C" int vvb_stream_wait_event(void* s, void* e) { CK(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0)); return 0; }
 #endif
 
@@ -397,6 +448,41 @@ extern "C" int vvb_stft_inverse_frames(vvb_engine* e, const vvb_cpx* d_spec, siz
     return 0;
 }
 
+/* marching / warp-specialised launch for one (fft_size, hop); -1 when there is none */
+static int launch_inverse_marching(vvb_engine* e, const InvArgs& a, long long batch, void* stream)
+{
+    int r = -1;
+    InvArgs am = a;
+    am.tables = e->d_tables_m;
+    if (e->nfft == 512 || e->nfft == 1024) r = tu_inv_march_small((int)e->nfft, e->hop, am, batch, e->sms, stream);
+    else if (e->nfft == 2048) {
+        if (!getenv("VVB_NO_WS")) r = tu_inv_ws_2048(e->hop, a, batch, e->sms, stream);
+        if (r < 0) r = tu_inv_march_2048(e->hop, a, batch, e->sms, stream);
+    }
+    else if (e->nfft == 4096) r = tu_inv_march_4096(e->hop, a, batch, e->sms, stream);
+    else if (e->nfft == 8192) r = tu_inv_march_8192(e->hop, a, batch, e->sms, stream);
+    return r;
+}
+
+/* One frame-range shard of a longer stream (see InvArgs::halo_frames): d_spec holds halo_frames + own frames. */
+extern "C" int vvb_stft_inverse_shard(vvb_engine* e, const vvb_cpx* d_spec, size_t frames, size_t halo_frames, int head_edge,
+                                      int tail_edge, size_t spec_pitch, float* d_y, size_t n_out, const float* d_inv_norm, void* stream)
+{
+    if (!e || !d_y || !d_spec) return fail(1, "vvb_stft_inverse_shard", "null");
+    if (frames == 0 || frames > 0x7fffffffu || halo_frames >= frames || n_out == 0) return fail(2, "vvb_stft_inverse_shard", "size");
+    if (halo_frames && head_edge) return fail(2, "vvb_stft_inverse_shard", "the first shard has no halo");
+    if (!e->fast) return fail(6, "vvb_stft_inverse_shard", "needs a marching kernel (fft_size 512 ... 8192)");
+    InvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.spec = reinterpret_cast<const float2*>(d_spec); a.spec_pitch = (long long)spec_pitch;
+    a.frames = (int)frames; a.hop = (int)e->hop;
+    a.y = d_y; a.y_pitch = (long long)((n_out + 1) & ~(size_t)1); a.n_out = (long long)n_out;
+    a.inv_norm = d_inv_norm; a.tables = e->d_tables;
+    a.halo_frames = (int)halo_frames; a.head_edge = head_edge ? 1 : 0; a.tail_edge = tail_edge ? 1 : 0;
+    const int r = launch_inverse_marching(e, a, 1, stream);
+    return r >= 0 ? r : fail(6, "vvb_stft_inverse_shard", "no marching kernel for this (fft_size, hop)");
+}
+
 extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t batch, size_t frames, size_t spec_pitch,
                                 float* d_y, size_t n_out, size_t y_pitch, const float* d_inv_norm, void* stream)
 {
@@ -415,22 +501,13 @@ extern "C" int vvb_stft_inverse(vvb_engine* e, const vvb_cpx* d_spec, size_t bat
         a.frames = (int)frames; a.hop = (int)e->hop;
         a.y = d_y; a.y_pitch = (long long)y_pitch; a.n_out = (long long)n_out;
         a.inv_norm = d_inv_norm; a.tables = e->d_tables;
+        a.halo_frames = 0; a.head_edge = 1; a.tail_edge = 1;          /* whole signals */
         if (e->d_tables_p && !getenv("VVB_NO_PAIR") && !getenv("VVB_NO_MARCH")) {
             const int r = tu_inv_pair((int)e->nfft, e->hop, a, (long long)batch, e->sms, e->d_tables_p, e->d_tables, stream);
             if (r >= 0) return r;
         }
-        const bool y_aligned = ((uintptr_t)d_y % 8 == 0) && (y_pitch % 2 == 0);   /* 64-bit stores */
-        if (y_aligned && !getenv("VVB_NO_MARCH")) {
-            int r = -1;
-            InvArgs am = a;
-            am.tables = e->d_tables_m;
-            if (e->nfft == 512 || e->nfft == 1024) r = tu_inv_march_small((int)e->nfft, e->hop, am, (long long)batch, e->sms, stream);
-            else if (e->nfft == 2048) {
-                if (!getenv("VVB_NO_WS")) r = tu_inv_ws_2048(e->hop, a, (long long)batch, e->sms, stream);
-                if (r < 0) r = tu_inv_march_2048(e->hop, a, (long long)batch, e->sms, stream);
-            }
-            else if (e->nfft == 4096) r = tu_inv_march_4096(e->hop, a, (long long)batch, e->sms, stream);
-            else if (e->nfft == 8192) r = tu_inv_march_8192(e->hop, a, (long long)batch, e->sms, stream);
+        if (!getenv("VVB_NO_MARCH")) {          /* (rows that are not 8-byte aligned are stored with 32-bit stores) */
+            const int r = launch_inverse_marching(e, a, (long long)batch, stream);
             if (r >= 0) return r;
         }
         return tu_inv_generic((int)(e->nfft / 2), true, a, (long long)batch, e->sms, stream);

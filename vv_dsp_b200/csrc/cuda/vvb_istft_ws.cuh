@@ -228,9 +228,11 @@ __global__ void __launch_bounds__(64 * NPAIR, 1) istft_ws_kernel(const InvArgs a
             const int b = (int)(g0 / F);
             const int f_begin = (int)(g0 - (long long)b * F);
             const int f_end = (int)min((long long)F, (long long)f_begin + (g1 - g0));
-            const int emit_end = (f_end == F) ? f_end + PERIOD - 1 : f_end;   /* hop-blocks [f_begin, emit_end) are ours */
+            const int emit_end = (f_end == F && a.tail_edge) ? f_end + PERIOD - 1 : f_end;   /* hop-blocks [f_begin, emit_end) are ours */
+            const int emit_begin = max(f_begin, a.halo_frames);        /* a shard's halo frames: overlap only (see InvArgs) */
             const int fr0 = f_begin - min(PERIOD - 1, f_begin);
             float* yb = a.y + (long long)b * a.y_pitch;
+            const bool y8 = (reinterpret_cast<uintptr_t>(yb) & 7) == 0;   /* 64-bit stores possible for this signal's row */
             g0 += f_end - f_begin;
 
             float2 acc[E];
@@ -258,9 +260,9 @@ __global__ void __launch_bounds__(64 * NPAIR, 1) istft_ws_kernel(const InvArgs a
                     for (int r = 0; r < 32; ++r)
                         acc[r] = __ffma2_rn(make_float2(v[r].y, v[r].x), wsyn2[t + T * r], acc[r]);
                 }
-                if (frame >= f_begin) {
-                    const long long base = (long long)frame * HOP;
-                    if (normalise && (frame < PERIOD - 1 || frame >= F)) {
+                if (frame >= emit_begin) {
+                    const long long base = (long long)(frame - a.halo_frames) * HOP;
+                    if (normalise && ((a.head_edge && frame < PERIOD - 1) || frame >= F)) {
                         /* edge block: undo the folded steady-state factor, apply this block's own 1/sum(w^2) */
                         const float* edge = (frame >= F) ? a.inv_norm + EDGE + HOP + (long long)(frame - F) * HOP
                                                          : a.inv_norm + (long long)frame * HOP;
@@ -275,8 +277,11 @@ __global__ void __launch_bounds__(64 * NPAIR, 1) istft_ws_kernel(const InvArgs a
 #pragma unroll
                     for (int r = 0; r < S; ++r) {
                         const long long tt = base + 2 * (t + T * r);
-                        if (tt + 1 < a.n_out) *reinterpret_cast<float2*>(yb + tt) = acc[r];
-                        else if (tt < a.n_out) yb[tt] = acc[r].x;
+                        if (y8 && tt + 1 < a.n_out) *reinterpret_cast<float2*>(yb + tt) = acc[r];
+                        else {                                             /* row not 8-byte aligned (odd pitch), or the last sample */
+                            if (tt < a.n_out) yb[tt] = acc[r].x;
+                            if (tt + 1 < a.n_out) yb[tt + 1] = acc[r].y;
+                        }
                     }
                 }
 #pragma unroll
@@ -284,8 +289,8 @@ __global__ void __launch_bounds__(64 * NPAIR, 1) istft_ws_kernel(const InvArgs a
 #pragma unroll
                 for (int r = E - S; r < E; ++r) acc[r] = make_float2(0.f, 0.f);
             }
-            if (f_end == F) {                                          /* nothing covers [cov, n_out): zeros */
-                const long long cov = (long long)(F - 1) * HOP + N;
+            if (f_end == F && a.tail_edge) {                           /* nothing covers [cov, n_out): zeros */
+                const long long cov = (long long)(F - 1 - a.halo_frames) * HOP + N;
                 for (long long tt = cov + t; tt < a.n_out; tt += T) yb[tt] = 0.f;
             }
         }

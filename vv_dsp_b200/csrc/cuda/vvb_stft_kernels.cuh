@@ -80,6 +80,15 @@ struct InvArgs {
     const float* inv_norm;   /* [head L | mid hop | tail L], L = N - hop; or nullptr = raw sum */
     const float* tables;
     int num_items, chunks_per_signal, chunk_frames;
+    /* frame-range shard of a longer stream (marching kernels only; whole signals: 0, 1, 1).  The first halo_frames
+     * rows of every signal's spectra belong to the PREVIOUS shard: they are synthesised only for their overlap into
+     * this shard's samples (the same halo re-synthesis a warp does when its range starts mid-signal), nothing is
+     * emitted for them and output position 0 is the first sample of frame halo_frames.  head_edge / tail_edge say
+     * whether the shard starts / ends at the true start / end of the stream: only there fewer than N/hop frames
+     * overlap (edge normalisation tables) and only at the true end the N - hop samples after the last frame's
+     * hop-block are emitted.  Every output sample is the same ascending-frame FMA chain as in the unsharded call,
+     * so shards concatenate to a bit-identical result. */
+    int halo_frames, head_edge, tail_edge;
 };
 
 /* edge-inclusive reflection of any index into [0, n): ... 1 0 | 0 1 .. n-1 | n-1 n-2 ...
@@ -938,10 +947,12 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
         const int b = (int)(g0 / F);
         const int f_begin = (int)(g0 - (long long)b * F);
         const int f_end = (int)min((long long)F, (long long)f_begin + (g1 - g0));
-        const int emit_end = (f_end == F) ? f_end + PERIOD - 1 : f_end;   /* hop-blocks [f_begin, emit_end) are ours */
+        const int emit_end = (f_end == F && a.tail_edge) ? f_end + PERIOD - 1 : f_end;   /* hop-blocks [f_begin, emit_end) are ours */
+        const int emit_begin = max(f_begin, a.halo_frames);            /* halo frames: overlap only, nothing emitted */
         const int fr0 = f_begin - min(PERIOD - 1, f_begin);            /* halo frames re-synthesised */
         const float2* specb = a.spec + (long long)b * F * a.spec_pitch;
         float* yb = a.y + (long long)b * a.y_pitch;
+        const bool y8 = (reinterpret_cast<uintptr_t>(yb) & 7) == 0;    /* 64-bit stores possible for this signal's row */
         g0 += f_end - f_begin;
 
         /* asynchronous copy of one frame's half spectrum X[0..M] into the team's staging buffer, issued right
@@ -1009,9 +1020,9 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
                         acc[sl] = __ffma2_rn(make_float2(z.y, z.x), wsyn2[t + T * sl], acc[sl]);   /* z is stored swapped */
                     }
             }
-            if (frame >= f_begin) {
-                const long long base = (long long)frame * HOP;
-                if (normalise && (frame < PERIOD - 1 || frame >= F)) {
+            if (frame >= emit_begin) {
+                const long long base = (long long)(frame - a.halo_frames) * HOP;
+                if (normalise && ((a.head_edge && frame < PERIOD - 1) || frame >= F)) {
                     /* edge block: fewer than PERIOD frames overlap; undo the folded steady-state factor and
                      * apply this block's own 1/sum(w^2) (head or tail table of InvArgs::inv_norm) */
                     const float* edge = (frame >= F) ? a.inv_norm + EDGE + HOP + (long long)(frame - F) * HOP
@@ -1027,8 +1038,11 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
 #pragma unroll
                 for (int r = 0; r < S; ++r) {
                     const long long tt = base + 2 * (t + T * r);
-                    if (tt + 1 < a.n_out) *reinterpret_cast<float2*>(yb + tt) = acc[r];
-                    else if (tt < a.n_out) yb[tt] = acc[r].x;
+                    if (y8 && tt + 1 < a.n_out) *reinterpret_cast<float2*>(yb + tt) = acc[r];
+                    else {                                             /* row not 8-byte aligned (odd pitch), or the last sample */
+                        if (tt < a.n_out) yb[tt] = acc[r].x;
+                        if (tt + 1 < a.n_out) yb[tt + 1] = acc[r].y;
+                    }
                 }
             }
             /* advance one hop: slot r now means what slot r+S meant (register moves; an unrolled ring
@@ -1040,8 +1054,8 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
         }
         cp_async_wait_all();                                           /* nothing in flight across pieces */
         team_sync<T>(team);
-        if (f_end == F) {                                              /* nothing covers [cov, n_out): zeros */
-            const long long cov = (long long)(F - 1) * HOP + N;
+        if (f_end == F && a.tail_edge) {                               /* nothing covers [cov, n_out): zeros */
+            const long long cov = (long long)(F - 1 - a.halo_frames) * HOP + N;
             for (long long tt = cov + t; tt < a.n_out; tt += T) yb[tt] = 0.f;
         }
     }

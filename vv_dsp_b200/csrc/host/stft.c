@@ -21,7 +21,7 @@
 #define NORM_CACHE 4
 #define NSLOT 4            /* slots 0,1: analysis (host -> device staging); slots 2,3: synthesis (device -> host) */
 #define NDEP 64            /* per-chunk completion events of the last stream-ordered analysis call */
-#define STAGE_TARGET_BYTES ((size_t)192 << 20)   /* per slot and direction */
+#define STAGE_TARGET_BYTES ((size_t)192 << 20)   /* per slot and direction (default; see stage_target below) */
 
 typedef struct stage_slot {
     void* stream;
@@ -34,6 +34,7 @@ struct vv_dsp_stft {
     vv_dsp_stft_window win_type;
     vv_dsp_real* win;                 /* host copy of the window (bit-identical to the reference's) */
     vvb_engine* eng;
+    int device;                       /* the CUDA device the handle was created on: every entry point runs there */
     void* own_stream;
     void* stream;                     /* own_stream or the caller's */
     /* per-frame staging */
@@ -46,6 +47,7 @@ struct vv_dsp_stft {
     int async;
     struct { const char* lo; const char* hi; void* ev; int valid; } dep[NDEP];
     int dep_next;
+    size_t stage_target;              /* staging bytes per slot and direction */
     /* log-mel chain: power scratch (grown on demand) and the last filterbank in device-sparse form */
     float* d_mel_scratch; size_t mel_scratch_bytes;
     mel_device mel; const float* mel_key_ptr; size_t mel_key_n; unsigned long long mel_key_hash;
@@ -63,6 +65,16 @@ static vv_dsp_status map_status(int st)
     if (st >= 1 && st <= 6 && st != 5) return (vv_dsp_status)st;
     return VV_DSP_ERROR_INTERNAL;
 }
+
+/* A handle lives on the device that was current when it was created.  Entry points switch to it when the caller's
+ * current device is another one and switch back before returning (multi-device callers: csrc/host/stream.c). */
+static int dev_enter(const vv_dsp_stft* h)
+{
+    int cur = -1;
+    if (!h || vvb_get_device(&cur) != 0 || cur == h->device) return -1;
+    return vvb_set_device(h->device) == 0 ? cur : -1;
+}
+static void dev_leave(int prev) { if (prev >= 0) vvb_set_device(prev); }
 
 const char* vv_dsp_b200_version(void) { return "vv-dsp_b200 0.1.0 (sm_100a)"; }
 const char* vv_dsp_b200_last_error(void) { return vvb_last_error(); }
@@ -104,6 +116,11 @@ vv_dsp_status vv_dsp_stft_create(const vv_dsp_stft_params* params, vv_dsp_stft**
     if (!h) return VV_DSP_ERROR_INTERNAL;
     h->nfft = params->fft_size; h->hop = params->hop_size; h->bins = h->nfft / 2 + 1;
     h->win_type = params->window;
+    h->stage_target = STAGE_TARGET_BYTES;
+    {   /* test hook: a small staging size makes a modest batch span many chunks (tests/test_gpu_parity.py) */
+        const char* env = getenv("VVB_STAGE_TARGET_BYTES");
+        if (env && atol(env) > 0) h->stage_target = (size_t)atol(env);
+    }
     h->win = (vv_dsp_real*)malloc(h->nfft * sizeof(vv_dsp_real));
     if (!h->win) { handle_free(h); return VV_DSP_ERROR_INTERNAL; }
     switch (params->window) {
@@ -113,7 +130,9 @@ vv_dsp_status vv_dsp_stft_create(const vv_dsp_stft_params* params, vv_dsp_stft**
     default: ws = VV_DSP_ERROR_OUT_OF_RANGE; break;
     }
     if (ws != VV_DSP_OK) { handle_free(h); return ws; }
-    st = vvb_engine_create(h->nfft, h->hop, h->win, &h->eng);
+    st = vvb_device_ready();                      /* 6 = no usable device: reported as UNSUPPORTED, never a CPU fallback */
+    if (!st) st = vvb_get_device(&h->device);
+    if (!st) st = vvb_engine_create(h->nfft, h->hop, h->win, &h->eng);
     if (!st) st = vvb_stream_create(&h->own_stream);
     h->stream = h->own_stream;
     if (!st) st = vvb_host_alloc((void**)&h->h_in, h->nfft * sizeof(float));
@@ -127,7 +146,7 @@ vv_dsp_status vv_dsp_stft_create(const vv_dsp_stft_params* params, vv_dsp_stft**
     return VV_DSP_OK;
 }
 
-vv_dsp_status vv_dsp_stft_destroy(vv_dsp_stft* h)
+static vv_dsp_status destroy_impl(vv_dsp_stft* h)
 {
     if (!h) return VV_DSP_ERROR_NULL_POINTER;     /* reference stft.c:63 */
     handle_free(h);
@@ -135,7 +154,7 @@ vv_dsp_status vv_dsp_stft_destroy(vv_dsp_stft* h)
 }
 
 /* ------------------------------------------------------------------ per-frame API */
-vv_dsp_status vv_dsp_stft_process(vv_dsp_stft* h, const vv_dsp_real* in, vv_dsp_cpx* out)
+static vv_dsp_status process_impl(vv_dsp_stft* h, const vv_dsp_real* in, vv_dsp_cpx* out)
 {
     int st;
     size_t k;
@@ -154,7 +173,7 @@ vv_dsp_status vv_dsp_stft_process(vv_dsp_stft* h, const vv_dsp_real* in, vv_dsp_
     return VV_DSP_OK;
 }
 
-vv_dsp_status vv_dsp_stft_reconstruct(vv_dsp_stft* h, const vv_dsp_cpx* in, vv_dsp_real* out_add, vv_dsp_real* norm_add)
+static vv_dsp_status reconstruct_impl(vv_dsp_stft* h, const vv_dsp_cpx* in, vv_dsp_real* out_add, vv_dsp_real* norm_add)
 {
     int st;
     size_t k, i;
@@ -200,7 +219,7 @@ vv_dsp_status vv_dsp_stft_set_stream(vv_dsp_stft* h, void* cuda_stream)
     return VV_DSP_OK;
 }
 
-vv_dsp_status vv_dsp_stft_synchronize(vv_dsp_stft* h)
+static vv_dsp_status synchronize_impl(vv_dsp_stft* h)
 {
     int i, st;
     if (!h) return VV_DSP_ERROR_NULL_POINTER;
@@ -214,7 +233,7 @@ vv_dsp_status vv_dsp_stft_synchronize(vv_dsp_stft* h)
 vv_dsp_status vv_dsp_stft_set_async(vv_dsp_stft* h, int enable)
 {
     if (!h) return VV_DSP_ERROR_NULL_POINTER;
-    if (h->async && !enable) { vv_dsp_status st = vv_dsp_stft_synchronize(h); if (st != VV_DSP_OK) return st; }
+    if (h->async && !enable) { vv_dsp_status st = synchronize_impl(h); if (st != VV_DSP_OK) return st; }
     h->async = enable ? 1 : 0;
     return VV_DSP_OK;
 }
@@ -225,6 +244,10 @@ static int dep_record(vv_dsp_stft* h, const void* lo, size_t bytes, void* stream
     int k = h->dep_next, st = 0;
     h->dep_next = (h->dep_next + 1) % NDEP;
     if (!h->dep[k].ev) st = vvb_event_create(&h->dep[k].ev);
+    /* the ring wrapped onto a chunk nobody has been told to wait for yet: a dependency is never dropped -- the
+     * host waits for that (NDEP chunks old, almost certainly finished) chunk, after which no consumer needs an
+     * event to read its range */
+    if (!st && h->dep[k].valid) { st = vvb_event_sync(h->dep[k].ev); h->dep[k].valid = 0; }
     if (!st) st = vvb_event_record(h->dep[k].ev, stream);
     h->dep[k].lo = (const char*)lo; h->dep[k].hi = (const char*)lo + bytes; h->dep[k].valid = !st;
     return st;
@@ -258,23 +281,24 @@ static int slot_reserve(stage_slot* s, size_t in_bytes, size_t out_bytes)
     return st;
 }
 
-static size_t chunk_signals(size_t batch, size_t bytes_per_signal)
+static size_t chunk_signals(const vv_dsp_stft* h, size_t batch, size_t bytes_per_signal)
 {
-    size_t c = bytes_per_signal ? STAGE_TARGET_BYTES / bytes_per_signal : batch;
+    size_t c = bytes_per_signal ? h->stage_target / bytes_per_signal : batch;
     if (c < 1) c = 1;
     if (c > batch) c = batch;
     return c;
 }
 
 /* ------------------------------------------------------------------ batched forward */
-vv_dsp_status vv_dsp_stft_batch_forward(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space,
+static vv_dsp_status batch_forward_impl(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space,
                                         size_t batch, size_t n, size_t signal_pitch,
                                         vv_dsp_frame_convention convention, vv_dsp_spec_kind kind, void* out,
                                         vv_dsp_mem_space out_space, size_t spec_pitch, size_t* out_frames)
 {
     size_t frames, esize, done;
-    int pad, st = 0, c = 0;
+    int pad, st = 0, c = 0, fast;
     if (!h || !signals || !out) return VV_DSP_ERROR_NULL_POINTER;
+    fast = vvb_engine_is_fast(h->eng);
     if ((unsigned)convention > 3u || (unsigned)kind > 2u || (unsigned)signals_space > 1u || (unsigned)out_space > 1u)
         return VV_DSP_ERROR_OUT_OF_RANGE;
     if (signal_pitch == 0) signal_pitch = n;
@@ -294,10 +318,12 @@ vv_dsp_status vv_dsp_stft_batch_forward(vv_dsp_stft* h, const vv_dsp_real* signa
     {
         const size_t in_per = (signals_space == VV_DSP_MEM_HOST) ? (n ? n : 1) * sizeof(float) : 0;
         const size_t out_per = (out_space == VV_DSP_MEM_HOST) ? frames * h->bins * esize : 0;
-        const size_t cs = chunk_signals(batch, in_per > out_per ? in_per : out_per);
+        const size_t cs = chunk_signals(h, batch, in_per > out_per ? in_per : out_per);
         if (!h->async) st = vvb_stream_sync(h->stream);   /* device-side operands may still be in flight */
         for (done = 0; done < batch && !st; done += cs, ++c) {
-            stage_slot* s = &h->slot[c % 2];
+            /* sizes without a Stockham kernel keep per-engine scratch buffers (chirp-z work buffer, synthesis frames):
+             * their chunks all run on ONE stream, in order, in both directions */
+            stage_slot* s = &h->slot[fast ? c % 2 : 0];
             const size_t nb = (batch - done < cs) ? batch - done : cs;
             const float* d_x;
             char* d_o;
@@ -383,14 +409,15 @@ static int norm_tables(vv_dsp_stft* h, size_t frames, const float** d_tab)
 }
 
 /* ------------------------------------------------------------------ batched inverse */
-vv_dsp_status vv_dsp_stft_batch_inverse(vv_dsp_stft* h, const vv_dsp_cpx* spectra, vv_dsp_mem_space spectra_space,
+static vv_dsp_status batch_inverse_impl(vv_dsp_stft* h, const vv_dsp_cpx* spectra, vv_dsp_mem_space spectra_space,
                                         size_t batch, size_t frames, size_t spec_pitch, vv_dsp_real* out,
                                         vv_dsp_mem_space out_space, size_t n_out, size_t out_pitch, int normalise)
 {
     const float* d_tab = NULL;
     size_t done;
-    int st = 0, c = 0;
+    int st = 0, c = 0, fast;
     if (!h || !out || (!spectra && frames)) return VV_DSP_ERROR_NULL_POINTER;
+    fast = vvb_engine_is_fast(h->eng);
     if ((unsigned)spectra_space > 1u || (unsigned)out_space > 1u) return VV_DSP_ERROR_OUT_OF_RANGE;
     if (spec_pitch == 0) spec_pitch = h->bins;
     if (out_pitch == 0) out_pitch = n_out;
@@ -404,10 +431,10 @@ vv_dsp_status vv_dsp_stft_batch_inverse(vv_dsp_stft* h, const vv_dsp_cpx* spectr
     {
         const size_t in_per = (spectra_space == VV_DSP_MEM_HOST) ? frames * h->bins * sizeof(vvb_cpx) : 0;
         const size_t out_per = (out_space == VV_DSP_MEM_HOST) ? n_out * sizeof(float) : 0;
-        const size_t cs = chunk_signals(batch, in_per > out_per ? in_per : out_per);
+        const size_t cs = chunk_signals(h, batch, in_per > out_per ? in_per : out_per);
         if (!h->async) st = vvb_stream_sync(h->stream);
         for (done = 0; done < batch && !st; done += cs, ++c) {
-            stage_slot* s = &h->slot[2 + c % 2];                       /* own streams: D2H overlaps the analysis H2D */
+            stage_slot* s = &h->slot[fast ? 2 + c % 2 : 0];            /* own streams: D2H overlaps the analysis H2D */
             const size_t nb = (batch - done < cs) ? batch - done : cs;
             const vvb_cpx* d_s;
             float* d_y;
@@ -507,8 +534,9 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
     per_signal = frames * h->bins * sizeof(float);
     cs = scratch_target / per_signal; if (cs < 1) cs = 1; if (cs > batch) cs = batch;
     stream = h->stream;
-    /* the device-sparse filterbank is cached per handle; fingerprint = pointer, size and a strided FNV-1a hash */
-    for (i = 0; i < n_mels * h->bins; i += 13) {
+    /* the device-sparse filterbank is cached per handle; fingerprint = pointer, size and an FNV-1a hash of EVERY weight
+     * (about 80 k words: negligible next to the kernels, and an in-place edit of any weight is seen) */
+    for (i = 0; i < n_mels * h->bins; ++i) {
         unsigned int bits; memcpy(&bits, filterbank_weights + i, sizeof(bits));
         hash = (hash ^ bits) * 1099511628211ull;
     }
@@ -516,7 +544,8 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
         st = vvb_stream_sync(stream);
         vvdsp_internal_mel_device_free(&h->mel);
         if (!st) st = vvdsp_internal_mel_device_build(filterbank_weights, n_mels, h->bins, stream, &h->mel);
-        h->mel_key_ptr = filterbank_weights; h->mel_key_n = n_mels; h->mel_key_hash = hash;
+        if (!st) { h->mel_key_ptr = filterbank_weights; h->mel_key_n = n_mels; h->mel_key_hash = hash; }
+        else { h->mel_key_ptr = NULL; h->mel_key_n = 0; }
     }
     if (!st && h->mel_scratch_bytes < cs * per_signal) {
         st = vvb_stream_sync(stream);
@@ -573,8 +602,11 @@ vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signal
                                        const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
                                        vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames)
 {
-    return batch_mel_chain(h, signals, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels, log_epsilon,
-                           0, 0.0f, out, out_space, out_frames);
+    const int prev = dev_enter(h);
+    const vv_dsp_status st = batch_mel_chain(h, signals, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels,
+                                             log_epsilon, 0, 0.0f, out, out_space, out_frames);
+    dev_leave(prev);
+    return st;
 }
 
 vv_dsp_status vv_dsp_stft_batch_mfcc(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch,
@@ -583,7 +615,93 @@ vv_dsp_status vv_dsp_stft_batch_mfcc(vv_dsp_stft* h, const vv_dsp_real* signals,
                                      size_t num_mfcc_coeffs, vv_dsp_real lifter_coeff,
                                      vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames)
 {
+    int prev;
+    vv_dsp_status st;
     if (num_mfcc_coeffs == 0) return VV_DSP_ERROR_INVALID_SIZE;
-    return batch_mel_chain(h, signals, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels, log_epsilon,
-                           num_mfcc_coeffs, lifter_coeff, out, out_space, out_frames);
+    prev = dev_enter(h);
+    st = batch_mel_chain(h, signals, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels, log_epsilon,
+                         num_mfcc_coeffs, lifter_coeff, out, out_space, out_frames);
+    dev_leave(prev);
+    return st;
 }
+
+/* ------------------------------------------------- one frame-range shard of a longer stream (include/vv_dsp/b200.h) */
+static vv_dsp_status shard_inverse_impl(vv_dsp_stft* h, const vv_dsp_cpx* spectra, size_t local_frames, size_t halo_frames,
+                                        int is_first, int is_last, vv_dsp_real* out, size_t n_out)
+{
+    const float* d_tab = NULL;
+    int st;
+    if (!h || !spectra || !out) return VV_DSP_ERROR_NULL_POINTER;
+    if (local_frames == 0 || halo_frames >= local_frames || n_out == 0) return VV_DSP_ERROR_INVALID_SIZE;
+    if (h->nfft % h->hop) return VV_DSP_ERROR_UNSUPPORTED;
+    if (halo_frames != (is_first ? 0 : h->nfft / h->hop - 1)) return VV_DSP_ERROR_INVALID_SIZE;
+    /* the edge tables depend on the frame count only when fewer than nfft/hop frames exist: a shard that carries its
+     * halo sees the same head / tail factors as the whole stream */
+    if (!is_first && local_frames - halo_frames < h->nfft / h->hop - 1) return VV_DSP_ERROR_INVALID_SIZE;
+    st = norm_tables(h, local_frames, &d_tab);
+    if (!st) st = vvb_stft_inverse_shard(h->eng, (const vvb_cpx*)spectra, local_frames, halo_frames, is_first, is_last, h->bins,
+                                         out, n_out, d_tab, h->stream);
+    return map_status(st);
+}
+
+/* ------------------------------------------------- public entry points: run on the handle's device */
+vv_dsp_status vv_dsp_stft_destroy(vv_dsp_stft* h)
+{
+    const int prev = dev_enter(h);
+    const vv_dsp_status st = destroy_impl(h);
+    dev_leave(prev);
+    return st;
+}
+vv_dsp_status vv_dsp_stft_process(vv_dsp_stft* h, const vv_dsp_real* in, vv_dsp_cpx* out)
+{
+    const int prev = dev_enter(h);
+    const vv_dsp_status st = process_impl(h, in, out);
+    dev_leave(prev);
+    return st;
+}
+vv_dsp_status vv_dsp_stft_reconstruct(vv_dsp_stft* h, const vv_dsp_cpx* in, vv_dsp_real* out_add, vv_dsp_real* norm_add)
+{
+    const int prev = dev_enter(h);
+    const vv_dsp_status st = reconstruct_impl(h, in, out_add, norm_add);
+    dev_leave(prev);
+    return st;
+}
+vv_dsp_status vv_dsp_stft_synchronize(vv_dsp_stft* h)
+{
+    const int prev = dev_enter(h);
+    const vv_dsp_status st = synchronize_impl(h);
+    dev_leave(prev);
+    return st;
+}
+vv_dsp_status vv_dsp_stft_batch_forward(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space,
+                                        size_t batch, size_t n, size_t signal_pitch,
+                                        vv_dsp_frame_convention convention, vv_dsp_spec_kind kind, void* out,
+                                        vv_dsp_mem_space out_space, size_t spec_pitch, size_t* out_frames)
+{
+    const int prev = dev_enter(h);
+    const vv_dsp_status st = batch_forward_impl(h, signals, signals_space, batch, n, signal_pitch, convention, kind, out, out_space,
+                                                spec_pitch, out_frames);
+    dev_leave(prev);
+    return st;
+}
+vv_dsp_status vv_dsp_stft_batch_inverse(vv_dsp_stft* h, const vv_dsp_cpx* spectra, vv_dsp_mem_space spectra_space,
+                                        size_t batch, size_t frames, size_t spec_pitch, vv_dsp_real* out,
+                                        vv_dsp_mem_space out_space, size_t n_out, size_t out_pitch, int normalise)
+{
+    const int prev = dev_enter(h);
+    const vv_dsp_status st = batch_inverse_impl(h, spectra, spectra_space, batch, frames, spec_pitch, out, out_space, n_out, out_pitch,
+                                                normalise);
+    dev_leave(prev);
+    return st;
+}
+vv_dsp_status vv_dsp_stft_shard_inverse(vv_dsp_stft* h, const vv_dsp_cpx* spectra, size_t local_frames, size_t halo_frames,
+                                        int is_first, int is_last, vv_dsp_real* out, size_t n_out)
+{
+    const int prev = dev_enter(h);
+    const vv_dsp_status st = shard_inverse_impl(h, spectra, local_frames, halo_frames, is_first, is_last, out, n_out);
+    dev_leave(prev);
+    return st;
+}
+int vv_dsp_stft_device(const vv_dsp_stft* h) { return h ? h->device : -1; }
+void* vv_dsp_stft_get_stream(const vv_dsp_stft* h) { return h ? h->stream : NULL; }
+const vv_dsp_real* vv_dsp_stft_window_ptr(const vv_dsp_stft* h) { return h ? h->win : NULL; }
