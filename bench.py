@@ -56,6 +56,27 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, read from the NEWEST ncu summary under
+    profiles/ (r*_ncu_full_*.csv: metric rows, one column per kernel) that has a column for it.  Returns (bytes, file)."""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_*.csv")), reverse=True):
+        try:
+            rows = [r for r in csv.reader(open(path)) if r and not r[0].startswith("#")]
+            hdr = rows[0]
+            cols = [i for i, h in enumerate(hdr) if kernel_substr in h]
+            if not cols:
+                continue
+            vals = {r[0]: (r[1], r[cols[0]]) for r in rows[1:] if len(r) > cols[0]}
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            rd, wr = vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"]
+            return float(rd[1]) * scale[rd[0]] + float(wr[1]) * scale[wr[0]], os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -100,9 +121,10 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference(threads, target_seconds):
+def cpu_reference(threads, target_seconds, signals=None):
     """Time the reference's CPU implementation of the step (process -> reconstruct -> normalise,
-    tools/dump_stft_roundtrip.c:44-54) on a bounded sample.  Returns (Msamples/s, info)."""
+    tools/dump_stft_roundtrip.c:44-54) on a bounded sample: `signals` signals of the headline shape if given, else as
+    many as fit target_seconds.  Returns (run() -> seconds, signals per run, kind, pilot seconds per signal and thread)."""
     import numpy as np
     from oracle.oracle import Oracle, Reference
     if Reference.available():
@@ -114,22 +136,40 @@ def cpu_reference(threads, target_seconds):
     t = time.perf_counter()
     impl.batch_roundtrip(pilot, NFFT, HOP, "hann", threads=threads, want_output=False)
     dt = time.perf_counter() - t
-    per_thread = max(1, min(64, int(target_seconds / max(dt, 1e-3))))
-    B = threads * per_thread
-    x = np.tile(pilot, (per_thread, 1)) if per_thread > 1 else pilot
+    if signals is None:
+        per_thread = max(1, min(64, int(target_seconds / max(dt, 1e-3))))
+        B = threads * per_thread
+    else:
+        B = int(signals)
+    reps = -(-B // threads)
+    x = np.tile(pilot, (reps, 1))[:B] if B != threads else pilot
 
     def run():
         t0 = time.perf_counter()
         impl.batch_roundtrip(x, NFFT, HOP, "hann", threads=threads, want_output=False)
         return time.perf_counter() - t0
+    run.pilot_seconds = dt
     return run, B, kind
 
 
 def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the step on this box's host cores (oracle/_ref =
+    the unmodified reference compiled by oracle/Makefile; the oracle port if that is absent).  One step = the SAME
+    workload as the GPU arm's step (1024 signals) whenever K + W such steps fit in about four minutes on this host;
+    otherwise a bounded sample of it (the metric is per-sample throughput on identical signal shapes)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    run, B, kind = cpu_reference(cores, target_seconds=max(2.0, 60.0 / max(1, args.steps + args.warmup)))
+    probe, _, _ = cpu_reference(cores, target_seconds=1.0)
+    est_full = probe.pilot_seconds * BATCH / cores                        # seconds per step of 1024 signals
+    nsteps = max(1, args.steps + args.warmup)
+    if est_full * nsteps <= 240.0:
+        run, B, kind = cpu_reference(cores, 0.0, signals=BATCH)
+        note = "same workload as the GPU arm's step"
+    else:
+        run, B, kind = cpu_reference(cores, target_seconds=max(2.0, 240.0 / nsteps))
+        note = (f"bounded sample: {BATCH} signals per step would take ~{est_full * nsteps:.0f} s for {nsteps} steps on {cores} cores; "
+                "throughput is per sample on identical signal shapes")
     for _ in range(args.warmup):
         run()
     times = [run() for _ in range(args.steps)]
@@ -139,8 +179,10 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nfft": NFFT, "hop": HOP, "window": "hann", "signal_samples": N_SAMPLES,
-                   "sample_signals_per_step": B, "note": "CPU reference path on the box's host cores, one vv_dsp_stft handle per thread"},
+        "config": {"workload": WORKLOAD, "nfft": NFFT, "hop": HOP, "window": "hann", "signals_per_gpu": BATCH,
+                   "signal_samples": N_SAMPLES, "frames_per_signal": FRAMES, "bins": BINS,
+                   "sample_signals_per_step": B, "sample_note": note,
+                   "note": "CPU reference path on the box's host cores, one vv_dsp_stft handle per thread"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{B} signals x {N_SAMPLES} samples per step, STFT->ISTFT->normalise loop of tools/dump_stft_roundtrip.c:44-54"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -218,8 +260,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG is left as the launcher set it (the driver reads communicator ranks from it); NCCL logs to
-        # stderr / NCCL_DEBUG_FILE, stdout carries the one JSON line
+        # NCCL_DEBUG is left as the launcher set it (the driver reads communicator ranks from it); NCCL's own log
+        # lines go to stderr so that stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     # CPU-side rendezvous for the phases in which ONE rank drives every GPU (the config-4 stream leg): the other
     # ranks must wait on the host, not inside an NCCL kernel on a GPU that rank 0 is using
@@ -357,10 +400,9 @@ def main():
         hbm_peak, peak_src = measured_peaks()
         bytes_fwd = B * (4 * N_SAMPLES + 8 * FRAMES * BINS)       # read samples once + write half spectra once
         bytes_inv = B * (8 * FRAMES * BINS + 4 * N_SAMPLES)
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_ncu_full_v6_packed_tma_kernels.csv
-        # (same shape, same kernels): equal to the algorithmic bytes, i.e. no re-reads
-        NCU_TRAFFIC = {"istft_ws_kernel": 7.872063e9 + 1.953476e9, "stft_march_kernel": 1.973042e9 + 7.786636e9}
         dom = ("istft_ws_kernel", inv_ms, bytes_inv) if inv_ms >= fwd_ms else ("stft_march_kernel", fwd_ms, bytes_fwd)
+        # measured DRAM traffic of that kernel at this shape: the newest ncu --set full summary committed under profiles/
+        traffic, traffic_file = ncu_traffic(dom[0]) if B == BATCH else (None, None)
         achieved = dom[2] / (dom[1] * 1e-3) / 1e9
         flops_dir = B * FRAMES * 5 * NFFT * 11                     # 5 N log2 N per frame per direction
         line = {
@@ -373,7 +415,7 @@ def main():
                        "parallelism": f"shard-by-signal x{world}, no collective"},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
-                         "traffic": NCU_TRAFFIC[dom[0]] if B == BATCH else None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_file, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom[2], "ms_per_launch": dom[1]},
             "kernels": {"stft_forward_ms": fwd_ms, "stft_inverse_ms": inv_ms, "stft_forward_power_ms": pow_ms,
                         "stft_forward_GBps": bytes_fwd / (fwd_ms * 1e-3) / 1e9, "stft_inverse_GBps": bytes_inv / (inv_ms * 1e-3) / 1e9,
@@ -400,6 +442,10 @@ def main():
             line["cpu_baseline"] = {"value": Bc * N_SAMPLES / dt / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{Bc} signals x {N_SAMPLES} samples, STFT->ISTFT->normalise loop of "
                                               f"tools/dump_stft_roundtrip.c:44-54, one handle per thread, {dt:.1f} s"}
+            run1, B1, _ = cpu_reference(1, target_seconds=4.0)        # also on ONE thread
+            dt1 = run1()
+            line["cpu_baseline_1thread"] = {"value": B1 * N_SAMPLES / dt1 / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
+                                            "sample": f"{B1} signals x {N_SAMPLES} samples, same loop, {dt1:.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -2,6 +2,7 @@
 #ifndef VV_DSP_H
 #define VV_DSP_H
 #include "vv_dsp/vv_dsp_types.h"
+#include "vv_dsp/vv_dsp_math.h"
 #include "vv_dsp/core.h"
 #include "vv_dsp/window.h"
 #include "vv_dsp/spectral.h"

@@ -53,7 +53,9 @@ int vvb_device_count(int* count);
 int vvb_get_device(int* device);
 int vvb_set_device(int device);
 int vvb_enable_peer_access(int device, int peer);   /* device may then read / write peer's memory; 0 also when already on or device == peer */
-int vvb_memcpy_peer(void* dst, int dst_device, const void* src, int src_device, size_t bytes, void* stream);
+/* dst_left[i] = src_left[i], dst_right[i] = src_right[i], i < count, by a kernel on the current device; the sources may be
+ * memory of a peer device (vvb_enable_peer_access) -- the halo exchange of stream.c.  Either pair may be NULL. */
+int vvb_halo_gather(float* dst_left, const float* src_left, float* dst_right, const float* src_right, size_t count, void* stream);
 int vvb_event_create_timing(void** ev);
 int vvb_event_elapsed_ms(void* ev_start, void* ev_end, float* ms);
 /* capture what is enqueued on `stream` between begin and end into an executable graph; 6 = not supported here */

@@ -7,6 +7,7 @@ import pytest
 
 import parity_cases as pc
 from _util import ROUNDTRIP_REL_L2, noise, rel_l2, spectra_close
+from vv_dsp_b200 import Stft
 
 pytestmark = pytest.mark.gpu
 

@@ -65,7 +65,6 @@ extern "C" int vvb_device_count(int* n) { *n = 1; return 0; }
 extern "C" int vvb_get_device(int* d) { *d = 0; return 0; }
 extern "C" int vvb_set_device(int) { return 0; }
 extern "C" int vvb_enable_peer_access(int, int) { return 0; }
-extern "C" int vvb_memcpy_peer(void* d, int, const void* s, int, size_t n, void*) { memcpy(d, s, n); return 0; }
 extern "C" int vvb_event_create_timing(void** e) { *e = malloc(1); return 0; }
 extern "C" int vvb_event_elapsed_ms(void*, void*, float* ms) { *ms = 0.f; return 0; }
 extern "C" int vvb_graph_capture_begin(void*) { return 6; }
@@ -131,10 +130,6 @@ extern "C" int vvb_enable_peer_access(int device, int peer)
     cudaSetDevice(cur);
     CK(e);
     return 0;
-}
-extern "C" int vvb_memcpy_peer(void* d, int dd, const void* s, int sd, size_t n, void* st)
-{
-    CK(cudaMemcpyPeerAsync(d, dd, s, sd, n, (cudaStream_t)st)); return 0;
 }
 extern "C" int vvb_event_create_timing(void** e) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); *e = ev; return 0; }
 extern "C" int vvb_event_elapsed_ms(void* e0, void* e1, float* ms) { CK(cudaEventElapsedTime(ms, (cudaEvent_t)e0, (cudaEvent_t)e1)); return 0; }
@@ -860,6 +855,28 @@ extern "C" int vvb_fp32_peak(int packed, double* tflops)
     *tflops = best;
     return 0;
 #endif
+}
+
+/* ---------------------------------------------------------------- halo gather (one stream over several GPUs) */
+/* The two sample halos of a frame-range shard, fetched by the shard's OWN device with plain loads from its neighbours'
+ * memory (peer access over NVLink; the same pointers work when both shards live on one device).  A kernel, not a
+ * copy-engine transfer: 12 KB per halo is latency-, not bandwidth-bound, and a kernel node replays inside the step's
+ * CUDA graph. */
+__global__ void __launch_bounds__(256) halo_gather_kernel(float* dst_left, const float* src_left, float* dst_right, const float* src_right,
+                                                        long long count)
+{
+    const float* src = blockIdx.y ? src_right : src_left;
+    float* dst = blockIdx.y ? dst_right : dst_left;
+    if (!src || !dst) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+extern "C" int vvb_halo_gather(float* dst_left, const float* src_left, float* dst_right, const float* src_right, size_t count, void* stream)
+{
+    if (count == 0 || (!dst_left && !dst_right)) return 0;
+    const int blocks = (int)std::min<size_t>((count + 255) / 256, 16);
+    VVB_LAUNCH(halo_gather_kernel, dim3(blocks, 2), 256, 0, stream, dst_left, src_left, dst_right, src_right, (long long)count);
+    return 0;
 }
 
 /* ---------------------------------------------------------------- SM clock probe */

@@ -531,6 +531,98 @@ template <class C> VVB_DEV void team_fft_auto(float2 (&v)[C::E], float2* xb, con
     }
 }
 
+/* ---- three-pass configurations (M = R1 R2 R3, T a multiple of R1, T E / R3 = R1 R2): inter-pass twiddles computed.
+ * Pass 2 (radix R2, Ns = R1): the twiddle index (t + T q) mod R1 = t mod R1 does not depend on the sub-transform q, so a
+ * thread needs R2 - 1 twiddles in all: powers of ONE base, W_{R1 R2}^{t mod R1}.
+ * Pass 3 (radix R3, Ns = R1 R2): the index is t + T q itself, W_M^{r (t + T q)} = W_M^{r t} x W_M^{r T q}: powers of one
+ * per-thread base times compile-time rotations (as apply_tw_all_q does for the two-pass configurations).
+ * The table version loads (R2 - 1) + (R3 - 1) E / R3 twiddles per thread and transform (35 LDS.64 at fft_size 4096, where
+ * the kernels are bound by shared-memory wavefronts: two exchanges of the whole transform per frame); this one loads the
+ * power-of-two bases (3 + 3 at radix 8) and spends packed FP32 instructions, of which there are plenty to spare. */
+template <class C, int RADIX, int Q, int R> VVB_DEV float2 tw_power_rot(const TwBase& b)
+{
+    if constexpr (Q == 0) {
+        return tw_power<R>(b);
+    } else {
+        constexpr int K = (R * C::T * Q) % C::M;
+        return cmul(tw_power<R>(b), make_float2(TwC<C::M, K>::c, -TwC<C::M, K>::s));
+    }
+}
+template <class C, int RADIX, int Q, int... Rs> VVB_DEV void apply_tw_rot_q(float2* v, const TwBase& b, iseq<Rs...>)
+{
+    ((v[Rs + 1] = cmul(v[Rs + 1], tw_power_rot<C, RADIX, Q, Rs + 1>(b))), ...);
+}
+template <class C, int RADIX, int... Qs> VVB_DEV void apply_tw_rot_all(float2* v, const TwBase& b, iseq<Qs...>)
+{
+    (apply_tw_rot_q<C, RADIX, Qs>(v + Qs * RADIX, b, typename make_iseq<RADIX - 1>::type{}), ...);
+}
+/* the same power for every sub-transform q (pass 2) */
+template <int NQ, int RADIX, int R> VVB_DEV void apply_tw_same_one(float2* v, const TwBase& b)
+{
+    const float2 w = tw_power<R>(b);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q * RADIX + R] = cmul(v[q * RADIX + R], w);
+}
+template <int NQ, int RADIX, int... Rs> VVB_DEV void apply_tw_same(float2* v, const TwBase& b, iseq<Rs...>)
+{
+    (apply_tw_same_one<NQ, RADIX, Rs + 1>(v, b), ...);
+}
+template <class C, class Hook = NoHook>
+VVB_DEV void team_fft_tw3(float2 (&v)[C::E], float2* xb, const float2* s_tw2, const float2* s_tw3, int t, int team, Hook after_last_read = Hook())
+{
+    static_assert(C::NP == 3 && C::T % C::R1 == 0 && C::T * (C::E / C::R3) == C::R1 * C::R2 && C::R2 <= 32 && C::R3 <= 32, "see above");
+    stockham_pass<C, C::R1, 1, true, false>(v, xb, nullptr, t, team);
+    {   /* pass 2 */
+        constexpr int R = C::R2, NS = C::R1, NQ = C::E / R, STRIDE = C::M / R;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[q * R + r] = xb[C::pad(t + C::T * q + r * STRIDE)];
+        team_sync<C::T>(team);
+        TwBase b;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) b.w[j] = ((1 << j) < R) ? s_tw2[((1 << j) - 1) * NS + (t % NS)] : make_float2(1.f, 0.f);
+        apply_tw_same<NQ, R>(v, b, typename make_iseq<R - 1>::type{});
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) fft_reg<R, 0>(&v[q * R]);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int j = t + C::T * q;
+            const int j0 = (j / NS) * NS * R + (j % NS);
+#pragma unroll
+            for (int r = 0; r < R; ++r) xb[C::pad(j0 + r * NS)] = v[q * R + r];
+        }
+        team_sync<C::T>(team);
+    }
+    {   /* pass 3 */
+        constexpr int R = C::R3, NS = C::R1 * C::R2, NQ = C::E / R, STRIDE = C::M / R;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[q * R + r] = xb[C::pad(t + C::T * q + r * STRIDE)];
+        team_sync<C::T>(team);
+        after_last_read();
+        TwBase b;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) b.w[j] = ((1 << j) < R) ? s_tw3[((1 << j) - 1) * NS + t] : make_float2(1.f, 0.f);
+        apply_tw_rot_all<C, R>(v, b, typename make_iseq<NQ>::type{});
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) fft_reg<R, 0>(&v[q * R]);
+    }
+}
+
+#ifndef VVB_TW3_COMPUTE
+#define VVB_TW3_COMPUTE 1             /* marching kernels, three-pass configurations: 1 = computed inter-pass twiddles, 0 = tables */
+#endif
+/* marching kernels: the three-pass transform with computed twiddles where the configuration allows it */
+template <class C, bool COMPUTE = true> VVB_DEV void team_fft_march(float2 (&v)[C::E], float2* xb, const float2* s_tw2, const float2* s_tw3, int t, int team)
+{
+    if constexpr (VVB_TW3_COMPUTE && COMPUTE && C::NP == 3 && C::T % C::R1 == 0 && C::T * (C::E / C::R3) == C::R1 * C::R2 && C::R2 <= 32 && C::R3 <= 32)
+        team_fft_tw3<C>(v, xb, s_tw2, s_tw3, t, team);
+    else
+        team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+}
+
 template <class C> struct LastPass {
     static constexpr int R = (C::NP == 2) ? C::R2 : C::R3;
     static constexpr int NS = C::M / R;

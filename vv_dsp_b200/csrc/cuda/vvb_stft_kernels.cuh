@@ -557,7 +557,9 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
                 }
                 team_sync<T>(team);                                    /* xb is reused by the next frame */
             } else {
-                team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+                /* computed inter-pass twiddles, same-box A/B (1024 x 480000 samples): fft_size 4096 complex 2.528 -> 2.472 ms,
+                 * power 2.218 -> 2.263 ms; fft_size 8192 complex unchanged, power 2.476 -> 2.619 ms: kept where they pay */
+                team_fft_march<C, (OUT == OUT_COMPLEX && C::M == 2048)>(v, xb, s_tw2, s_tw3, t, team);
                 /* computed split twiddles help at fft_size 4096 (2.94 -> 2.86 ms) and hurt at 8192 (3.24 -> 3.75 ms) */
                 /* (fft_size 8192 with power / magnitude output is the one case measured slower with the half exchange:
                  * 2.46 -> 2.58 ms, while its complex output gains 8 %) */
@@ -1009,7 +1011,7 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
                 prefetch(frame + 1, off_next, bulk_next);
                 if constexpr (REGTW) team_fft_regtw<C>(v, xb, twb, t, team);
                 else if constexpr (VVB_INV_BASETW && C::T == 32 && C::R1 == 32 && C::R2 == 32 && C::NP == 2) team_fft_basetw<C>(v, xb, s_tw2, t, team);
-                else team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+                else team_fft_march<C>(v, xb, s_tw2, s_tw3, t, team);   /* three passes: computed twiddles (fft_size 4096: 2.576 -> 2.522 ms, 8192: 2.830 -> 2.581 ms) */
                 /* v[q*RL + r] is sample pair i = t + T*(q + NQ*r): accumulate into that slot */
 #pragma unroll
                 for (int q = 0; q < L::NQ; ++q)

@@ -9,7 +9,8 @@
  * Here every device runs the two fused kernels of the batched path on its own frame range; the coupling at a
  * shard boundary is carried by sample halos (see b200.h): each shard recomputes the K-1 frames in front of its
  * range from its left halo, so synthesis needs no exchange and is bit-identical to the unsharded call.  Per
- * step and device: two peer-to-peer copies of nfft - hop floats (cudaMemcpyPeerAsync over NVLink), the analysis
+ * step and device: one small kernel that loads the two halos of nfft - hop floats from the neighbours' memory
+ * (peer-to-peer over NVLink), the analysis
  * kernel, the synthesis kernel -- enqueued on the device's own stream, replayed as one CUDA graph per device
  * after the first step.  The devices never wait for one another inside a step: the halos are read from the
  * neighbours' owned INPUT samples, which no step writes.
@@ -183,20 +184,22 @@ vv_dsp_status vv_dsp_stft_stream_upload(vv_dsp_stft_stream* s, const vv_dsp_real
     return vv_dsp_stft_stream_synchronize(s);
 }
 
-/* the two halos of shard d: the last nfft-hop owned samples of d-1 and the first nfft-hop owned samples of d+1 */
+/* the two halos of shard d: the last nfft-hop owned samples of d-1 and the first nfft-hop owned samples of d+1, read
+ * straight from the neighbours' memory by a small kernel on d's own device (peer-to-peer loads over NVLink) */
 static int enqueue_halos(vv_dsp_stft_stream* s, size_t d)
 {
     shard* k = &s->sh[d];
-    int st = 0;
+    float *dl = NULL, *dr = NULL;
+    const float *sl = NULL, *sr = NULL;
     if (k->lh) {
         const shard* l = &s->sh[d - 1];
-        st = vvb_memcpy_peer(k->d_x, k->device, l->d_x + l->lh + (l->s1 - l->s0) - s->halo, l->device, s->halo * sizeof(float), k->stream);
+        dl = k->d_x; sl = l->d_x + l->lh + (l->s1 - l->s0) - s->halo;
     }
-    if (!st && k->rh) {
+    if (k->rh) {
         const shard* r = &s->sh[d + 1];
-        st = vvb_memcpy_peer(k->d_x + k->lh + (k->s1 - k->s0), k->device, r->d_x + r->lh, r->device, s->halo * sizeof(float), k->stream);
+        dr = k->d_x + k->lh + (k->s1 - k->s0); sr = r->d_x + r->lh;
     }
-    return st;
+    return vvb_halo_gather(dl, sl, dr, sr, s->halo, k->stream);
 }
 
 static int enqueue_forward(vv_dsp_stft_stream* s, size_t d)
