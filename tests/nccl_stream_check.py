@@ -39,6 +39,12 @@ def main():
             rt = float(torch.linalg.vector_norm((y[lo - s0: hi - s0] - x[lo:hi]).double()) / torch.linalg.vector_norm(x[lo:hi].double()))
             assert rel < 2e-6, rel
             assert rt < 1e-5, rt
+            # the halo scheme of the C library (vv_dsp_stft_shard_inverse): bit-identical to the unsharded call
+            hs = sharding.stream_stft_halo(h, x[s0:s1].contiguous(), n)
+            hf = nfft // hop - 1 if rank else 0
+            yh = sharding.stream_istft_halo(h, hs, n)
+            torch.cuda.synchronize()
+            assert torch.equal(hs[hf:], whole[f0:f1]) and torch.equal(yh, ywhole[s0:s1]), "halo-scheme shard differs from the unsharded call"
             if rank == 0:
                 print(f"nccl stream sharding ok: nfft={nfft} hop={hop} n={n} world={world} frames={frames} "
                       f"vs-unsharded {rel:.2e} round-trip {rt:.2e}", flush=True)

@@ -559,6 +559,13 @@ class Stft:
         _check(self.lib, st, "vv_dsp_stft_shard_inverse")
         return out
 
+    def shard_inverse_raw(self, spectra, halo_frames, is_first, is_last, out):
+        """the same through raw pointers (numpy arrays standing in for device memory: emulator library only)"""
+        st = self.lib.vv_dsp_stft_shard_inverse(self._h, _ptr(spectra), int(spectra.shape[0]), int(halo_frames), int(bool(is_first)),
+                                                int(bool(is_last)), _ptr(out), int(out.size))
+        _check(self.lib, st, "vv_dsp_stft_shard_inverse")
+        return out
+
     def istft(self, half_spectra, n_out):
         half_spectra = np.ascontiguousarray(half_spectra, np.complex64)
         out = np.empty(n_out, np.float32)

@@ -4,16 +4,22 @@ torch.distributed for the plumbing (NCCL over NVLink on the B200 box, gloo in th
 * Batched independent signals: `shard_batch` -- contiguous ranges of the batch per rank, no
   communication at all.
 * One long stream: `stream_stft` / `stream_istft` -- rank d owns frames [F*d/G, F*(d+1)/G) and
-  the samples [f0*hop, f1*hop) (the last rank up to n).  Analysis needs the first nfft-hop
-  samples of the right neighbour (one point-to-point "halo" message, 12 KB at nfft=4096/hop=1024).
-  Synthesis runs the fused, normalised ISTFT kernel on the local frames, then sends the trailing
-  nfft-hop partial sums to the right neighbour, which adds them to its head and renormalises
-  those nfft-hop samples with the global window-sum; everything else is already final.
+  the samples [f0*hop, f1*hop) (the last rank up to n).  This is the multi-process flavour of the C
+  library's vv_dsp_stft_stream_* handle (include/vv_dsp/b200.h) and uses the same scheme: the only
+  communication is two sample halos of nfft-hop floats per boundary (12 KB at nfft=4096/hop=1024), one
+  from each neighbour; the LEFT halo makes a rank also compute the nfft/hop-1 frames in front of its
+  range, which the synthesis kernel (vv_dsp_stft_shard_inverse) re-synthesises for their overlap into
+  the rank's first samples.  No partial sums are exchanged and the ranks' outputs concatenate to the
+  bit-identical result of the unsharded call.  (Sizes without a marching kernel -- hop not dividing
+  nfft, nfft outside 512..8192 -- fall back to the round-1 scheme: right halo only, trailing partial
+  sums sent to the right neighbour, which adds and renormalises; equal to rounding, not bit for bit.)
 
 The functions take a `vv_dsp_b200.Stft` handle; tensors may be CUDA tensors (device-resident
 path) or CPU tensors (host-staged path).
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -67,6 +73,54 @@ def _exchange(send_to: int | None, send_buf: torch.Tensor | None, recv_from: int
     if ops:
         for r in dist.batch_isend_irecv(ops):
             r.wait()
+
+
+def halo_mode(nfft: int, hop: int) -> bool:
+    """True when (nfft, hop) has a marching synthesis kernel with shard mode (include/vv_dsp/b200.h)"""
+    return nfft in (512, 1024, 2048, 4096, 8192) and hop in (nfft // 8, nfft // 4, nfft // 2)
+
+
+def _is_emulator(h) -> bool:
+    return "emu" in os.path.basename(getattr(h.lib, "path", ""))
+
+
+def stream_stft_halo(h, x_owned: torch.Tensor, n: int, group=None) -> torch.Tensor:
+    """Analysis of this rank's shard, halo scheme: returns [halo_frames + own frames, bins] complex64 (the halo rows,
+    nfft/hop - 1 of them on every rank but the first, duplicate the previous rank's last frames)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nfft, hop = h.nfft, h.hop
+    frames = 0 if n < nfft else 1 + (n - nfft) // hop
+    halo = nfft - hop
+    assert frames // world >= nfft // hop, "every shard must hold at least nfft/hop frames"
+    dev = x_owned.device
+    left = torch.empty(halo, dtype=torch.float32, device=dev) if rank > 0 else None
+    right = torch.empty(halo, dtype=torch.float32, device=dev) if rank < world - 1 else None
+    if world > 1:
+        ops = []
+        if rank > 0:                     # my first samples are the left neighbour's right halo; its last ones my left halo
+            ops += [dist.P2POp(dist.isend, x_owned[:halo].contiguous(), rank - 1, group), dist.P2POp(dist.irecv, left, rank - 1, group)]
+        if rank < world - 1:
+            ops += [dist.P2POp(dist.isend, x_owned[-halo:].contiguous(), rank + 1, group), dist.P2POp(dist.irecv, right, rank + 1, group)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    local = torch.cat([t for t in (left, x_owned, right) if t is not None])
+    return _from_lib(h.batch_forward(_as_lib(local[None, :].contiguous()), "complex", "valid"), local)[0]
+
+
+def stream_istft_halo(h, spec_local: torch.Tensor, n: int, group=None) -> torch.Tensor:
+    """Synthesis of this rank's shard from stream_stft_halo's layout: the rank's owned samples, bit-identical to the
+    same samples of the unsharded call.  No communication."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nfft, hop = h.nfft, h.hop
+    s0, s1 = owned_samples(n, nfft, hop, world, rank)
+    halo_frames = nfft // hop - 1 if rank > 0 else 0
+    if spec_local.is_cuda:
+        return h.shard_inverse(spec_local.contiguous(), halo_frames, rank == 0, rank == world - 1, s1 - s0)
+    if _is_emulator(h):                                  # CPU tests: the emulator's "device" memory is host memory
+        out = np.empty(s1 - s0, np.float32)
+        h.shard_inverse_raw(np.ascontiguousarray(spec_local.numpy()), halo_frames, rank == 0, rank == world - 1, out)
+        return torch.from_numpy(out)
+    return h.shard_inverse(spec_local.cuda().contiguous(), halo_frames, rank == 0, rank == world - 1, s1 - s0).cpu()
 
 
 def stream_stft(h, x_owned: torch.Tensor, n: int, kind: str = "complex", group=None) -> torch.Tensor:
