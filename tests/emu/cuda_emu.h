@@ -201,3 +201,4 @@ static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline void sincospi(double x, double *s, double *c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }

@@ -173,6 +173,33 @@ def check_fft_plans(lib, oracle, sizes):
         assert np.abs(back - x).max() < 1e-5
 
 
+def check_fft_large(lib, oracle, sizes):
+    """Plan API at powers of two above 8192 (four-step kernels).  The reference's radix-2 loop carries a float32 twiddle
+    recurrence whose error grows with n (4.3e-5 of max|X| at 8192), so the yardstick is float64
+    truth: this library within 2e-6 of it, and within the triangle bound (own error + the oracle's) of the oracle."""
+    rng = np.random.default_rng(31)
+    report = {}
+    for n in sizes:
+        x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+        xr = rng.uniform(-1, 1, n).astype(np.float32)
+        for direction, truth in ((+1, np.fft.fft(x.astype(np.complex128))), (-1, np.fft.ifft(x.astype(np.complex128)))):
+            got = FftPlan(n, 0, direction, lib=lib).execute(x)
+            ref = oracle.fft_c2c(x, direction)
+            mx = np.abs(truth).max()
+            mine, theirs = np.abs(got - truth).max() / mx, np.abs(ref - truth).max() / mx
+            assert mine < 2e-6, (n, direction, mine)
+            assert np.abs(got - ref).max() / mx <= mine + theirs + 1e-7
+            report[(n, direction)] = (float(mine), float(theirs))
+        r = FftPlan(n, 1, +1, lib=lib).execute(xr)
+        tr = np.fft.rfft(xr.astype(np.float64))
+        assert np.abs(r - tr).max() / np.abs(tr).max() < 2e-6 and r[-1].imag == 0.0 and r.shape == (n // 2 + 1,)
+        c = FftPlan(n, 2, -1, lib=lib).execute(r)
+        assert np.abs(c - xr).max() < 1e-5, (n, np.abs(c - xr).max())
+        back = FftPlan(n, 0, -1, lib=lib).execute(FftPlan(n, 0, +1, lib=lib).execute(x))
+        assert np.abs(back - x).max() < 1e-5
+    return report
+
+
 def check_fft_batch(lib, oracle, sizes, batch=5):
     """vv_dsp_fft_execute_batch == looping vv_dsp_fft_execute == the oracle, transform by transform"""
     rng = np.random.default_rng(11)

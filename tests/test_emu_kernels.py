@@ -71,6 +71,13 @@ def test_fft_plans(emu, oracle):
     pc.check_fft_plans(emu, oracle, [1, 2, 3, 8, 16, 100, 128, 256, 1024, 2048, 8192])    # 8192: three-pass C2C, 256-thread team
 
 
+def test_fft_four_step(emu, oracle):
+    """powers of two above 8192: two batched Stockham plans + transposes (the reference runs its radix-2 loop at any
+    power of two, src/spectral/fft_kiss.c:108-116); C2C both directions, R2C, C2R"""
+    pc.check_fft_plans(emu, oracle, [16384])
+    pc.check_fft_large(emu, oracle, [16384, 32768])
+
+
 def test_fft_execute_batch(emu, oracle):
     pc.check_fft_batch(emu, oracle, [1, 8, 100, 128, 256, 1024])
 

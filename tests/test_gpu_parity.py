@@ -314,6 +314,13 @@ def test_mel_chain_device_buffers(lib, oracle):
         assert mf_dev.cpu().numpy().tobytes() == mf_host.tobytes()
 
 
+def test_fft_four_step_sizes(lib, oracle):
+    """plan API above 8192: four-step C2C / R2C / C2R against the oracle (whose power-of-two path is the radix-2 loop)"""
+    pc.check_fft_plans(lib, oracle, [16384])
+    print("error vs float64 truth (mine, reference):", pc.check_fft_large(lib, oracle, [16384, 32768, 65536, 1 << 20, 1 << 22]))
+    pc.check_fft_batch(lib, oracle, [16384], batch=3)
+
+
 def test_reconstruct_non_hermitian(lib, oracle):
     pc.check_reconstruct_non_hermitian(lib, oracle)
 

@@ -536,7 +536,17 @@ struct vvb_fft_engine {
     float2* d_wtab = nullptr;        /* direct C2C */
     vvb_engine* real = nullptr;      /* R2C / C2R: STFT engine with a boxcar window, hop = n */
     Chirp* chirp = nullptr;          /* C2C sizes served by the Bluestein path */
+    /* four-step (n = n1 n2, powers of two above 8192): two batched Stockham plans + transposes through work buffers */
+    size_t n1 = 0, n2 = 0;
+    vvb_fft_engine* sub1 = nullptr;  /* C2C size n1, same direction */
+    vvb_fft_engine* sub2 = nullptr;  /* C2C size n2 */
+    vvb_fft_engine* c2c = nullptr;   /* R2C / C2R of a four-step size: the complex plan underneath */
+    float2* d_work[2] = {nullptr, nullptr};
+    size_t work_elems = 0;
 };
+
+/* powers of two in (8192, 2^26]: n1 = 2^ceil(log2(n)/2) <= 8192, n2 = n / n1 >= 128 */
+static bool four_step_size(size_t n) { return n > 8192 && n <= ((size_t)1 << 26) && (n & (n - 1)) == 0; }
 
 extern "C" int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine** out)
 {
@@ -557,11 +567,19 @@ extern "C" int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine
         if (e->fast_c2c) {
             build_c2c_tables(n, blob);
             st = upload(&e->d_tables, blob);
+        } else if (four_step_size(n)) {
+            int lg = 0;
+            while (((size_t)1 << lg) < n) ++lg;
+            e->n1 = (size_t)1 << ((lg + 1) / 2); e->n2 = n / e->n1;
+            st = vvb_fft_engine_create(e->n1, 0, dir, &e->sub1);
+            if (!st) st = vvb_fft_engine_create(e->n2, 0, dir, &e->sub2);
         } else {
             make_wtab(blob, n);
             st = upload((float**)&e->d_wtab, blob);
             if (!st && chirp_size(n)) st = chirp_create(n, &e->chirp);
         }
+    } else if (four_step_size(n)) {
+        st = vvb_fft_engine_create(n, 0, dir, &e->c2c);       /* R2C = C2C of (x, 0), half kept; C2R = C2C of the Hermitian extension */
     } else {
         std::vector<float> ones(n, 1.0f);
         st = vvb_engine_create(n, n, ones.data(), &e->real);
@@ -576,7 +594,78 @@ extern "C" void vvb_fft_engine_destroy(vvb_fft_engine* e)
     if (!e) return;
     vvb_free(e->d_tables); vvb_free(e->d_wtab); vvb_engine_destroy(e->real);
     chirp_destroy(e->chirp);
+    vvb_fft_engine_destroy(e->sub1); vvb_fft_engine_destroy(e->sub2); vvb_fft_engine_destroy(e->c2c);
+    vvb_free(e->d_work[0]); vvb_free(e->d_work[1]);
     delete e;
+}
+
+/* work buffers for `want` transforms of n points, bounded at 256 MB each: *chunk = transforms per pass */
+static int four_step_reserve(vvb_fft_engine* e, size_t want, size_t* chunk)
+{
+    const size_t cap = std::max<size_t>(((size_t)256 << 20) / (e->n * sizeof(float2)), 1);
+    want = std::min(want, cap);
+    if (e->work_elems < want * e->n) {
+        for (int i = 0; i < 2; ++i) { vvb_free(e->d_work[i]); e->d_work[i] = nullptr; }
+        e->work_elems = 0;
+        for (int i = 0; i < 2; ++i)
+            if (int st = vvb_malloc((void**)&e->d_work[i], want * e->n * sizeof(float2))) return st;
+        e->work_elems = want * e->n;
+    }
+    *chunk = e->work_elems / e->n;
+    return 0;
+}
+
+static int four_step_transpose(const float2* in, float2* out, size_t rows, size_t cols, size_t batch, size_t twiddle_n, int inverse, int sms,
+                               void* stream)
+{
+    FourStepArgs a;
+    a.in = in; a.out = out; a.rows = (int)rows; a.cols = (int)cols; a.batch = (long long)batch; a.twiddle_n = (long long)twiddle_n; a.inverse = inverse;
+    const long long tiles = (long long)((rows + 31) / 32) * ((cols + 31) / 32) * (long long)batch;
+    VVB_LAUNCH(fourstep_transpose_kernel, persistent_grid(tiles, 8, sms), 256, 0, stream, a);
+    return 0;
+}
+
+/* X[k1 + n1 k2] = sum_j2 W_n2^(j2 k2) [ W_n^(j2 k1) sum_j1 x[j1 n2 + j2] W_n1^(j1 k1) ]: transpose, n2 transforms of n1 points,
+ * twiddle + transpose, n1 transforms of n2 points, transpose.  in == out is fine (everything goes through the work buffers). */
+static int four_step_exec(vvb_fft_engine* e, const float2* d_in, float2* d_out, size_t batch, void* stream)
+{
+    const int inv = e->dir < 0;
+    size_t chunk = 0;
+    if (int st = four_step_reserve(e, batch, &chunk)) return st;
+    for (size_t b0 = 0; b0 < batch; b0 += chunk) {
+        const size_t nb = std::min(chunk, batch - b0);
+        const float2* x = d_in + b0 * e->n;
+        float2* y = d_out + b0 * e->n;
+        if (int st = four_step_transpose(x, e->d_work[0], e->n1, e->n2, nb, 0, inv, e->sms, stream)) return st;
+        if (int st = vvb_fft_exec(e->sub1, e->d_work[0], e->d_work[0], nb * e->n2, stream)) return st;
+        if (int st = four_step_transpose(e->d_work[0], e->d_work[1], e->n2, e->n1, nb, e->n, inv, e->sms, stream)) return st;
+        if (int st = vvb_fft_exec(e->sub2, e->d_work[1], e->d_work[1], nb * e->n1, stream)) return st;
+        if (int st = four_step_transpose(e->d_work[1], y, e->n1, e->n2, nb, 0, inv, e->sms, stream)) return st;
+    }
+    return 0;
+}
+
+static int four_step_real_exec(vvb_fft_engine* e, const void* d_in, void* d_out, size_t batch, void* stream)
+{
+    vvb_fft_engine* c = e->c2c;
+    size_t chunk = 0;
+    if (int st = four_step_reserve(e, batch, &chunk)) return st;        /* e->d_work[0]: the complex signal / spectrum */
+    const size_t bins = e->n / 2 + 1;
+    for (size_t b0 = 0; b0 < batch; b0 += chunk) {
+        const size_t nb = std::min(chunk, batch - b0);
+        const long long total = (long long)(nb * e->n);
+        const int grid = persistent_grid((total + 255) / 256, 8, e->sms);
+        if (e->type == 1) {
+            VVB_LAUNCH(real_to_cpx_kernel, grid, 256, 0, stream, (const float*)d_in + b0 * e->n, e->d_work[0], total);
+            if (int st = vvb_fft_exec(c, e->d_work[0], e->d_work[0], nb, stream)) return st;
+            VVB_LAUNCH(cpx_keep_half_kernel, grid, 256, 0, stream, (const float2*)e->d_work[0], (float2*)d_out + b0 * bins, (long long)nb, (int)e->n);
+        } else {
+            VVB_LAUNCH(hermitian_extend_kernel, grid, 256, 0, stream, (const float2*)d_in + b0 * bins, e->d_work[0], (long long)nb, (int)e->n);
+            if (int st = vvb_fft_exec(c, e->d_work[0], e->d_work[0], nb, stream)) return st;
+            VVB_LAUNCH(cpx_real_part_kernel, grid, 256, 0, stream, (const float2*)e->d_work[0], (float*)d_out + b0 * e->n, total);
+        }
+    }
+    return 0;
 }
 
 extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, size_t batch, void* stream)
@@ -584,6 +673,8 @@ extern "C" int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, si
     if (!e || !d_in || !d_out) return fail(1, "vvb_fft_exec", "null");
     if (batch == 0) return 0;
     if (batch > 0x7fffffffu) return fail(2, "vvb_fft_exec", "batch");
+    if (e->type == 0 && e->sub1) return four_step_exec(e, (const float2*)d_in, (float2*)d_out, batch, stream);
+    if (e->type != 0 && e->c2c) return four_step_real_exec(e, d_in, d_out, batch, stream);
     if (e->type == 0) {
         if (e->fast_c2c) {
             C2CArgs a;

@@ -113,6 +113,84 @@ __global__ void fft_c2c_direct_kernel(const DirC2CArgs a)
     }
 }
 
+/* ------------------------------------------------------------------ four-step FFT plumbing (plan API, n = n1 n2 > 8192) */
+/* out[b][c][r] = in[b][r][c] (x W_n^{+-r c} when twiddle_n != 0): the transposes of the four-step algorithm, the second
+ * one fused with the inter-step twiddle (exponent reduced mod n in integers, angle in double: no large-angle error).
+ * 32 x 32 tiles through shared memory so that both the loads and the stores are coalesced. */
+struct FourStepArgs { const float2* in; float2* out; int rows, cols; long long batch; long long twiddle_n; int inverse; };
+
+__global__ void __launch_bounds__(256) fourstep_transpose_kernel(const FourStepArgs a)
+{
+#ifdef VVB_EMU
+    static float2 tile[32][33];                                        /* CTAs run one after another in the emulator */
+#else
+    __shared__ float2 tile[32][33];
+#endif
+    const int tiles_c = (a.cols + 31) / 32, tiles_r = (a.rows + 31) / 32;
+    const long long per = (long long)tiles_c * tiles_r, total = per * a.batch;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            /* 32 x 8 threads */
+    for (long long tl = blockIdx.x; tl < total; tl += gridDim.x) {
+        const long long b = tl / per;
+        const int tr = (int)((tl % per) / tiles_c), tc = (int)((tl % per) % tiles_c);
+        const float2* src = a.in + b * (long long)a.rows * a.cols;
+        float2* dst = a.out + b * (long long)a.rows * a.cols;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = tr * 32 + ty + 8 * i, c = tc * 32 + tx;
+            if (r < a.rows && c < a.cols) tile[ty + 8 * i][tx] = src[(long long)r * a.cols + c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = tc * 32 + ty + 8 * i, r = tr * 32 + tx;
+            if (r < a.rows && c < a.cols) {
+                float2 v = tile[tx][ty + 8 * i];
+                if (a.twiddle_n) {
+                    const long long m = ((long long)r * c) % a.twiddle_n;
+                    double sn, cs;
+                    sincospi(2.0 * (double)m / (double)a.twiddle_n, &sn, &cs);
+                    const float wr = (float)cs, wi = (float)(a.inverse ? sn : -sn);
+                    v = make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+                }
+                dst[(long long)c * a.rows + r] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* real <-> complex glue for R2C / C2R plans of four-step sizes */
+__global__ void real_to_cpx_kernel(const float* in, float2* out, long long total)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        out[i] = make_float2(in[i], 0.f);
+}
+__global__ void cpx_keep_half_kernel(const float2* in, float2* out, long long batch, int n)
+{
+    const int bins = n / 2 + 1;
+    const long long total = batch * bins;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / bins; const int k = (int)(i % bins);
+        out[i] = in[b * n + k];
+    }
+}
+__global__ void hermitian_extend_kernel(const float2* half, float2* full, long long batch, int n)
+{
+    const int bins = n / 2 + 1;
+    const long long total = batch * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / n; const int k = (int)(i % n);
+        float2 v = (k < bins) ? half[b * bins + k] : half[b * bins + (n - k)];
+        if (k >= bins) v.y = -v.y;
+        if (k == 0 || 2 * k == n) v.y = 0.f;                            /* Re(IDFT): DC / Nyquist imaginary parts drop out */
+        full[i] = v;
+    }
+}
+__global__ void cpx_real_part_kernel(const float2* in, float* out, long long total)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) out[i] = in[i].x;
+}
+
 struct OlaArgs {
     const float* frames_in;  /* [batch][frames][nfft] windowed synthesis frames */
     int batch, frames, hop, nfft;

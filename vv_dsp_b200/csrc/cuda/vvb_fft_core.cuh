@@ -25,11 +25,13 @@
 
 #ifdef VVB_EMU
 #include "cuda_emu.h"
+#include <type_traits>
 #define VVB_DEV inline __attribute__((always_inline))
 #define VVB_CX constexpr
 #define VVB_MAXNREG(n)
 #else
 #include <cuda_runtime.h>
+#include <type_traits>
 #define VVB_DEV __device__ __forceinline__
 #define VVB_CX __host__ __device__ constexpr
 #define VVB_MAXNREG(n) __maxnreg__(n)      /* explicit per-thread register cap (one CTA of W warps per SM) */
@@ -567,11 +569,15 @@ template <int NQ, int RADIX, int... Rs> VVB_DEV void apply_tw_same(float2* v, co
 {
     (apply_tw_same_one<NQ, RADIX, Rs + 1>(v, b), ...);
 }
+#ifndef VVB_TW3_HALF_EXCHANGE
+#define VVB_TW3_HALF_EXCHANGE 1       /* 32.8.8 configuration: exchange only the partner warp's half between passes 2 and 3 */
+#endif
 template <class C, class Hook = NoHook>
 VVB_DEV void team_fft_tw3(float2 (&v)[C::E], float2* xb, const float2* s_tw2, const float2* s_tw3, int t, int team, Hook after_last_read = Hook())
 {
     static_assert(C::NP == 3 && C::T % C::R1 == 0 && C::T * (C::E / C::R3) == C::R1 * C::R2 && C::R2 <= 32 && C::R3 <= 32, "see above");
     stockham_pass<C, C::R1, 1, true, false>(v, xb, nullptr, t, team);
+    constexpr bool HALFX = VVB_TW3_HALF_EXCHANGE && C::T == 64 && C::R1 == 32 && C::R2 == 8 && C::R3 == 8 && C::E == 32;
     {   /* pass 2 */
         constexpr int R = C::R2, NS = C::R1, NQ = C::E / R, STRIDE = C::M / R;
 #pragma unroll
@@ -585,16 +591,62 @@ VVB_DEV void team_fft_tw3(float2 (&v)[C::E], float2* xb, const float2* s_tw2, co
         apply_tw_same<NQ, R>(v, b, typename make_iseq<R - 1>::type{});
 #pragma unroll
         for (int q = 0; q < NQ; ++q) fft_reg<R, 0>(&v[q * R]);
+        if constexpr (!HALFX) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int j = t + C::T * q;
-            const int j0 = (j / NS) * NS * R + (j % NS);
+            for (int q = 0; q < NQ; ++q) {
+                const int j = t + C::T * q;
+                const int j0 = (j / NS) * NS * R + (j % NS);
 #pragma unroll
-            for (int r = 0; r < R; ++r) xb[C::pad(j0 + r * NS)] = v[q * R + r];
+                for (int r = 0; r < R; ++r) xb[C::pad(j0 + r * NS)] = v[q * R + r];
+            }
+            team_sync<C::T>(team);
         }
-        team_sync<C::T>(team);
     }
-    {   /* pass 3 */
+    if constexpr (HALFX) {
+        /* pass 2 -> pass 3 of the 32.8.8 configuration (two warps per transform) moves data only between the SAME lane of
+         * the two warps: the pass-3 input r' of sub-transform q' of thread (warp a', lane l) is output slot a' + 2 q' of
+         * sub-transform r' / 2 of thread (warp r' mod 2, lane l).  Half of a thread's 32 inputs are therefore already in
+         * its own registers; only the other half goes through shared memory (16 STS.64 + 16 LDS.64 instead of 32 + 32:
+         * 128 of the ~960 shared-memory wavefronts per frame).  The register permutation depends on the warp, hence the
+         * two (warp-uniform) code paths. */
+        constexpr int R = 8, NQ = 4;
+        const int a = t >> 5;
+        float2 u[C::E];
+        auto exchange = [&](auto AC) {
+            constexpr int A = decltype(AC)::value;                     /* this thread's warp within the team */
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)                               /* slots the partner needs: r = (1 - A) + 2 q' */
+#pragma unroll
+                for (int qq = 0; qq < NQ; ++qq) {
+                    const int r = (1 - A) + 2 * qq;
+                    xb[C::pad((A + 2 * q) * 256 + (t & 31) + 32 * r)] = v[q * R + r];
+                }
+#pragma unroll
+            for (int qq = 0; qq < NQ; ++qq)                            /* own half: r' = A + 2 k  <-  v[k * 8 + A + 2 q'] */
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) u[qq * R + A + 2 * k] = v[k * R + A + 2 * qq];
+            team_sync<C::T>(team);
+#pragma unroll
+            for (int qq = 0; qq < NQ; ++qq)                            /* partner's half: r' = (1 - A) + 2 k at its natural position */
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) {
+                    const int rp = (1 - A) + 2 * k;
+                    u[qq * R + rp] = xb[C::pad(t + C::T * qq + rp * 256)];
+                }
+        };
+        if (a == 0) exchange(std::integral_constant<int, 0>{}); else exchange(std::integral_constant<int, 1>{});
+        team_sync<C::T>(team);
+        after_last_read();
+#pragma unroll
+        for (int i = 0; i < C::E; ++i) v[i] = u[i];
+        constexpr int NS = C::R1 * C::R2;
+        TwBase b;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) b.w[j] = ((1 << j) < R) ? s_tw3[((1 << j) - 1) * NS + t] : make_float2(1.f, 0.f);
+        apply_tw_rot_all<C, R>(v, b, typename make_iseq<NQ>::type{});
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) fft_reg<R, 0>(&v[q * R]);
+    } else {   /* pass 3 */
         constexpr int R = C::R3, NS = C::R1 * C::R2, NQ = C::E / R, STRIDE = C::M / R;
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
