@@ -323,22 +323,28 @@ VVB_DEV void cp_async_wait_all()
 
 /* ---- TMA 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) completing on an mbarrier.
  * src, dst and bytes must be multiples of 16.  Issued by ONE thread. */
-/* (emulator: the 8-byte barrier word holds {phase bit, expected arrivals, pending arrivals}; a TMA copy is a memcpy
- * followed by the arrival that expect_tx stands for, and a wait yields to the other fibres until the phase flips) */
+/* (emulator: the 8-byte barrier word holds {phase bit, expected arrivals, pending arrivals, transaction bytes}; a TMA
+ * copy is a memcpy that works off the bytes announced by expect_tx, a phase completes when no arrival and no byte is
+ * pending, and a wait yields to the other fibres until the phase flips) */
 #ifdef VVB_EMU
-struct EmuMbar { unsigned phase; unsigned short expected, pending; };
+struct EmuMbar { unsigned char phase, expected, pending, pad; int tx; };
 static_assert(sizeof(EmuMbar) == 8, "mbarrier word");
+inline void emu_mbar_check(EmuMbar* b)
+{
+    if (b->pending == 0 && b->tx == 0) { b->phase ^= 1u; b->pending = b->expected; }
+}
 inline void emu_mbar_arrive(unsigned long long* bar)
 {
     EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
-    if (--b->pending == 0) { b->phase ^= 1u; b->pending = b->expected; }
+    --b->pending;
+    emu_mbar_check(b);
 }
 #endif
 VVB_DEV void mbar_init(unsigned long long* bar, unsigned count)
 {
 #ifdef VVB_EMU
     EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
-    b->phase = 0; b->expected = (unsigned short)count; b->pending = (unsigned short)count;
+    b->phase = 0; b->expected = (unsigned char)count; b->pending = (unsigned char)count; b->pad = 0; b->tx = 0;
 #else
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory");
@@ -351,7 +357,10 @@ VVB_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
 #else
-    (void)bar; (void)bytes;                       /* the arrival is performed by bulk_load's completion */
+    EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);  /* one arrival + a transaction count that the copies work off */
+    b->tx += (int)bytes;
+    --b->pending;
+    emu_mbar_check(b);
 #endif
 }
 /* plain arrival (release semantics at CTA scope): signals "my earlier shared-memory writes / reads are done" */
@@ -368,7 +377,11 @@ VVB_DEV void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigne
 {
 #ifdef VVB_EMU
     memcpy(smem_dst, gsrc, bytes);
-    emu_mbar_arrive(bar);
+    {
+        EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+        b->tx -= (int)bytes;
+        emu_mbar_check(b);
+    }
 #else
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);

@@ -115,16 +115,22 @@ __global__ void __launch_bounds__(64 * NPAIR, 1) istft_ws_kernel(const InvArgs a
     unsigned long long* bar_empty = bar_stage + 2 * LY::NBUF;
 
     const int F = a.frames;
-    const long long total = (long long)a.num_items * F;               /* num_items carries the batch */
-    const long long nteams = (long long)gridDim.x * NPAIR;
-    const long long quota = (total + nteams - 1) / nteams;
-    long long g0 = ((long long)blockIdx.x * NPAIR + pair) * quota;
-    const long long g1 = min(total, g0 + quota);
+    /* the pair's range [g0, g1) of the flattened (signal, frame) list: computed inside each role, after its register
+     * budget is set (computed up here the four 64-bit values were spilled across the role branch) */
+    auto pair_range = [&](long long& g0, long long& g1) {
+        const long long total = (long long)a.num_items * F;           /* num_items carries the batch */
+        const long long nteams = (long long)gridDim.x * NPAIR;
+        const long long quota = (total + nteams - 1) / nteams;
+        g0 = ((long long)blockIdx.x * NPAIR + pair) * quota;
+        g1 = min(total, g0 + quota);
+    };
     unsigned it = 0;                                                   /* frames handed over so far (both roles count alike) */
 
     if (producer) {
         /* ================================================================ producer: stage -> merge -> pass 1 -> publish */
         setmaxnreg_dec<VVB_WS_PRODUCER_REGS>();
+        long long g0, g1;
+        pair_range(g0, g1);
         const float2 hw_t = __ldg(reinterpret_cast<const float2*>(a.tables + TB::POST) + t);
         const bool spec16 = (reinterpret_cast<uintptr_t>(a.spec) & 15) == 0;
         while (g0 < g1) {
@@ -223,6 +229,8 @@ __global__ void __launch_bounds__(64 * NPAIR, 1) istft_ws_kernel(const InvArgs a
     } else {
         /* ================================================================ consumer: twiddle -> pass 2 -> window, overlap-add */
         setmaxnreg_inc<VVB_WS_CONSUMER_REGS>();
+        long long g0, g1;
+        pair_range(g0, g1);
         const float2* wsyn2 = reinterpret_cast<const float2*>(s_wsyn);
         while (g0 < g1) {
             const int b = (int)(g0 / F);

@@ -518,10 +518,34 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
             return false;
         };
 
-        /* prologue: the N/hop blocks of the first frame, one after another */
-        for (int q = 0; q < NB; ++q) {
-            team_sync<T>(team);
-            if (load_block(f_begin + q)) { mbar_wait(bar, parity); parity ^= 1; }
+        /* prologue: the N/hop blocks of the first frame.  All TMA copies are issued at once against ONE transaction
+         * count (a range then starts after one memory latency instead of N/hop of them: with ~36 frames per team, as on
+         * 8 GPUs of a sharded stream, that was ~5 % of the kernel); blocks that touch a signal edge are filled by hand */
+        team_sync<T>(team);
+        {
+            int nbulk = 0;
+#pragma unroll 1
+            for (int q = 0; q < NB; ++q) {
+                const long long s0 = origin + (long long)(f_begin + q) * HOP;
+                nbulk += (bulk_ok && s0 >= 0 && s0 + HOP <= a.n) ? 1 : 0;
+            }
+            if (nbulk && t == 0) { fence_proxy_async(); mbar_expect_tx(bar, (unsigned)nbulk * HOP * 4); }
+#pragma unroll 1
+            for (int q = 0; q < NB; ++q) {
+                const int j = f_begin + q;
+                float2* dst = ring + (j % RING) * HB;
+                const long long s0 = origin + (long long)j * HOP;
+                if (bulk_ok && s0 >= 0 && s0 + HOP <= a.n) {
+                    if (t == 0) bulk_load(dst, xs + s0, HOP * 4, bar);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < S; ++r) {
+                        const long long i0 = s0 + 2 * (t + T * r);
+                        dst[t + T * r] = make_float2(fetch_sample(xs, a.n, i0, a.pad_mode), fetch_sample(xs, a.n, i0 + 1, a.pad_mode));
+                    }
+                }
+            }
+            if (nbulk) { mbar_wait(bar, parity); parity ^= 1; }
         }
         bool pending = false;
 
@@ -559,7 +583,9 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
             } else {
                 /* computed inter-pass twiddles, same-box A/B (1024 x 480000 samples): fft_size 4096 complex 2.528 -> 2.472 ms,
                  * power 2.218 -> 2.263 ms; fft_size 8192 complex unchanged, power 2.476 -> 2.619 ms: kept where they pay */
-                team_fft_march<C, (OUT == OUT_COMPLEX && C::M == 2048)>(v, xb, s_tw2, s_tw3, t, team);
+                /* (fft_size 4096, 32.8.8: the computed version also exchanges only half of the data between passes 2 and 3,
+                 * complex 2.455 -> 2.274 ms on one box, so every output kind takes it there) */
+                team_fft_march<C, (C::M == 2048)>(v, xb, s_tw2, s_tw3, t, team);
                 /* computed split twiddles help at fft_size 4096 (2.94 -> 2.86 ms) and hurt at 8192 (3.24 -> 3.75 ms) */
                 /* (fft_size 8192 with power / magnitude output is the one case measured slower with the half exchange:
                  * 2.46 -> 2.58 ms, while its complex output gains 8 %) */

@@ -4,9 +4,14 @@
 #include <stddef.h>
 
 /* device-resident sparse mel filterbank: meta = lo | len | off per band, packed non-zero weights */
-typedef struct mel_device { int* d_meta; float* d_w; size_t n_groups; } mel_device;
+/* d_scan (may be NULL): the per-bin records and band ranges of the single-pass log-mel kernel, see mel.c */
+typedef struct mel_device { int* d_meta; float* d_w; size_t n_groups; int* d_scan; } mel_device;
 int vvdsp_internal_mel_device_build(const float* dense_weights, size_t n_mels, size_t bins, void* stream, mel_device* md);
 void vvdsp_internal_mel_device_free(mel_device* md);
+/* log-mel of densely packed power rows on the device: the single-pass kernel where the filterbank and the sizes allow it,
+ * else the group kernels (same results bit for bit) */
+int vvdsp_internal_logmel(const mel_device* md, const float* d_power, size_t frames, size_t bins, size_t n_mels, float eps,
+                          float* d_out, void* stream);
 
 /* MFCC tables on the device: cosine table [n_coeffs][n_mels] and lifter factors [n_coeffs] */
 typedef struct mfcc_device { float* d_table; float* d_lifter; size_t n_mels, n_coeffs; float lifter; } mfcc_device;

@@ -583,7 +583,7 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
         if (out_space == VV_DSP_MEM_HOST) o_dev = d_o;
         if (!st) st = vvb_stft_forward(h->eng, x_dev, nb, n, xp, frames, pad, VVB_OUT_POWER, d_power, h->bins, stream);
         lm_dev = n_coeffs ? h->d_logmel_scratch : o_dev;
-        if (!st) st = vvb_logmel(d_power, nb * frames, h->bins, h->bins, h->mel.d_meta, h->mel.d_w, n_mels, h->mel.n_groups, log_epsilon, lm_dev, stream);
+        if (!st) st = vvdsp_internal_logmel(&h->mel, d_power, nb * frames, h->bins, n_mels, log_epsilon, lm_dev, stream);
         if (!st && n_coeffs) st = vvb_mfcc(lm_dev, nb * frames, n_mels, n_coeffs, h->mfcc.d_table, h->mfcc.d_lifter, o_dev, stream);
         if (!st && out_space == VV_DSP_MEM_HOST)
             st = vvb_memcpy_d2h(out + done * frames * width, d_o, nb * frames * width * sizeof(float), stream);
