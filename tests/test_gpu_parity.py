@@ -7,7 +7,7 @@ import pytest
 
 import parity_cases as pc
 from _util import ROUNDTRIP_REL_L2, noise, rel_l2, spectra_close
-from vv_dsp_b200 import Stft
+from vv_dsp_b200 import FftPlan, Stft
 
 pytestmark = pytest.mark.gpu
 
@@ -274,6 +274,26 @@ def test_bluestein_sizes(lib, oracle):
     report = pc.check_bluestein(lib, oracle, [(400, 160), (33, 11), (96, 24), (480, 120), (1000, 250), (1536, 384), (2000, 500), (2047, 512), (64, 16),
                                               (3000, 750), (4095, 1365)])
     print("error vs float64 truth (mine, reference):", report)
+
+
+def test_bluestein_above_4096(lib, oracle):
+    """non-power-of-two sizes whose chirp-z length exceeds the largest one-kernel transform (M = 16384 ... 131072: four-step
+    plans underneath).  The reference serves these with its O(n^2) float DFT (src/spectral/fft_kiss.c:76-92,115)."""
+    report = pc.check_bluestein(lib, oracle, [(5000, 1250), (12000, 3000)])
+    print("error vs float64 truth (mine, reference):", report)
+    rng = np.random.default_rng(5)
+    for n in (48000, 100003):                       # plan API only: float64 truth (the O(n^2) oracle would take minutes here)
+        z = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+        xr = rng.uniform(-1, 1, n).astype(np.float32)
+        f = FftPlan(n, 0, +1, lib=lib).execute(z)
+        t = np.fft.fft(z.astype(np.complex128))
+        assert np.abs(f - t).max() <= 3e-6 * np.abs(t).max(), (n, np.abs(f - t).max() / np.abs(t).max())
+        back = FftPlan(n, 0, -1, lib=lib).execute(f)
+        assert np.abs(back - z).max() < 1e-5
+        r = FftPlan(n, 1, +1, lib=lib).execute(xr)
+        tr = np.fft.rfft(xr.astype(np.float64))
+        assert r.shape == (n // 2 + 1,) and np.abs(r - tr).max() <= 3e-6 * np.abs(tr).max()
+        assert np.abs(FftPlan(n, 2, -1, lib=lib).execute(r) - xr).max() < 1e-5
 
 
 def test_bluestein_unfused_and_direct_paths(lib, oracle, monkeypatch):
