@@ -37,7 +37,8 @@ with Stft(nfft, hop, "hann") as h:
     ms_pow = e0.elapsed_time(e1) / 5
 print(json.dumps({"workload": f"STFT->log-mel, {B} x {n} samples, nfft={nfft} hop={hop}, {n_mels} mels", "ms": ms,
                   "Msamples_per_s": B * n / ms / 1e3, "power_kernel_ms": ms_pow, "logmel_and_overhead_ms": ms - ms_pow,
-                  "note": "power goes through a 768 MB device scratch in chunks; scratch and the device filterbank are cached in the handle"}))
+                  "path": "power kernel + log-mel kernel through a 768 MB device scratch" if os.environ.get("VVB_MEL_UNFUSED") else "one fused kernel (no power spectrogram in HBM)",
+                  "algorithmic_GB": (B * n * 4 + B * F * n_mels * 4) / 1e9, "GBps": (B * n * 4 + B * F * n_mels * 4) / ms / 1e6}))
 # MFCC tail: same chain + DCT-II (13 coefficients, lifter 22)
 out2 = torch.empty((B, F, 13), device=dev)
 with Stft(nfft, hop, "hann") as h:

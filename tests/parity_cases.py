@@ -250,6 +250,49 @@ def check_mel(lib, oracle, nfft=2048, hop=512, n_mels=80, sr=48000.0, n=30000, b
             assert np.abs(e - er).max() <= 1e-4 * er.max(), np.abs(e - er).max() / er.max()
 
 
+def check_mel_fused(lib, oracle, cases=((512, 80, 48000.0), (256, 128, 48000.0), (1024, 40, 16000.0), (512, 23, 8000.0)), n=9000, batch=5):
+    """STFT -> log-mel in ONE kernel (fft_size 2048 marching kernel, band sums by the warp that made the frame) against the
+    chained power and log-mel kernels (VVB_MEL_UNFUSED=1): bit for bit, every hop with a marching kernel, zero-padded and
+    centred frames, filterbanks with short and long schedules; plus a filterbank with an all-zero band, a band whose
+    support has holes and negative weights (nothing in the kernel assumes a triangular shape)."""
+    import os
+    from vv_dsp_b200 import mel_filterbank
+    nfft = 2048
+    x = np.stack([noise(160 + i, n + 37 * i)[:n] for i in range(batch)])
+    rng = np.random.default_rng(9)
+    for hop, n_mels, sr in cases:
+        st, w = mel_filterbank(nfft, n_mels, sr, 0.0, sr / 2, lib=lib)
+        assert st == 0
+        banks = [w]
+        odd = w.copy()
+        odd[1] = 0.0                                                   # an empty band: log(eps)
+        odd[n_mels // 2, ::3] = 0.0                                    # holes inside a support
+        odd[n_mels - 2] *= -1.0                                        # negative weights (sum + eps stays whatever it is)
+        odd[0, :150] = rng.uniform(0, 1e-3, 150).astype(np.float32)      # a wide band out of order
+        banks.append(odd)
+        with Stft(nfft, hop, "hann", lib=lib) as h:
+            for wb in banks:
+                for conv in ("valid", "center"):
+                    fused = h.batch_logmel(x, wb, 1e-6, conv)
+                    os.environ["VVB_MEL_SINGLE"] = "1"                   # one frame per band-sum phase instead of two
+                    try:
+                        single = h.batch_logmel(x, wb, 1e-6, conv)
+                    finally:
+                        del os.environ["VVB_MEL_SINGLE"]
+                    os.environ["VVB_MEL_UNFUSED"] = "1"
+                    try:
+                        chained = h.batch_logmel(x, wb, 1e-6, conv)
+                    finally:
+                        del os.environ["VVB_MEL_UNFUSED"]
+                    assert fused.shape == chained.shape
+                    assert np.array_equal(fused, chained, equal_nan=True), (hop, n_mels, conv, np.nanmax(np.abs(fused - chained)))
+                    assert np.array_equal(single, chained, equal_nan=True), (hop, n_mels, conv)
+            ref = np.stack([oracle.log_mel(np.abs(oracle.stft(x[i], nfft, hop)) ** 2, w, 1e-6) for i in range(2)])
+            lm = h.batch_logmel(x[:2], w, 1e-6, "valid")
+            e, er = np.exp(lm.astype(np.float64)), np.exp(ref.astype(np.float64))
+            assert np.abs(e - er).max() <= 1e-4 * er.max()
+
+
 def check_mfcc(lib, oracle):
     """vv_dsp_mfcc, the MFCC plan and the batched STFT -> MFCC chain against the oracle (same float32 sums as the
     reference: only the logf feeding the DCT may differ in the last ulp)."""
@@ -458,7 +501,8 @@ def check_bluestein(lib, oracle, sizes):
                     own = h.batch_inverse(s, n, True)
                     assert rel_l2(own[:, nfft:n - nfft], x[:, nfft:n - nfft]) <= ROUNDTRIP_REL_L2
                     oref = np.stack([oracle.istft(ref[i], nfft, hop, n, win) for i in range(2)])
-                    assert rel_l2(y[:, nfft:n - nfft], oref[:, nfft:n - nfft]) <= 2e-4     # the oracle's inverse DFT error dominates
+                    # the oracle's O(n^2) float32 inverse DFT error dominates here and grows with the size
+                    assert rel_l2(y[:, nfft:n - nfft], oref[:, nfft:n - nfft]) <= 2e-4 * max(1.0, nfft / 2048)
                     # binding check beside the widened tolerance: float64 truth of the same spectra, relative L2
                     assert rel_l2(y[:, nfft:n - nfft], yt[:, nfft:n - nfft]) <= ROUNDTRIP_REL_L2
         report[nfft] = (float(mine), float(theirs))

@@ -87,6 +87,10 @@ def test_mel(emu, oracle):
     pc.check_mel(emu, oracle, 512, 128, 26, 16000.0, 6000)
 
 
+def test_mel_fused(emu, oracle):
+    pc.check_mel_fused(emu, oracle, cases=((512, 80, 48000.0), (1024, 40, 16000.0)), n=6000, batch=3)
+
+
 def test_mfcc(emu, oracle):
     pc.check_mfcc(emu, oracle)
 

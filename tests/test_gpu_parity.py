@@ -169,6 +169,10 @@ def test_mel(lib, oracle):
 
 
 @pytest.mark.gpu
+def test_mel_fused_kernel_equals_chained_kernels(lib, oracle):
+    pc.check_mel_fused(lib, oracle)
+
+
 def test_mfcc(lib, oracle):
     pc.check_mfcc(lib, oracle)
 

@@ -9,7 +9,10 @@ template <class C, int S, int OUT> static int launch_fwd_march_t(FwdArgs a, int 
     constexpr int G = March<C>::G, MINB = March<C>::MINB;
     static OccCache occ;
     auto kern = stft_march_kernel<C, S, G, MINB, OUT>;
-    const size_t smem = sizeof(float) * 2 * (C::TW2 + C::TW3 + C::POST + 1 + G * C::XBUF + G * (C::E / S + 1) * C::T * S) + 8 * G;
+    size_t smem = sizeof(float) * 2 * (C::TW2 + C::TW3 + C::POST + 1 + G * C::XBUF + G * (C::E / S + 1) * C::T * S) + 8 * G;
+    if constexpr (OUT == OUT_LOGMEL)      /* + schedule tables and one row of band sums per team (see mel_phase) */
+        smem += mel_smem_bytes(G, a.mel_S, a.n_mels, a.mel_prow, a.mel_pair);
+    if (smem > 227 * 1024) return 6;                             /* schedule too long for the shared memory left: unfused chain */
     const int per_sm = occ.get(kern, C::T * G, smem);
     if (per_sm == 0) return rt_fail(4, "stft_march_kernel", "does not fit on this device");
     const long long total = (long long)a.num_groups * a.frames;  /* num_groups carries the batch */
@@ -23,6 +26,9 @@ template <class C, int S> static int launch_fwd_march_s(const FwdArgs& a, int ki
     case OUT_COMPLEX: return launch_fwd_march_t<C, S, OUT_COMPLEX>(a, sms, stream);
     case OUT_POWER: return launch_fwd_march_t<C, S, OUT_POWER>(a, sms, stream);
     case OUT_MAGNITUDE: return launch_fwd_march_t<C, S, OUT_MAGNITUDE>(a, sms, stream);
+    case OUT_LOGMEL:
+        if constexpr (C::T == 32) return launch_fwd_march_t<C, S, OUT_LOGMEL>(a, sms, stream);
+        else return -1;
     default: return rt_fail(3, "vvb_stft_forward", "bad out_kind");
     }
 }

@@ -45,7 +45,8 @@
 
 namespace vvb {
 
-enum { OUT_COMPLEX = 0, OUT_POWER = 1, OUT_MAGNITUDE = 2 };
+enum { OUT_COMPLEX = 0, OUT_POWER = 1, OUT_MAGNITUDE = 2, OUT_LOGMEL = 3 };   /* OUT_LOGMEL: marching kernel only, see mel_phase */
+constexpr int MEL_U = 4;              /* fused log-mel: four-tap groups ("quads") per schedule segment */
 enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
 
 /* float offsets of the per-plan table blob in global memory (host builds it, vvb_runtime.cu) */
@@ -69,7 +70,20 @@ struct FwdArgs {
     long long out_pitch;
     const float* tables;
     int num_groups, groups_per_signal;
+    /* OUT_LOGMEL only (tables: csrc/host/mel.c, build_fused_tables): out = [batch][frames][n_mels] log-mel rows */
+    const float4* mel_w;     /* [mel_S * MEL_U][32]: the four weights of lane l's quad at schedule step i */
+    const int2* mel_seg;     /* [mel_S][32]: { float offset of the segment's first quad in the power row, reset | (band + 1) << 1 } */
+    int mel_S, mel_prow, n_mels;
+    int mel_pair;            /* 1: the band sums of two consecutive frames of a warp run together and share every weight load */
+    float mel_eps;
 };
+
+/* bytes of shared memory the fused log-mel phase adds to a marching forward kernel with G one-warp teams */
+VVB_CX size_t mel_smem_bytes(int G, int mel_S, int n_mels, int mel_prow, int pair)
+{
+    return (size_t)(8 * (G & 1)) + (size_t)mel_S * 32 * (16 * MEL_U + 8) + sizeof(float) * (size_t)G * (size_t)((n_mels + 31) & ~31) * (pair ? 2 : 1) +
+           (pair ? sizeof(float) * (size_t)G * (size_t)mel_prow : 0);
+}
 
 struct InvArgs {
     const float2* spec;      /* [batch][frames][spec_pitch] */
@@ -118,7 +132,62 @@ template <int OUT> VVB_DEV void emit_bin(void* out, long long idx, float2 x)
 {
     if constexpr (OUT == OUT_COMPLEX) reinterpret_cast<float2*>(out)[idx] = x;
     else if constexpr (OUT == OUT_POWER) reinterpret_cast<float*>(out)[idx] = x.x * x.x + x.y * x.y;
+    else if constexpr (OUT == OUT_LOGMEL) reinterpret_cast<float*>(out)[(int)idx] = x.x * x.x + x.y * x.y;   /* the team's power row in shared memory */
     else reinterpret_cast<float*>(out)[idx] = sqrtf(x.x * x.x + x.y * x.y);
+}
+
+/* Fused log-mel (reference: src/features/mel.c:204-245, log(sum_k P[k] W[m][k] + eps) with an ascending float32 sum, separate
+ * multiply and add).  The warp that has just split a frame keeps the frame's power row in shared memory instead of storing
+ * it, and its 32 lanes sum the bands: the host has packed the bands into 32 lane schedules of mel_S segments of MEL_U quads
+ * (a quad = four consecutive bins, 16-byte aligned in the row; a band occupies whole segments of ONE lane, padded with zero
+ * weights, which add exactly 0 like the zero weights of the reference's full-row sum).  All lanes walk the same number of
+ * steps, band changes happen only at segment boundaries, so there is no divergence; per quad one LDS.128 of weights
+ * ([step][lane]: conflict-free), one LDS.128 of power values, 4 FMUL + 4 FADD.  No power spectrogram reaches HBM.
+ * NF = 2: a warp parks the row of every other frame in a second buffer and sums two frames at once -- two independent
+ * chains that share every weight load (the phase is bound by shared-memory wavefronts: 4 + 4 per quad and frame -> 2 + 4). */
+template <int NF>
+VVB_DEV void mel_phase(const FwdArgs& a, const float4* s_w, const int2* s_seg, const float* row0, const float* row1, float* mout, int t,
+                       long long out_row0, long long out_row1)
+{
+    __syncwarp();                                                      /* the power rows are complete */
+    const int nmp = (a.n_mels + 31) & ~31;
+    float acc0 = 0.f, acc1 = 0.f;
+    const float4* wq = s_w + t;
+#pragma unroll 1
+    for (int s = 0; s < a.mel_S; ++s) {
+        const int2 d = s_seg[s * 32 + t];
+        if (d.y & 1) { acc0 = 0.f; acc1 = 0.f; }
+        const float4* p0 = reinterpret_cast<const float4*>(row0 + d.x);
+        const float4* p1 = reinterpret_cast<const float4*>(row1 + d.x);
+#pragma unroll
+        for (int u = 0; u < MEL_U; ++u) {
+            const float4 w = wq[(s * MEL_U + u) * 32];
+            const float4 x0 = p0[u];
+            acc0 = __fadd_rn(acc0, __fmul_rn(x0.x, w.x));
+            acc0 = __fadd_rn(acc0, __fmul_rn(x0.y, w.y));
+            acc0 = __fadd_rn(acc0, __fmul_rn(x0.z, w.z));
+            acc0 = __fadd_rn(acc0, __fmul_rn(x0.w, w.w));
+            if constexpr (NF == 2) {
+                const float4 x1 = p1[u];
+                acc1 = __fadd_rn(acc1, __fmul_rn(x1.x, w.x));
+                acc1 = __fadd_rn(acc1, __fmul_rn(x1.y, w.y));
+                acc1 = __fadd_rn(acc1, __fmul_rn(x1.z, w.z));
+                acc1 = __fadd_rn(acc1, __fmul_rn(x1.w, w.w));
+            }
+        }
+        if (d.y >> 1) {
+            mout[(d.y >> 1) - 1] = acc0;
+            if constexpr (NF == 2) mout[nmp + (d.y >> 1) - 1] = acc1;
+        }
+    }
+    __syncwarp();
+    float* o0 = reinterpret_cast<float*>(a.out) + out_row0 * a.out_pitch;
+    float* o1 = reinterpret_cast<float*>(a.out) + out_row1 * a.out_pitch;
+    for (int m = t; m < a.n_mels; m += 32) {
+        o0[m] = logf(mout[m] + a.mel_eps);
+        if constexpr (NF == 2) o1[m] = logf(mout[nmp + m] + a.mel_eps);
+    }
+    __syncwarp();                                                      /* the rows and the band sums are free again */
 }
 /* X[k] = sm/2 - g, X[M-k] = conj(sm/2 + g) with sm = A + conj(Bc), g = ((sin + j cos)/2) (A - conj(Bc)) */
 VVB_DEV void split_math(float2 A, float2 Bc, float2 hw, float2& x0, float2& x1)
@@ -462,6 +531,29 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ring + G * RING * HB);
     copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3 + C::POST));
     const int team = threadIdx.x / T, t = threadIdx.x % T;
+    /* OUT_LOGMEL: schedule tables | one power row per team (tail kept at zero) | one row of band sums per team */
+    float4* s_melw = reinterpret_cast<float4*>(s_bar + ((G + 1) & ~1));
+    int2* s_melseg = nullptr;
+    float *prow = nullptr, *mout = nullptr, *row_a = nullptr;
+    if constexpr (OUT == OUT_LOGMEL) {
+        static_assert(T == 32, "the fused log-mel phase is written for one-warp teams");
+        s_melseg = reinterpret_cast<int2*>(s_melw + a.mel_S * MEL_U * 32);
+        float* s_mout = reinterpret_cast<float*>(s_melseg + a.mel_S * 32);
+        const int nmp = (a.n_mels + 31) & ~31;
+        copy_table(reinterpret_cast<float*>(s_melw), reinterpret_cast<const float*>(a.mel_w), a.mel_S * MEL_U * 32 * 4);
+        copy_table(reinterpret_cast<float*>(s_melseg), reinterpret_cast<const float*>(a.mel_seg), a.mel_S * 32 * 2);
+        /* the power row lives in the lower half of the team's exchange buffer: the split step publishes and reads only the
+         * upper half (floats >= 2 pad(M/2)), and the next frame's first pass overwrites it after the closing team barrier */
+        prow = reinterpret_cast<float*>(s_xb + team * C::XBUF);
+        mout = s_mout + team * nmp * (a.mel_pair ? 2 : 1);
+        if (a.mel_pair) {                                                /* second row buffers: written only by the split step, tails stay zero */
+            float* s_rowa = s_mout + G * nmp * 2;
+            for (int i = threadIdx.x; i < G * a.mel_prow; i += blockDim.x) s_rowa[i] = 0.f;
+            row_a = s_rowa + team * a.mel_prow;
+        }
+    }
+    bool have_a = false;                                                  /* OUT_LOGMEL, pairs: row_a holds a frame that waits for its partner */
+    long long out_a = 0;
     if (t == 0) mbar_init(&s_bar[team], 1);
     __syncthreads();
 
@@ -572,7 +664,19 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
             } else if constexpr (REGTW) {
                 if constexpr (VVB_FWD_BASETW) team_fft_basetw<C>(v, xb, s_tw2, t, team);
                 else team_fft_regtw<C>(v, xb, twb, t, team);
-                if constexpr (VVB_FWD_HALF_SPLIT) {
+                if constexpr (OUT == OUT_LOGMEL) {
+                    const long long orow = (long long)b * F + frame;
+                    const bool park = a.mel_pair && !have_a;
+                    split_and_store_half<C, OUT, true>(v, xb, hw_t, s_post, t, team, park ? row_a : prow, 0);
+                    if (park) {
+                        have_a = true; out_a = orow;
+                    } else {
+                        if (M + 1 + t < a.mel_prow) prow[M + 1 + t] = 0.f;  /* quads past the last bin read zeros, not stale exchange data */
+                        if (a.mel_pair) mel_phase<2>(a, s_melw, s_melseg, row_a, prow, mout, t, out_a, orow);
+                        else mel_phase<1>(a, s_melw, s_melseg, prow, prow, mout, t, orow, orow);
+                        have_a = false;
+                    }
+                } else if constexpr (VVB_FWD_HALF_SPLIT) {
                     split_and_store_half<C, OUT, true>(v, xb, hw_t, s_post, t, team, a.out, ((long long)b * F + frame) * a.out_pitch);
                 } else {
                     team_store_natural<C>(v, xb, t);
@@ -600,6 +704,9 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
                 team_sync<T>(team);                                    /* xb is reused by the next frame */
             }
         }
+    }
+    if constexpr (OUT == OUT_LOGMEL) {
+        if (have_a) mel_phase<1>(a, s_melw, s_melseg, row_a, row_a, mout, t, out_a, out_a);    /* odd number of frames in this team's range */
     }
 }
 

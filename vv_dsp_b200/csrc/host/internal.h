@@ -5,7 +5,9 @@
 
 /* device-resident sparse mel filterbank: meta = lo | len | off per band, packed non-zero weights */
 /* d_scan (may be NULL): the per-bin records and band ranges of the single-pass log-mel kernel, see mel.c */
-typedef struct mel_device { int* d_meta; float* d_w; size_t n_groups; int* d_scan; } mel_device;
+/* d_fw / d_fseg (may be NULL): lane schedules of the fused STFT -> log-mel kernel (f_segments segments per lane, power row of
+ * f_prow floats), see mel.c build_fused_tables */
+typedef struct mel_device { int* d_meta; float* d_w; size_t n_groups; int* d_scan; float* d_fw; int* d_fseg; size_t f_segments, f_prow; } mel_device;
 int vvdsp_internal_mel_device_build(const float* dense_weights, size_t n_mels, size_t bins, void* stream, mel_device* md);
 void vvdsp_internal_mel_device_free(mel_device* md);
 /* log-mel of densely packed power rows on the device: the single-pass kernel where the filterbank and the sizes allow it,

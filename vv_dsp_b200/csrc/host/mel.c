@@ -86,8 +86,211 @@ void vv_dsp_mel_filterbank_free(vv_dsp_real* filterbank_weights, size_t n_mels)
  * least loaded slot, so that every slot of the kernel walks about the same number of groups. */
 void vvdsp_internal_mel_device_free(mel_device* md)
 {
-    vvb_free(md->d_meta); vvb_free(md->d_w); vvb_free(md->d_scan);
-    md->d_meta = NULL; md->d_w = NULL; md->d_scan = NULL;
+    vvb_free(md->d_meta); vvb_free(md->d_w); vvb_free(md->d_scan); vvb_free(md->d_fw); vvb_free(md->d_fseg);
+    md->d_meta = NULL; md->d_w = NULL; md->d_scan = NULL; md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0;
+}
+
+/* Lane schedules of the fused STFT -> log-mel kernel (csrc/cuda/vvb_stft_kernels.cuh, mel_phase).  The warp that has just
+ * computed a frame's power row sums the bands with its 32 lanes.  A band's ordered float32 sum is one dependent chain, so a
+ * band goes to ONE lane; to keep the 32 lanes in step without any divergence every lane walks the same S segments of
+ * FUSED_U quads (a quad = four consecutive bins starting at a multiple of four) and a band occupies whole consecutive
+ * segments of its lane, from the quad that contains its first non-zero weight on.  Weights are taken from the dense row, so
+ * everything outside the band's support inside those segments is an exact zero that adds nothing -- like the zero weights
+ * of the reference's full-row sum (src/features/mel.c:229-236).  Bands are dealt longest first, each to the fullest lane
+ * that still has room (best fit decreasing), for the smallest S that works.
+ *   d_fw   float4 [S * FUSED_U][32]   weights of lane l's quad at step i
+ *   d_fseg int2   [S][32]             { float offset of the segment's first quad in the power row, (band + 1) << 1 | reset }
+ *                                      reset: the accumulator starts from zero here; band + 1: emit the sum after this segment
+ * Bank conflicts: a lane reads its quad with one LDS.128, which the hardware serves a quarter warp (8 lanes x 16 bytes) at
+ * a time, conflict-free iff the eight quad indices differ mod 8.  Lanes advance in step, so what matters is the residue
+ * of every segment's first quad.  A first placement gave 2.7 wavefronts where one suffices (ncu: +162 conflicts per frame,
+ * the whole fused kernel bound by shared-memory wavefronts), so the schedules are then improved by a deterministic local
+ * search over (a) which physical lane runs which schedule, (b) the order of the bands inside a schedule and (c) starting a
+ * band up to `slack` quads early (zero weights) where its last segment has room: 260 -> 108 wavefronts per frame for the
+ * 80-band / 1025-bin filterbank, against 96 without any conflict.  Idle segments read the least loaded residue.
+ * Not built (the chained kernels serve the call) when the schedule would exceed FUSED_MAX_STEPS quad steps. */
+#define FUSED_U 4
+#define FUSED_LANES 32
+#define FUSED_MAX_STEPS 48
+typedef struct fused_sched {
+    size_t S, n_mels;
+    const int *nseg, *q0;
+    int* delta;                 /* quads a band starts early */
+    int* list;                  /* [32][n_mels]: bands of schedule v in execution order */
+    int count[FUSED_LANES];     /* bands per schedule */
+    int perm[FUSED_LANES];      /* physical lane -> schedule */
+} fused_sched;
+
+/* residue (mod 8) of the first quad of every segment of schedule v, -1 = idle */
+static void fused_residues(const fused_sched* fs, int v, int* res)
+{
+    size_t s = 0;
+    int i, j;
+    for (i = 0; i < fs->count[v]; ++i) {
+        const int b = fs->list[(size_t)v * fs->n_mels + (size_t)i];
+        for (j = 0; j < fs->nseg[b]; ++j) res[s++] = (fs->q0[b] - fs->delta[b] + j * FUSED_U) & 7;
+    }
+    while (s < fs->S) res[s++] = -1;
+}
+
+/* shared-memory wavefronts of the power-row loads per frame: per quarter warp and segment, FUSED_U loads of max-multiplicity */
+static long fused_cost(const fused_sched* fs, int* scratch)
+{
+    long total = 0;
+    int quarter, i;
+    size_t s;
+    for (quarter = 0; quarter < FUSED_LANES / 8; ++quarter) {
+        for (i = 0; i < 8; ++i) fused_residues(fs, fs->perm[quarter * 8 + i], scratch + (size_t)i * fs->S);
+        for (s = 0; s < fs->S; ++s) {
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, idle = 0, worst = 0, k;
+            for (i = 0; i < 8; ++i) { const int r = scratch[(size_t)i * fs->S + s]; if (r < 0) ++idle; else ++cnt[r]; }
+            while (idle-- > 0) { int least = 0; for (k = 1; k < 8; ++k) if (cnt[k] < cnt[least]) least = k; ++cnt[least]; }
+            for (k = 0; k < 8; ++k) if (cnt[k] > worst) worst = cnt[k];
+            total += (long)worst * FUSED_U;
+        }
+    }
+    return total;
+}
+
+static int build_fused_tables(const float* weights, size_t n_mels, size_t bins, const int* lo, const int* len, void* stream, mel_device* md)
+{
+    int *nseg = NULL, *q0 = NULL, *nq = NULL, *order = NULL, *seg = NULL, *scratch = NULL;
+    int load[FUSED_LANES];
+    fused_sched fs;
+    float* wq = NULL;
+    size_t m, total = 0, S, l, prow_quads = (bins + 3) / 4;
+    int st = 0, maxseg = 1, ok = 0, p;
+    unsigned long long rng = 0x9E3779B97F4A7C15ull;
+    long cost;
+    md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0;
+    memset(&fs, 0, sizeof(fs));
+    if (n_mels == 0 || n_mels > 1024 || bins == 0 || bins > (1u << 20)) return 0;
+    nseg = (int*)malloc(n_mels * sizeof(int)); q0 = (int*)malloc(n_mels * sizeof(int)); nq = (int*)malloc(n_mels * sizeof(int));
+    order = (int*)malloc(n_mels * sizeof(int));
+    fs.delta = (int*)calloc(n_mels, sizeof(int)); fs.list = (int*)malloc(FUSED_LANES * n_mels * sizeof(int));
+    if (!nseg || !q0 || !nq || !order || !fs.delta || !fs.list) { st = 4; goto done; }
+    for (m = 0; m < n_mels; ++m) {
+        const int first = len[m] > 0 ? lo[m] : 0, end = len[m] > 0 ? lo[m] + len[m] : 1;
+        const int qa = first / 4, qb = (end + 3) / 4;
+        q0[m] = qa; nq[m] = qb - qa;
+        nseg[m] = (nq[m] + FUSED_U - 1) / FUSED_U;
+        if (nseg[m] > maxseg) maxseg = nseg[m];
+        total += (size_t)nseg[m];
+        if ((size_t)(qa + nseg[m] * FUSED_U) > prow_quads) prow_quads = (size_t)(qa + nseg[m] * FUSED_U);
+    }
+    for (m = 0; m < n_mels; ++m) {                                     /* bands by descending segment count */
+        size_t q = m;
+        while (q > 0 && nseg[order[q - 1]] < nseg[m]) { order[q] = order[q - 1]; --q; }
+        order[q] = (int)m;
+    }
+    S = (total + FUSED_LANES - 1) / FUSED_LANES;
+    if (S < (size_t)maxseg) S = (size_t)maxseg;
+    for (; S * FUSED_U <= FUSED_MAX_STEPS; ++S) {                      /* best fit decreasing for the smallest S that works */
+        ok = 1;
+        for (l = 0; l < FUSED_LANES; ++l) { load[l] = 0; fs.count[l] = 0; }
+        for (m = 0; m < n_mels && ok; ++m) {
+            const int b = order[m];
+            int best = -1;
+            for (l = 0; l < FUSED_LANES; ++l)
+                if (load[l] + nseg[b] <= (int)S && (best < 0 || load[l] > load[best])) best = (int)l;
+            if (best < 0) { ok = 0; break; }
+            fs.list[(size_t)best * n_mels + (size_t)fs.count[best]++] = b;
+            load[best] += nseg[b];
+        }
+        if (ok) break;
+    }
+    if (!ok) goto done;                                                /* no schedule short enough: not an error */
+    fs.S = S; fs.n_mels = n_mels; fs.nseg = nseg; fs.q0 = q0;
+    for (p = 0; p < FUSED_LANES; ++p) fs.perm[p] = p;
+    scratch = (int*)malloc(8 * S * sizeof(int));
+    if (!scratch) { st = 4; goto done; }
+    cost = fused_cost(&fs, scratch);
+    {   /* local search (deterministic): keep every move that does not make the loads slower */
+        const long floor_cost = (long)(S * FUSED_U * (FUSED_LANES / 8));
+        int it;
+        for (it = 0; it < 30000 && cost > floor_cost; ++it) {
+            unsigned r0, r1, r2;
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull; r0 = (unsigned)(rng >> 33);
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull; r1 = (unsigned)(rng >> 33);
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull; r2 = (unsigned)(rng >> 33);
+            if (r0 % 10 < 5) {                                         /* swap the schedules of two lanes */
+                const int a = (int)(r1 % FUSED_LANES), b = (int)(r2 % FUSED_LANES), t = fs.perm[a];
+                long c2;
+                if (a == b) continue;
+                fs.perm[a] = fs.perm[b]; fs.perm[b] = t;
+                c2 = fused_cost(&fs, scratch);
+                if (c2 <= cost) cost = c2; else { fs.perm[b] = fs.perm[a]; fs.perm[a] = t; }
+            } else if (r0 % 10 < 8) {                                  /* start a band early, inside the room of its last segment */
+                const int b = (int)(r1 % n_mels), room = nseg[b] * FUSED_U - nq[b], slack = room < q0[b] ? room : q0[b];
+                const int old = fs.delta[b];
+                long c2;
+                if (slack <= 0) continue;
+                fs.delta[b] = (int)(r2 % (unsigned)(slack + 1));
+                c2 = fused_cost(&fs, scratch);
+                if (c2 <= cost) cost = c2; else fs.delta[b] = old;
+            } else {                                                   /* exchange two bands inside one schedule */
+                const int v = (int)(r1 % FUSED_LANES);
+                if (fs.count[v] > 1) {
+                    int* li = fs.list + (size_t)v * n_mels;
+                    const int i = (int)(r2 % (unsigned)fs.count[v]), j = (int)((r2 >> 8) % (unsigned)fs.count[v]), t = li[i];
+                    long c2;
+                    if (i == j) continue;
+                    li[i] = li[j]; li[j] = t;
+                    c2 = fused_cost(&fs, scratch);
+                    if (c2 <= cost) cost = c2; else { li[j] = li[i]; li[i] = t; }
+                }
+            }
+        }
+    }
+    if (getenv("VVB_MEL_DEBUG"))
+        fprintf(stderr, "vvb: fused log-mel schedule: %zu bands, %zu segments of %d quads per lane, %ld shared-memory wavefronts per frame for the power row (%zu without conflicts)\n",
+                n_mels, S, FUSED_U, cost, S * FUSED_U * (FUSED_LANES / 8));
+    wq = (float*)calloc(S * FUSED_U * FUSED_LANES * 4, sizeof(float));
+    seg = (int*)calloc(S * FUSED_LANES * 2, sizeof(int));
+    if (!wq || !seg) { st = 4; goto done; }
+    for (p = 0; p < FUSED_LANES; p += 8) {                             /* a quarter warp at a time: idle segments take the least loaded residue */
+        size_t s;
+        int i;
+        for (i = 0; i < 8; ++i) fused_residues(&fs, fs.perm[p + i], scratch + (size_t)i * S);
+        for (s = 0; s < S; ++s) {
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, k;
+            for (i = 0; i < 8; ++i) if (scratch[(size_t)i * S + s] >= 0) ++cnt[scratch[(size_t)i * S + s]];
+            for (i = 0; i < 8; ++i)
+                if (scratch[(size_t)i * S + s] < 0) {
+                    int least = 0;
+                    for (k = 1; k < 8; ++k) if (cnt[k] < cnt[least]) least = k;
+                    ++cnt[least];
+                    seg[2 * (s * FUSED_LANES + (size_t)(p + i))] = 4 * least;          /* weights stay zero, nothing is emitted */
+                }
+        }
+    }
+    for (p = 0; p < FUSED_LANES; ++p) {
+        const int v = fs.perm[p];
+        int i, j, u, e, s = 0;
+        for (i = 0; i < fs.count[v]; ++i) {
+            const int b = fs.list[(size_t)v * n_mels + (size_t)i], first_quad = q0[b] - fs.delta[b];
+            for (j = 0; j < nseg[b]; ++j, ++s) {
+                int* d = seg + 2 * ((size_t)s * FUSED_LANES + (size_t)p);
+                d[0] = 4 * (first_quad + j * FUSED_U);
+                d[1] = (j == 0 ? 1 : 0) | (j + 1 == nseg[b] ? (b + 1) << 1 : 0);
+                for (u = 0; u < FUSED_U; ++u)
+                    for (e = 0; e < 4; ++e) {
+                        const size_t k = (size_t)d[0] + 4 * (size_t)u + (size_t)e;
+                        wq[4 * (((size_t)s * FUSED_U + (size_t)u) * FUSED_LANES + (size_t)p) + (size_t)e] = k < bins ? weights[(size_t)b * bins + k] : 0.0f;
+                    }
+            }
+        }
+    }
+    st = vvb_malloc((void**)&md->d_fw, S * FUSED_U * FUSED_LANES * 4 * sizeof(float));
+    if (!st) st = vvb_malloc((void**)&md->d_fseg, S * FUSED_LANES * 2 * sizeof(int));
+    if (!st) st = vvb_memcpy_h2d(md->d_fw, wq, S * FUSED_U * FUSED_LANES * 4 * sizeof(float), stream);
+    if (!st) st = vvb_memcpy_h2d(md->d_fseg, seg, S * FUSED_LANES * 2 * sizeof(int), stream);
+    if (!st) st = vvb_stream_sync(stream);
+    if (!st) { md->f_segments = S; md->f_prow = 4 * prow_quads; }
+    else { vvb_free(md->d_fw); vvb_free(md->d_fseg); md->d_fw = NULL; md->d_fseg = NULL; }
+done:
+    free(nseg); free(q0); free(nq); free(order); free(fs.delta); free(fs.list); free(scratch); free(wq); free(seg);
+    return st;
 }
 
 /* Tables of the single-pass ("scan") log-mel kernel.  A triangular filterbank has at most TWO filters alive at any bin,
@@ -184,6 +387,7 @@ int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t 
     float* packed = NULL;
     int st = 4;
     md->d_meta = NULL; md->d_w = NULL; md->n_groups = 0; md->d_scan = NULL;
+    md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0;
     gcount = (int*)malloc(n_mels * sizeof(int)); gfirst = (int*)malloc(n_mels * sizeof(int));
     order = (int*)malloc(n_mels * sizeof(int)); owner = (int*)malloc(n_mels * sizeof(int));
     load = (int*)malloc(128 * sizeof(int));
@@ -270,6 +474,7 @@ int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t 
     if (!st) st = vvb_stream_sync(stream);          /* the host staging arrays die below */
     if (!st) md->n_groups = groups;
     if (!st) st = build_scan_tables(weights, n_mels, bins, meta, meta + n_mels, stream, md);
+    if (!st) st = build_fused_tables(weights, n_mels, bins, meta, meta + n_mels, stream, md);
 done:
     free(meta); free(packed); free(order); free(gcount); free(gfirst); free(load); free(owner);
     if (st) vvdsp_internal_mel_device_free(md);
@@ -307,7 +512,7 @@ vv_dsp_status vv_dsp_compute_log_mel_spectrogram(const vv_dsp_real* power_spectr
     if (!power_spectrogram || !filterbank_weights || !out_log_mel_spectrogram) return VV_DSP_ERROR_NULL_POINTER;
     if (num_frames == 0 || n_fft_bins == 0 || n_mels == 0) return VV_DSP_ERROR_INVALID_SIZE;
     if (log_epsilon < 0.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
-    md.d_meta = NULL; md.d_w = NULL; md.n_groups = 0;
+    memset(&md, 0, sizeof(md));
     st = vvb_device_ready();                         /* no CUDA device -> UNSUPPORTED, never a CPU computation */
     if (st) return to_status(st);
     st = vvb_stream_create(&stream);

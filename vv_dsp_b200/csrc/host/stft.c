@@ -10,6 +10,7 @@
  * kernel per direction for a whole batch, device-resident or staged through pinned
  * double buffers so host<->device copies overlap the kernels.
  */
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "vv_dsp/b200.h"
@@ -518,7 +519,7 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
     float *d_power, *d_x = NULL, *d_o = NULL;
     unsigned long long hash = 1469598103934665603ull;
     void* stream;
-    int st = 0, pad;
+    int st = 0, pad, fused;
     if (!h || !signals || !filterbank_weights || !out) return VV_DSP_ERROR_NULL_POINTER;
     if ((unsigned)convention > 3u || (unsigned)signals_space > 1u || (unsigned)out_space > 1u) return VV_DSP_ERROR_OUT_OF_RANGE;
     if (n_mels == 0) return VV_DSP_ERROR_INVALID_SIZE;
@@ -547,7 +548,23 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
         if (!st) { h->mel_key_ptr = filterbank_weights; h->mel_key_n = n_mels; h->mel_key_hash = hash; }
         else { h->mel_key_ptr = NULL; h->mel_key_n = 0; }
     }
-    if (!st && h->mel_scratch_bytes < cs * per_signal) {
+    /* one kernel from samples to log-mel rows where the plan has it (fft_size 2048 marching kernel): the power spectrogram
+     * then never exists in HBM and there is no scratch; chunks only bound the host staging buffers */
+    fused = !st && h->mel.d_fw && vvb_stft_forward_logmel_ok(h->eng, h->mel.f_segments, h->mel.f_prow, n_mels);
+    if (getenv("VVB_MEL_DEBUG")) fprintf(stderr, "vvb: STFT -> log-mel: %s\n", fused ? "one fused kernel" : "power kernel + log-mel kernel");
+    if (fused) {
+        const size_t stage_target = (size_t)192 << 20;
+        cs = batch;
+        if (signals_space == VV_DSP_MEM_HOST || out_space == VV_DSP_MEM_HOST) {
+            const size_t per = (n ? n : 1) * sizeof(float) + frames * n_mels * sizeof(float);
+            cs = stage_target / per;
+        } else if (n_coeffs) {
+            cs = scratch_target / (frames * n_mels * sizeof(float));    /* the log-mel rows between the two kernels */
+        }
+        if (cs < 1) cs = 1;
+        if (cs > batch) cs = batch;
+    }
+    if (!st && !fused && h->mel_scratch_bytes < cs * per_signal) {
         st = vvb_stream_sync(stream);
         vvb_free(h->d_mel_scratch); h->d_mel_scratch = NULL; h->mel_scratch_bytes = 0;
         if (!st) st = vvb_malloc((void**)&h->d_mel_scratch, cs * per_signal);
@@ -581,9 +598,14 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
             x_dev = d_x; xp = n ? n : 1;
         }
         if (out_space == VV_DSP_MEM_HOST) o_dev = d_o;
-        if (!st) st = vvb_stft_forward(h->eng, x_dev, nb, n, xp, frames, pad, VVB_OUT_POWER, d_power, h->bins, stream);
         lm_dev = n_coeffs ? h->d_logmel_scratch : o_dev;
-        if (!st) st = vvdsp_internal_logmel(&h->mel, d_power, nb * frames, h->bins, n_mels, log_epsilon, lm_dev, stream);
+        if (fused) {
+            if (!st) st = vvb_stft_forward_logmel(h->eng, x_dev, nb, n, xp, frames, pad, h->mel.d_fw, h->mel.d_fseg, h->mel.f_segments,
+                                                  h->mel.f_prow, n_mels, log_epsilon, lm_dev, stream);
+        } else {
+            if (!st) st = vvb_stft_forward(h->eng, x_dev, nb, n, xp, frames, pad, VVB_OUT_POWER, d_power, h->bins, stream);
+            if (!st) st = vvdsp_internal_logmel(&h->mel, d_power, nb * frames, h->bins, n_mels, log_epsilon, lm_dev, stream);
+        }
         if (!st && n_coeffs) st = vvb_mfcc(lm_dev, nb * frames, n_mels, n_coeffs, h->mfcc.d_table, h->mfcc.d_lifter, o_dev, stream);
         if (!st && out_space == VV_DSP_MEM_HOST)
             st = vvb_memcpy_d2h(out + done * frames * width, d_o, nb * frames * width * sizeof(float), stream);
