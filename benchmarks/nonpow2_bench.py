@@ -44,3 +44,10 @@ if __name__ == "__main__":
     small = label == "direct"
     for nfft, hop in ((400, 160), (1000, 250)):
         run(nfft, hop, 16 if small else 1024, 160_000, label, 2 if small else 5)
+    if not small:
+        # power-of-two sizes with hops that have no marching / pair kernel (generic forward kernel + slot overlap-add)
+        for nfft, hop in ((512, 160), (1024, 160), (2048, 300)):
+            run(nfft, hop, 1024, 160_000, "pow2, odd hop (generic kernels)", 5)
+        run(512, 128, 1024, 160_000, "pow2, hop N/4 (for comparison)", 5)
+        # chirp-z beyond one fused kernel: four-step plans underneath
+        run(6000, 1500, 256, 160_000, "bluestein on four-step plans", 3)
