@@ -252,6 +252,37 @@ def test_full_size_spot_check_against_oracle(oracle):
         assert rel_l2(y[i][nfft:-nfft], refy[nfft:-nfft]) < 2e-5
 
 
+def test_full_size_batch_1024_spot_check_against_oracle(oracle):
+    """BASELINE configs 2/3 at their full size (1024 x 480000 samples, device-resident): the first, a middle and the LAST
+    signal -- the last CTA's range, where a partition error would sit -- bin by bin against the oracle, and the fused
+    log-mel kernel's rows of those signals against the same signals processed alone (range partition independence)."""
+    import torch
+    from vv_dsp_b200 import Stft, mel_filterbank
+    B, n, nfft, hop = 1024, 480000, 2048, 512
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(77)
+    x = torch.rand((B, n), device=dev, generator=g) * 2 - 1
+    st, w = mel_filterbank(nfft, 80, 48000.0, 0.0, 24000.0)
+    assert st == 0
+    with Stft(nfft, hop, "hann") as h:
+        s = h.batch_forward(x, "complex", "valid")
+        y = h.batch_inverse(s, n, True)
+        lm = h.batch_logmel(x, w, 1e-10)
+        torch.cuda.synchronize()
+        for i in (0, 517, B - 1):
+            xi = x[i].cpu().numpy()
+            ref = oracle.stft(xi, nfft, hop)
+            ok, frac = spectra_close(s[i].cpu().numpy(), ref)
+            assert ok, (i, frac)
+            refy = oracle.istft(ref, nfft, hop, n)
+            assert rel_l2(y[i].cpu().numpy()[nfft:-nfft], refy[nfft:-nfft]) < 2e-5
+            alone = h.batch_logmel(x[i:i + 1].contiguous(), w, 1e-10)
+            torch.cuda.synchronize()
+            assert torch.equal(lm[i], alone[0]), i
+    del x, s, y, lm
+    torch.cuda.empty_cache()
+
+
 def test_stream_sharding_nccl():
     """config-4 style frame-range sharding over NCCL; needs >= 2 GPUs (skipped on a 1-GPU box)"""
     import os
