@@ -372,9 +372,35 @@ def main():
     if world > 1:
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * N_SAMPLES / float(te_t.item()) / 1e6
-    h.set_async(False)
     sel = [0, 1, B // 2, B - 1]
     e2e_err = float(np.linalg.norm((yh_np[sel] - xh_np[sel])[:, NFFT:-NFFT]) / np.linalg.norm(xh_np[sel][:, NFFT:-NFFT]))
+
+    # ---- the same step fed with 16-bit PCM as it sits in a WAV file (vv_dsp_stft_batch_forward_pcm): the upload is half
+    # the bytes, the samples are decoded on the device next to the STFT; the output is still float32 in host memory
+    x16 = torch.empty((B, N_SAMPLES), dtype=torch.int16).pin_memory()
+    x16.copy_((x * 32767.0).round().to(torch.int16))
+    x16_np = x16.numpy()
+
+    def e2e_pcm_step():
+        h.batch_forward_pcm(x16_np, 16, "complex", "valid", out=spec)
+        h.batch_inverse(spec, N_SAMPLES, True, out=yh_np)
+        h.synchronize()
+
+    e2e_pcm_step()
+    barrier()
+    tp = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_pcm_step()
+    torch.cuda.synchronize()
+    pcm_s = (time.perf_counter() - tp) / e2e_steps
+    tp_t = torch.tensor([pcm_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tp_t, op=dist.ReduceOp.MAX)
+    e2e_pcm_value = world * B * N_SAMPLES / float(tp_t.item()) / 1e6
+    ref16 = x16_np[sel].astype(np.float32) / 32768.0
+    e2e_pcm_err = float(np.linalg.norm((yh_np[sel] - ref16)[:, NFFT:-NFFT]) / np.linalg.norm(ref16[:, NFFT:-NFFT]))
+    h.set_async(False)
+    del x16, x16_np
 
     fp32_scalar = fp32_packed = None
     if rank == 0:
@@ -431,6 +457,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": B * N_SAMPLES * 4,
                     "ms_per_step": float(te_t.item()) * 1e3, "steps": e2e_steps, "roundtrip_rel_l2": e2e_err,
                     "api": "vv_dsp_stft_set_async(1); vv_dsp_stft_batch_forward(HOST signals -> DEVICE spectra); vv_dsp_stft_batch_inverse(DEVICE spectra -> HOST signals); vv_dsp_stft_synchronize()"},
+            "e2e_pcm16": {"value": e2e_pcm_value, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 2, "d2h_bytes_per_step": B * N_SAMPLES * 4,
+                          "ms_per_step": float(tp_t.item()) * 1e3, "steps": e2e_steps, "roundtrip_rel_l2_vs_decoded_samples": e2e_pcm_err,
+                          "api": "the same with vv_dsp_stft_batch_forward_pcm(HOST 16-bit PCM as in a WAV data chunk): decoded on the device, output still float32 on the host"},
             "gpu_launches": int(launches), "clocks": clocks, "roundtrip_rel_l2": err,
         }
         if stream_line is not None:

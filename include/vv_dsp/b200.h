@@ -93,6 +93,17 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_forward(
     vv_dsp_frame_convention convention, vv_dsp_spec_kind kind,
     void* out, vv_dsp_mem_space out_space, size_t spec_pitch, size_t* out_frames);
 
+/* The same analysis fed with the samples as they sit in a WAV data chunk: HOST rows of mono little-endian PCM
+ * (format 16 / 24 / 32) or IEEE float32 (format -32), signal_pitch in SAMPLES (0 = n).  Chunks are uploaded undecoded (2 or 3
+ * bytes per sample instead of 4) and converted on the device with the scaling of the reference's WAV reader
+ * (src/audio/wav.c:458-521: sample * 2^-15 / 2^-23 / 2^-31), so the spectra equal those of vv_dsp_stft_batch_forward on the
+ * decoded floats bit for bit.  Follows vv_dsp_stft_set_async like the float call. */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_forward_pcm(
+    vv_dsp_stft* h,
+    const void* pcm, int format, size_t batch, size_t n, size_t signal_pitch,
+    vv_dsp_frame_convention convention, vv_dsp_spec_kind kind,
+    void* out, vv_dsp_mem_space out_space, size_t spec_pitch, size_t* out_frames);
+
 /* Synthesis: inverse real FFT + synthesis window + overlap-add of `frames` frames per
  * signal at positions f*hop, into n_out samples per signal (positions >= n_out are
  * dropped like vv_dsp_overlap_add does, src/core/framing.c:139-145; positions no

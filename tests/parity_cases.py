@@ -293,6 +293,35 @@ def check_mel_fused(lib, oracle, cases=((512, 80, 48000.0), (256, 128, 48000.0),
             assert np.abs(e - er).max() <= 1e-4 * er.max()
 
 
+def check_mel_fused_random_filterbanks(lib, seeds=range(6), nfft=2048, hop=512):
+    """The fused kernel takes ANY weight matrix whose lane schedule fits: random band counts, supports, orders, holes and
+    signs, odd and even frame counts per signal (pair flush), against the chained kernels bit for bit."""
+    import os
+    bins = nfft // 2 + 1
+    for seed in seeds:
+        rng = np.random.default_rng(1000 + seed)
+        n_mels = int(rng.integers(1, 97))
+        w = np.zeros((n_mels, bins), np.float32)
+        for m in range(n_mels):
+            length = int(rng.integers(0, 120))                        # 0: an empty band
+            lo = int(rng.integers(0, bins - length + 1))
+            vals = rng.uniform(-0.2, 1.0, length).astype(np.float32)
+            vals[rng.uniform(size=length) < 0.15] = 0.0
+            w[m, lo:lo + length] = vals
+        frames = int(rng.integers(1, 6))
+        n = nfft + hop * (frames - 1) + int(rng.integers(0, hop))
+        x = np.stack([noise(300 + seed * 7 + i, n) for i in range(3)])
+        with Stft(nfft, hop, "hann", lib=lib) as h:
+            fused = h.batch_logmel(x, w, 1e-3)
+            os.environ["VVB_MEL_UNFUSED"] = "1"
+            try:
+                chained = h.batch_logmel(x, w, 1e-3)
+            finally:
+                del os.environ["VVB_MEL_UNFUSED"]
+        assert fused.shape == chained.shape == (3, frames, n_mels)
+        assert np.array_equal(fused, chained, equal_nan=True), (seed, n_mels, frames)
+
+
 def check_mfcc(lib, oracle):
     """vv_dsp_mfcc, the MFCC plan and the batched STFT -> MFCC chain against the oracle (same float32 sums as the
     reference: only the logf feeding the DCT may differ in the last ulp)."""
@@ -368,6 +397,30 @@ def check_pcm_decode(lib, oracle, golden_dir=None):
     assert f(vp(buf), 0, 8, 4, 1, vp(out), 0, 0, None) == 3 and f(vp(buf), 2, 16, 4, 1, vp(out), 0, 0, None) == 3
     assert f(vp(buf), 0, 16, 0, 1, vp(out), 0, 0, None) == 2 and f(vp(buf), 0, 16, 4, 0, vp(out), 0, 0, None) == 2
     assert f(vp(buf), 0, 16, 4, 1, vp(out), 0, 3, None) == 2
+
+
+def check_batch_forward_pcm(lib, nfft=512, hop=128, n=5000, batch=7):
+    """vv_dsp_stft_batch_forward_pcm: WAV samples uploaded undecoded and converted next to the STFT equal the float call on
+    the samples decoded like the reference's reader does (src/audio/wav.c:458-521), bit for bit; several chunks."""
+    from vv_dsp_b200 import pcm_to_planar
+    rng = np.random.default_rng(12)
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        for fmt in (16, 24, 32, -32):
+            if fmt == 16:
+                raw = rng.integers(-32768, 32768, (batch, n), dtype=np.int16)
+            elif fmt == 32:
+                raw = rng.integers(-2**31, 2**31, (batch, n), dtype=np.int64).astype(np.int32)
+            elif fmt == -32:
+                raw = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+            else:
+                raw = rng.integers(0, 256, (batch, 3 * n), dtype=np.uint8)
+            x = np.stack([pcm_to_planar(raw[i].tobytes(), fmt, 1, lib=lib)[0] for i in range(batch)])
+            want = h.batch_forward(x, "complex", "center")
+            got = h.batch_forward_pcm(raw, fmt, "complex", "center")
+            assert np.array_equal(want, got), fmt
+            assert np.array_equal(h.batch_forward(x, "power", "valid"), h.batch_forward_pcm(raw, fmt, "power", "valid")), fmt
+        assert lib.vv_dsp_stft_batch_forward_pcm(h._h, 1, 8, 1, n, n, 0, 0, 1, 0, 0, None) == 3      # a format the reader has not
+        assert lib.vv_dsp_stft_batch_forward_pcm(h._h, None, 16, 1, n, n, 0, 0, 1, 0, 0, None) == 1
 
 
 def check_status_codes(lib):

@@ -91,6 +91,10 @@ def test_mel_fused(emu, oracle):
     pc.check_mel_fused(emu, oracle, cases=((512, 80, 48000.0), (1024, 40, 16000.0)), n=6000, batch=3)
 
 
+def test_mel_fused_random_filterbanks(emu):
+    pc.check_mel_fused_random_filterbanks(emu)
+
+
 def test_mfcc(emu, oracle):
     pc.check_mfcc(emu, oracle)
 
@@ -107,6 +111,11 @@ def test_accuracy_vs_truth(emu, oracle):
     for nfft in (256, 2048, 8192):
         mine, theirs = pc.check_accuracy_vs_truth(emu, oracle, nfft)
         assert mine < theirs
+
+
+def test_batch_forward_pcm(emu, monkeypatch):
+    monkeypatch.setenv("VVB_STAGE_TARGET_BYTES", "40000")              # three chunks
+    pc.check_batch_forward_pcm(emu)
 
 
 def test_pcm_decode(emu, oracle):

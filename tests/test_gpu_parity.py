@@ -173,6 +173,10 @@ def test_mel_fused_kernel_equals_chained_kernels(lib, oracle):
     pc.check_mel_fused(lib, oracle)
 
 
+def test_mel_fused_random_filterbanks(lib):
+    pc.check_mel_fused_random_filterbanks(lib, seeds=range(25))
+
+
 def test_mfcc(lib, oracle):
     pc.check_mfcc(lib, oracle)
 
@@ -298,6 +302,13 @@ def test_stream_sharding_nccl():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "nccl stream sharding ok" in r.stdout
+
+
+def test_batch_forward_pcm(lib, monkeypatch):
+    monkeypatch.setenv("VVB_STAGE_TARGET_BYTES", "40000")
+    pc.check_batch_forward_pcm(lib)
+    monkeypatch.delenv("VVB_STAGE_TARGET_BYTES")
+    pc.check_batch_forward_pcm(lib, 2048, 512, 30000, 5)
 
 
 def test_pcm_decode(lib, oracle):

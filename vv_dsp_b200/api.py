@@ -67,6 +67,8 @@ class Library:
         "vv_dsp_stft_set_async": (C.c_int, [_vp, C.c_int]),
         "vv_dsp_stft_batch_forward": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, C.c_int, _vp, C.c_int, _sz,
                                                 C.POINTER(_sz)]),
+        "vv_dsp_stft_batch_forward_pcm": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, C.c_int, _vp, C.c_int, _sz,
+                                                    C.POINTER(_sz)]),
         "vv_dsp_stft_batch_inverse": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, _vp, C.c_int, _sz, _sz, C.c_int]),
         "vv_dsp_stft_istft": (C.c_int, [_vp, _vp, _sz, _vp, _sz]),
         "vv_dsp_hz_to_mel": (C.c_float, [C.c_float]),
@@ -441,6 +443,29 @@ class Stft:
                                                 CONVENTIONS[convention], KINDS[kind], _ptr(out),
                                                 DEVICE if _is_device(out) else HOST, spec_pitch, C.byref(nf))
         _check(self.lib, st, "vv_dsp_stft_batch_forward")
+        assert nf.value == frames
+        return out
+
+    def batch_forward_pcm(self, pcm, fmt=16, kind="complex", convention="valid", out=None):
+        """vv_dsp_stft_batch_forward_pcm: pcm = HOST [batch, n] numpy array of WAV samples -- int16 (fmt 16), int32 (fmt 32),
+        float32 (fmt -32) or uint8 [batch, 3 n] (fmt 24, packed little-endian).  The upload carries the undecoded bytes."""
+        dt = {16: np.int16, 32: np.int32, -32: np.float32, 24: np.uint8}[fmt]
+        pcm = np.ascontiguousarray(pcm, dt)
+        assert pcm.ndim == 2
+        batch, n = int(pcm.shape[0]), int(pcm.shape[1]) // (3 if fmt == 24 else 1)
+        frames = self.num_frames(n, convention)
+        if out is None:
+            out = np.empty((batch, frames, self.bins), np.complex64 if kind == "complex" else np.float32)
+        spec_pitch = 0
+        if _is_device(out):
+            self._check_device_tensor(out, "complex64" if kind == "complex" else "float32", "out")
+            assert tuple(out.shape) == (batch, frames, self.bins)
+            spec_pitch = self._spec_pitch(out)
+            self._bind_torch_stream(out)
+        nf = _sz(0)
+        st = self.lib.vv_dsp_stft_batch_forward_pcm(self._h, _ptr(pcm), fmt, batch, n, n, CONVENTIONS[convention], KINDS[kind],
+                                                    _ptr(out), DEVICE if _is_device(out) else HOST, spec_pitch, C.byref(nf))
+        _check(self.lib, st, "vv_dsp_stft_batch_forward_pcm")
         assert nf.value == frames
         return out
 

@@ -28,6 +28,7 @@ typedef struct stage_slot {
     void* stream;
     void* d_in;  size_t in_bytes;
     void* d_out; size_t out_bytes;
+    void* d_raw; size_t raw_bytes;     /* PCM ingest: the undecoded samples of a chunk */
 } stage_slot;
 
 struct vv_dsp_stft {
@@ -89,7 +90,7 @@ static void handle_free(vv_dsp_stft* h)
     int i;
     if (!h) return;
     for (i = 0; i < NSLOT; ++i) {
-        vvb_free(h->slot[i].d_in); vvb_free(h->slot[i].d_out);
+        vvb_free(h->slot[i].d_in); vvb_free(h->slot[i].d_out); vvb_free(h->slot[i].d_raw);
         if (h->slot[i].stream) vvb_stream_destroy(h->slot[i].stream);
     }
     for (i = 0; i < NORM_CACHE; ++i) vvb_free(h->norm[i].d_tab);
@@ -291,14 +292,20 @@ static size_t chunk_signals(const vv_dsp_stft* h, size_t batch, size_t bytes_per
 }
 
 /* ------------------------------------------------------------------ batched forward */
-static vv_dsp_status batch_forward_impl(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space,
+/* pcm_format 0: `signals_v` are float32 samples; 16 / 24 / 32 / -32: HOST rows of little-endian PCM (or float32) samples as
+ * they sit in a WAV data chunk (mono, one signal per row, pitch in samples), decoded on the device chunk by chunk with the
+ * scaling of the reference's reader (src/audio/wav.c:458-521) -- the upload then carries 2 or 3 bytes per sample */
+static vv_dsp_status batch_forward_impl(vv_dsp_stft* h, const void* signals_v, int pcm_format, vv_dsp_mem_space signals_space,
                                         size_t batch, size_t n, size_t signal_pitch,
                                         vv_dsp_frame_convention convention, vv_dsp_spec_kind kind, void* out,
                                         vv_dsp_mem_space out_space, size_t spec_pitch, size_t* out_frames)
 {
+    const vv_dsp_real* signals = (const vv_dsp_real*)signals_v;
+    const size_t bps = pcm_format ? (size_t)(pcm_format < 0 ? -pcm_format : pcm_format) / 8 : sizeof(float);
     size_t frames, esize, done;
     int pad, st = 0, c = 0, fast;
     if (!h || !signals || !out) return VV_DSP_ERROR_NULL_POINTER;
+    if (pcm_format && signals_space != VV_DSP_MEM_HOST) return VV_DSP_ERROR_UNSUPPORTED;   /* device PCM: vv_dsp_b200_pcm_to_planar first */
     fast = vvb_engine_is_fast(h->eng);
     if ((unsigned)convention > 3u || (unsigned)kind > 2u || (unsigned)signals_space > 1u || (unsigned)out_space > 1u)
         return VV_DSP_ERROR_OUT_OF_RANGE;
@@ -329,13 +336,26 @@ static vv_dsp_status batch_forward_impl(vv_dsp_stft* h, const vv_dsp_real* signa
             const float* d_x;
             char* d_o;
             size_t xp, op;
-            if (s->in_bytes < in_per * cs || s->out_bytes < out_per * cs || !s->stream) {
+            if (s->in_bytes < in_per * cs || s->out_bytes < out_per * cs || !s->stream || (pcm_format && s->raw_bytes < n * bps * cs)) {
                 if (s->stream) st = vvb_stream_sync(s->stream);        /* about to reallocate its buffers */
                 if (!st) st = slot_reserve(s, in_per * cs, out_per * cs);
+                if (!st && pcm_format && s->raw_bytes < n * bps * cs) {
+                    vvb_free(s->d_raw); s->d_raw = NULL; s->raw_bytes = 0;
+                    st = vvb_malloc(&s->d_raw, n * bps * cs);
+                    if (!st) s->raw_bytes = n * bps * cs;
+                }
             }
             if (!st && !h->async) st = vvb_stream_sync(s->stream);     /* slot free again (stream order suffices when async) */
             if (st) break;
-            if (signals_space == VV_DSP_MEM_HOST) {
+            if (pcm_format) {
+                if (n) {
+                    st = vvb_memcpy2d_h2d(s->d_raw, n * bps, (const char*)signals_v + done * signal_pitch * bps, signal_pitch * bps,
+                                          n * bps, nb, s->stream);
+                    /* the dense chunk is one channel of nb * n samples for the decoder */
+                    if (!st) st = vvb_pcm_to_planar(s->d_raw, pcm_format, nb * n, 1, (float*)s->d_in, nb * n, s->stream);
+                }
+                d_x = (const float*)s->d_in; xp = n;
+            } else if (signals_space == VV_DSP_MEM_HOST) {
                 if (n)
                     st = vvb_memcpy2d_h2d(s->d_in, n * sizeof(float), signals + done * signal_pitch,
                                           signal_pitch * sizeof(float), n * sizeof(float), nb, s->stream);
@@ -701,8 +721,20 @@ vv_dsp_status vv_dsp_stft_batch_forward(vv_dsp_stft* h, const vv_dsp_real* signa
                                         vv_dsp_mem_space out_space, size_t spec_pitch, size_t* out_frames)
 {
     const int prev = dev_enter(h);
-    const vv_dsp_status st = batch_forward_impl(h, signals, signals_space, batch, n, signal_pitch, convention, kind, out, out_space,
+    const vv_dsp_status st = batch_forward_impl(h, signals, 0, signals_space, batch, n, signal_pitch, convention, kind, out, out_space,
                                                 spec_pitch, out_frames);
+    dev_leave(prev);
+    return st;
+}
+vv_dsp_status vv_dsp_stft_batch_forward_pcm(vv_dsp_stft* h, const void* pcm, int format, size_t batch, size_t n, size_t signal_pitch,
+                                            vv_dsp_frame_convention convention, vv_dsp_spec_kind kind, void* out,
+                                            vv_dsp_mem_space out_space, size_t spec_pitch, size_t* out_frames)
+{
+    int prev;
+    vv_dsp_status st;
+    if (format != 16 && format != 24 && format != 32 && format != -32) return VV_DSP_ERROR_OUT_OF_RANGE;
+    prev = dev_enter(h);
+    st = batch_forward_impl(h, pcm, format, VV_DSP_MEM_HOST, batch, n, signal_pitch, convention, kind, out, out_space, spec_pitch, out_frames);
     dev_leave(prev);
     return st;
 }
