@@ -27,8 +27,9 @@
  *
  * Every fft_size >= 1 is served on the GPU: powers of two in [256, 8192] by the fused
  * Stockham kernels (the throughput path), other sizes in [32, 4096] by the fused
- * chirp-z kernel, the rest by direct-DFT kernels (correct, O(n^2) like the reference's
- * path for those sizes).  There is no CPU fallback anywhere.
+ * chirp-z kernel, larger ones up to 2^22 by the chirp-z pipeline on four-step plans, the
+ * rest by direct-DFT kernels (correct, O(n^2) like the reference's path for those
+ * sizes).  There is no CPU fallback anywhere.
  */
 #ifndef VV_DSP_B200_H
 #define VV_DSP_B200_H

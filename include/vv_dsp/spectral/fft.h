@@ -10,10 +10,11 @@
  * unscaled; backward is scaled by 1/n.  C2C: cpx[n] -> cpx[n] (in may alias out);
  * R2C: real[n] -> cpx[n/2+1] with the Nyquist imaginary part forced to 0 for even
  * n; C2R: cpx[n/2+1] -> real[n].  Any n >= 1 is accepted: powers of two 128..8192
- * run the register Stockham kernels, every other n in [32, 4096] a fused chirp-z
- * (Bluestein) kernel on top of them, and the rest (n < 32, non-powers of two above
- * 4096, powers of two above 8192) a direct-DFT kernel like the reference's own
- * O(n^2) path (src/spectral/fft_kiss.c:76-92,115); nothing ever runs on the CPU.
+ * run the register Stockham kernels, powers of two up to 2^26 four-step plans built
+ * on them, every other n in [32, 4096] a fused chirp-z (Bluestein) kernel, other n up
+ * to 2^22 the same chirp-z transform on four-step plans, and the rest (n < 32,
+ * anything larger) a direct-DFT kernel like the reference's own O(n^2) path
+ * (src/spectral/fft_kiss.c:76-92,115); nothing ever runs on the CPU.
  *
  * Backend ids: the B200 engine answers to id 0 (VV_DSP_FFT_BACKEND_KISS, the
  * default every caller uses).  FFTW / FFTS are "not compiled in": selecting them
