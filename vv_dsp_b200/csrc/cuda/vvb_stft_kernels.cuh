@@ -151,6 +151,9 @@ VVB_DEV void mel_phase(const FwdArgs& a, const float4* s_w, const int2* s_seg, c
 {
     __syncwarp();                                                      /* the power rows are complete */
     const int nmp = (a.n_mels + 31) & ~31;
+    /* NF == 2: the band sums sit right behind the parked row, so their address comes off the register that already holds
+     * the row pointer (the compiler otherwise re-derives the buffer address at every emit: ~20 instructions per segment) */
+    if constexpr (NF == 2) mout = const_cast<float*>(row0) + a.mel_prow;
     float acc0 = 0.f, acc1 = 0.f;
     const float4* wq = s_w + t;
 #pragma unroll 1
@@ -183,9 +186,11 @@ VVB_DEV void mel_phase(const FwdArgs& a, const float4* s_w, const int2* s_seg, c
     __syncwarp();
     float* o0 = reinterpret_cast<float*>(a.out) + out_row0 * a.out_pitch;
     float* o1 = reinterpret_cast<float*>(a.out) + out_row1 * a.out_pitch;
-    for (int m = t; m < a.n_mels; m += 32) {
-        o0[m] = logf(mout[m] + a.mel_eps);
-        if constexpr (NF == 2) o1[m] = logf(mout[nmp + m] + a.mel_eps);
+    /* NF * n_mels logarithms dealt evenly over the lanes (80 bands, two frames: 5 rounds instead of 6) */
+    for (int i = t; i < NF * a.n_mels; i += 32) {
+        const bool second = NF == 2 && i >= a.n_mels;
+        const int m = second ? i - a.n_mels : i;
+        (second ? o1 : o0)[m] = logf(mout[(second ? nmp : 0) + m] + a.mel_eps);
     }
     __syncwarp();                                                      /* the rows and the band sums are free again */
 }
@@ -545,11 +550,12 @@ __global__ void __launch_bounds__(C::T* G, MINB) stft_march_kernel(const FwdArgs
         /* the power row lives in the lower half of the team's exchange buffer: the split step publishes and reads only the
          * upper half (floats >= 2 pad(M/2)), and the next frame's first pass overwrites it after the closing team barrier */
         prow = reinterpret_cast<float*>(s_xb + team * C::XBUF);
-        mout = s_mout + team * nmp * (a.mel_pair ? 2 : 1);
-        if (a.mel_pair) {                                                /* second row buffers: written only by the split step, tails stay zero */
-            float* s_rowa = s_mout + G * nmp * 2;
-            for (int i = threadIdx.x; i < G * a.mel_prow; i += blockDim.x) s_rowa[i] = 0.f;
-            row_a = s_rowa + team * a.mel_prow;
+        mout = s_mout + team * nmp;
+        if (a.mel_pair) {                /* per team: [parked row (written only by the split step, tail stays zero) | band sums of two frames] */
+            const int stride = a.mel_prow + 2 * nmp;
+            for (int i = threadIdx.x; i < G * stride; i += blockDim.x) s_mout[i] = 0.f;
+            row_a = s_mout + team * stride;
+            mout = row_a + a.mel_prow;
         }
     }
     bool have_a = false;                                                  /* OUT_LOGMEL, pairs: row_a holds a frame that waits for its partner */
