@@ -346,6 +346,8 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
         if (!getenv("VVB_NO_MARCH")) {           /* zero padding and centred reflect padding both */
             int r = -1;
             /* (at fft_size 512 / 1024 the 2-pass generic forward kernel is faster than a 3-pass marching one) */
+            /* (a producer / consumer split of the forward kernel like istft_ws_kernel was measured slower: the window then
+             * lives in shared memory and the kernel becomes wavefront-bound, profiles/r02_ncu_full_forward_ws_experiment.csv) */
             if (e->nfft == 2048) r = tu_fwd_march_2048(e->hop, a, out_kind, e->sms, stream);
             else if (e->nfft == 4096) r = tu_fwd_march_4096(e->hop, a, out_kind, e->sms, stream);
             else if (e->nfft == 8192) r = tu_fwd_march_8192(e->hop, a, out_kind, e->sms, stream);
