@@ -110,11 +110,6 @@ int vvb_stft_inverse_frames(vvb_engine* e, const vvb_cpx* d_spec, size_t count, 
 int vvb_logmel(const float* d_power, size_t frames, size_t bins, size_t power_pitch, const int* d_meta, const float* d_w,
                size_t n_mels, size_t n_groups, float eps, float* d_out, void* stream);
 
-/* The same result bit for bit by ONE ascending pass over the bins (two accumulators, one per band parity): d_scan = the
- * per-bin records and band ranges csrc/host/mel.c builds for conventional filterbanks.  Densely packed, 16-byte aligned
- * power rows.  6 when the shape does not fit the kernel (caller falls back to vvb_logmel). */
-int vvb_logmel_scan(const float* d_power, size_t frames, size_t bins, const int* d_scan, size_t n_mels, float eps, float* d_out, void* stream);
-
 /* ---- MFCC: d_out[f][k] = d_lifter[k] * sum_n d_logmel[f][n] * d_table[k*n_mels + n], n ascending */
 int vvb_mfcc(const float* d_logmel, size_t frames, size_t n_mels, size_t n_coeffs, const float* d_table,
              const float* d_lifter, float* d_out, void* stream);

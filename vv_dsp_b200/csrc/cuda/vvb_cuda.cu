@@ -926,47 +926,6 @@ extern "C" int vvb_logmel(const float* d_power, size_t frames, size_t bins, size
     return 0;
 }
 
-template <int FR> static int launch_logmel_scan(const MelScanArgs& a, size_t smem, int stages, void* stream)
-{
-    static OccCache occ;
-    if (occ.get(logmel_scan_kernel<FR>, 256, smem) == 0) return fail(4, "logmel_scan_kernel", "does not fit on this device");
-    const long long tiles = (a.frames + FR - 1) / FR;
-    VVB_LAUNCH(logmel_scan_kernel<FR>, (int)std::min<long long>(tiles, rt_num_sms()), 256, smem, stream, a, stages);
-    return 0;
-}
-
-extern "C" int vvb_logmel_scan(const float* d_power, size_t frames, size_t bins, const int* d_scan, size_t n_mels, float eps, float* d_out,
-                               void* stream)
-{
-    if (!d_power || !d_scan || !d_out) return fail(1, "vvb_logmel_scan", "null");
-    if (frames == 0 || n_mels == 0) return 0;
-    if (bins > 0x7fffffffu / 64 || n_mels > 0x7fffffffu / 64) return fail(2, "vvb_logmel_scan", "size");
-    /* measured on B200 (1024 x 480000 samples, 80 bands): 3.39 ms against 1.70 ms for the four-tap group kernel -- a group must scan the
-     * whole support of its bands (~110 dependent steps for 16 frames), so the group kernel stays the default; VVB_MEL_SCAN=1 selects this one */
-    if (((uintptr_t)d_power & 15u) != 0 || getenv("VVB_MEL_SCAN") == nullptr) return 6;
-#ifndef VVB_EMU
-    if (int st = vvb_device_ready()) return st;
-#endif
-    MelScanArgs a;
-    a.power = d_power; a.frames = (long long)frames; a.bins = (int)bins; a.n_mels = (int)n_mels; a.scan = d_scan; a.eps = eps; a.out = d_out;
-    /* the largest tile (frames per tile) whose ring of three still fits beside the records and the staging rows */
-    const size_t budget = 226 * 1024, opitch = n_mels | 1;
-    for (int FR = 16; FR >= 4; FR >>= 1) {
-        const size_t fixed = MEL_HDR + bins * 16 + (size_t)(8 * 32 / FR) * 16 + 2 * (size_t)FR * opitch * 4 + 32;
-        const size_t stage = (size_t)FR * bins * 4;
-        if (fixed + 3 * stage > budget) continue;
-        int stages = (int)((budget - fixed) / stage);
-        if (stages > 4) stages = 4;
-        const size_t smem = fixed + (size_t)stages * stage;
-        switch (FR) {
-            case 16: return launch_logmel_scan<16>(a, smem, stages, stream);
-            case 8: return launch_logmel_scan<8>(a, smem, stages, stream);
-            default: return launch_logmel_scan<4>(a, smem, stages, stream);
-        }
-    }
-    return 6;                                   /* too many bins for the ring: the group kernels serve the call */
-}
-
 extern "C" int vvb_mfcc(const float* d_logmel, size_t frames, size_t n_mels, size_t n_coeffs, const float* d_table,
                         const float* d_lifter, float* d_out, void* stream)
 {

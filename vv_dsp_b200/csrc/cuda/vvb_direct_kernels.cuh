@@ -567,115 +567,6 @@ template <int R, int FPT> __global__ void __launch_bounds__(256 * (2 / FPT)) log
     }
 }
 
-/* ------------------------------------------------------------------ log-mel, single pass over the bins */
-/* Same result as the kernels above, bit for bit, with every power value read ONCE: a conventional (triangular)
- * filterbank has at most two filters alive at a bin, neighbours m and m+1, so one ascending pass with one accumulator
- * per band parity forms every band's ordered sum (tables and argument: csrc/host/mel.c, build_scan_tables).
- *   lane = (frame f of the tile, lane group j): FR frames per tile, 32/FR groups per warp, 8 warps: 8*32/FR groups, each
- *   scanning the bins of its consecutive bands -- P[f][k] (one LDS.32, conflict-free inside a group since bins is odd),
- *   the bin's record { w_even, w_odd, emit_even, emit_odd } (one LDS.128, the same address for a whole group), two
- *   multiplies and two adds (separate roundings: no FMA contraction), band sums parked in a staging row at emit events.
- *   Tiles of FR consecutive frames are ONE contiguous run in memory: one TMA bulk copy per tile into a ring of three,
- *   issued two tiles ahead; one CTA barrier per tile; logf and the coalesced store of the previous tile's band sums
- *   overlap the next tile's scan (double-buffered staging rows).
- * HBM-bound by design: 4 (bins + n_mels) bytes per frame, ~100 shared-memory wavefronts and ~350 issue slots per frame
- * against ~200 cycles of HBM time per frame and SM. */
-struct MelScanArgs {
-    const float* power; long long frames; int bins, n_mels;
-    const int* scan;          /* d_scan of mel_device */
-    float eps; float* out;
-};
-
-VVB_DEV float int_as_float_bits(int v)
-{
-#ifdef VVB_EMU
-    float f; memcpy(&f, &v, sizeof(f)); return f;
-#else
-    return __int_as_float(v);
-#endif
-}
-
-template <int FR> __global__ void __launch_bounds__(256) logmel_scan_kernel(const MelScanArgs a, const int stages)
-{
-    constexpr int LR = 32 / FR, NG = 8 * LR, NTHR = 256;
-#ifdef VVB_EMU
-    char* sm = reinterpret_cast<char*>(vvb_emu::g_dyn_smem);
-#else
-    extern __shared__ __align__(16) float smem[];
-    char* sm = reinterpret_cast<char*>(smem);
-#endif
-    const int bins = a.bins, opitch = a.n_mels | 1;
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm);                  /* [stages] */
-    int4* s_rec = reinterpret_cast<int4*>(sm + MEL_HDR);                                   /* [bins] */
-    int4* s_rng = s_rec + bins;                                                            /* [NG] */
-    float* sOut = reinterpret_cast<float*>(s_rng + NG);                                    /* [2][FR][opitch] */
-    float* ring = sOut + 2 * FR * opitch + ((2 * FR * opitch) & 1 ? 1 : 0);               /* keeps 8-byte steps ... */
-    ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ring) + 15) & ~(uintptr_t)15);   /* ... TMA needs 16 */
-    const size_t stage_floats = (size_t)FR * bins;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int f = lane % FR, grp = warp * LR + lane / FR;
-    {
-        const int4* rec = reinterpret_cast<const int4*>(a.scan + 8);
-        for (int i = tid; i < bins; i += NTHR) s_rec[i] = __ldg(rec + i);
-        const int which = (NG == 16) ? 1 : (NG == 32 ? 2 : 3);
-        const int4* rng = reinterpret_cast<const int4*>(a.scan + __ldg(a.scan + which));
-        if (tid < NG) s_rng[tid] = __ldg(rng + tid);
-        if (tid < stages) mbar_init(&bars[tid], 1);
-    }
-    __syncthreads();
-    const long long ntiles = (a.frames + FR - 1) / FR;
-    const int4 rg = s_rng[grp];
-    /* tile number i of this CTA is global tile blockIdx.x + i * gridDim.x and lives in ring slot i % stages */
-    auto tile_frames = [&](long long tile) -> int { return (int)min((long long)FR, a.frames - tile * FR); };
-    auto bulk_ok = [&](long long tile) -> bool { return ((unsigned)(tile_frames(tile) * (long long)bins * 4) & 15u) == 0; };
-    auto issue = [&](long long i) {
-        const long long tile = blockIdx.x + i * (long long)gridDim.x;
-        if (tile >= ntiles || !bulk_ok(tile)) return;
-        const int s = (int)(i % stages);
-        const unsigned bytes = (unsigned)(tile_frames(tile) * (long long)bins * 4);
-        fence_proxy_async();
-        mbar_expect_tx(&bars[s], bytes);
-        bulk_load(ring + (size_t)s * stage_floats, a.power + tile * (long long)stage_floats, bytes, &bars[s]);
-    };
-    if (tid == 0)
-        for (int i = 0; i < stages - 1; ++i) issue(i);
-    long long i = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-        const int s = (int)(i % stages), nf = tile_frames(tile);
-        float* P = ring + (size_t)s * stage_floats;
-        /* tile i + stages - 1 goes to the slot of tile i - 1, which everyone left at the barrier of the last iteration */
-        if (tid == 0) issue(i + stages - 1);
-        if (bulk_ok(tile)) {
-            mbar_wait(&bars[s], (unsigned)((i / stages) & 1));
-        } else {                                                       /* ragged last tile: not a multiple of 16 bytes */
-            const float* src = a.power + tile * (long long)stage_floats;
-            for (long long q = tid; q < (long long)nf * bins; q += NTHR) P[q] = __ldg(src + q);
-            __syncthreads();
-        }
-        float* so = sOut + (size_t)(i & 1) * FR * opitch + (size_t)f * opitch;
-        const float* Pf = P + (size_t)f * bins;
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-        for (int k = rg.x; k < rg.y; ++k) {
-            const int4 r = s_rec[k];
-            const float p = Pf[k];
-            a0 = __fadd_rn(a0, __fmul_rn(p, int_as_float_bits(r.x)));
-            a1 = __fadd_rn(a1, __fmul_rn(p, int_as_float_bits(r.y)));
-            if (r.z >= 0) { if (r.z >= rg.z && r.z < rg.w) so[r.z] = a0; a0 = 0.f; }
-            if (r.w >= 0) { if (r.w >= rg.z && r.w < rg.w) so[r.w] = a1; a1 = 0.f; }
-        }
-        __syncthreads();                                               /* tile scanned by everyone: its slot is free, its sums are complete */
-        {
-            const float* src = sOut + (size_t)(i & 1) * FR * opitch;
-            float* dst = a.out + tile * (long long)FR * a.n_mels;
-            for (int q = tid; q < nf * a.n_mels; q += NTHR) {
-                const int rr = q / a.n_mels, mm = q - rr * a.n_mels;
-                dst[q] = logf(src[rr * opitch + mm] + a.eps);
-            }
-        }
-    }
-}
-
 /* ------------------------------------------------------------------ MFCC (second half) */
 /* out[f][k] = lifter[k] * sum_n logmel[f][n] * table[k][n], the reference's unnormalised DCT-II
  * (src/spectral/dct.c:21-30) truncated to n_coeffs and liftered (src/features/mel.c:283-295).  The cosine

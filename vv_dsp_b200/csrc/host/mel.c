@@ -86,8 +86,8 @@ void vv_dsp_mel_filterbank_free(vv_dsp_real* filterbank_weights, size_t n_mels)
  * least loaded slot, so that every slot of the kernel walks about the same number of groups. */
 void vvdsp_internal_mel_device_free(mel_device* md)
 {
-    vvb_free(md->d_meta); vvb_free(md->d_w); vvb_free(md->d_scan); vvb_free(md->d_fw); vvb_free(md->d_fseg);
-    md->d_meta = NULL; md->d_w = NULL; md->d_scan = NULL; md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0;
+    vvb_free(md->d_meta); vvb_free(md->d_w); vvb_free(md->d_fw); vvb_free(md->d_fseg);
+    md->d_meta = NULL; md->d_w = NULL; md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0;
 }
 
 /* Lane schedules of the fused STFT -> log-mel kernel (csrc/cuda/vvb_stft_kernels.cuh, mel_phase).  The warp that has just
@@ -293,92 +293,6 @@ done:
     return st;
 }
 
-/* Tables of the single-pass ("scan") log-mel kernel.  A triangular filterbank has at most TWO filters alive at any bin,
- * and they are neighbours m, m+1: so one ascending pass over the bins with one accumulator per band PARITY forms every
- * band's ordered float32 sum -- acc[m & 1] += P[k] * W[m][k] with a separate multiply and add for every bin since the
- * previous band of the same parity ended (zero-weight terms add exactly 0, which is what the reference's full-row sum
- * does too, src/features/mel.c:229-236), emitted and reset at the band's last non-zero bin.  Every power value is read
- * once instead of once per filter that covers it.
- *   record per bin k (16 bytes): { w_even, w_odd, emit_even, emit_odd }   weights of the current even / odd band at k,
- *                                                                          band index to emit after k or -1
- *   ranges (for 16, 32 and 64 lane groups): { first bin, end bin, first band, end band } per group: a group scans the
- *          support of its consecutive bands; bands that merely overlap into its bins are accumulated and dropped.
- * Layout of d_scan (ints): [0] bins, [1..3] offsets of the three range tables, [4..7] spare, records from int 8.
- * Not applicable (d_scan stays NULL, the group kernels serve the call) when a filter is empty, when the supports of
- * two filters of equal parity overlap or are out of order -- i.e. for anything that is not a conventional filterbank. */
-static int build_scan_tables(const float* weights, size_t n_mels, size_t bins, const int* lo, const int* len, void* stream, mel_device* md)
-{
-    static const int group_counts[3] = {16, 32, 64};
-    const size_t rec0 = 8, total_ints = rec0 + 4 * bins + 4 * (16 + 32 + 64);
-    int* tab;
-    size_t m, k;
-    int p, v, st;
-    md->d_scan = NULL;
-    if (n_mels == 0 || bins == 0 || bins > 0x7fffffffu / 8) return 0;
-    for (m = 0; m < n_mels; ++m) {
-        if (len[m] <= 0) return 0;                                   /* an empty filter */
-        if (m >= 2 && lo[m - 2] + len[m - 2] > lo[m]) return 0;       /* same parity: supports must not overlap ... */
-        if (m >= 1 && lo[m] < lo[m - 1]) return 0;                    /* ... and the filters ascend */
-        if (m >= 1 && lo[m] + len[m] < lo[m - 1] + len[m - 1]) return 0;
-    }
-    tab = (int*)calloc(total_ints, sizeof(int));
-    if (!tab) return 4;
-    tab[0] = (int)bins;
-    for (p = 0; p < 2; ++p) {                                          /* records, one parity at a time */
-        size_t cur = (size_t)p;                                        /* the current band of this parity */
-        for (k = 0; k < bins; ++k) {
-            int* r = tab + rec0 + 4 * k;
-            float w = 0.0f;
-            r[2 + p] = -1;
-            if (cur < n_mels) {
-                w = weights[cur * bins + k];
-                if ((int)k == lo[cur] + len[cur] - 1) { r[2 + p] = (int)cur; cur += 2; }
-            }
-            memcpy(&r[p], &w, sizeof(float));
-        }
-    }
-    {   /* ranges: consecutive bands per group, spans balanced by bisection on the largest span allowed */
-        size_t at = rec0 + 4 * bins;
-        for (v = 0; v < 3; ++v) {
-            const int ng = group_counts[v];
-            int lo_span = 1, hi_span = (int)bins, best = (int)bins, g;
-            tab[1 + v] = (int)at;
-            while (lo_span <= hi_span) {
-                const int cap = (lo_span + hi_span) / 2;
-                int groups = 0, ok = 1;
-                m = 0;
-                while (m < n_mels) {
-                    const int first = lo[m];
-                    int end = lo[m] + len[m];
-                    if (end - first > cap) { ok = 0; break; }
-                    ++m;
-                    while (m < n_mels && (lo[m] + len[m]) - first <= cap) { end = lo[m] + len[m]; ++m; }
-                    ++groups;
-                }
-                if (ok && groups <= ng) { best = cap; hi_span = cap - 1; } else lo_span = cap + 1;
-            }
-            m = 0;
-            for (g = 0; g < ng; ++g) {
-                int* r = tab + at + 4 * (size_t)g;
-                if (m >= n_mels) { r[0] = r[1] = 0; r[2] = r[3] = (int)n_mels; continue; }
-                r[0] = lo[m]; r[2] = (int)m;
-                r[1] = lo[m] + len[m];
-                ++m;
-                while (m < n_mels && (lo[m] + len[m]) - r[0] <= best) { r[1] = lo[m] + len[m]; ++m; }
-                r[3] = (int)m;
-            }
-            if (m < n_mels) { free(tab); return 0; }                   /* cannot happen: best admits <= ng groups */
-            at += 4 * (size_t)ng;
-        }
-    }
-    st = vvb_malloc((void**)&md->d_scan, total_ints * sizeof(int));
-    if (!st) st = vvb_memcpy_h2d(md->d_scan, tab, total_ints * sizeof(int), stream);
-    if (!st) st = vvb_stream_sync(stream);
-    free(tab);
-    if (st) { vvb_free(md->d_scan); md->d_scan = NULL; }
-    return st;
-}
-
 int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t bins, void* stream, mel_device* md)
 {
     const size_t hdr = 3 * n_mels;
@@ -386,7 +300,7 @@ int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t 
     int *meta = NULL, *order = NULL, *gcount = NULL, *gfirst = NULL, *load = NULL, *owner = NULL;
     float* packed = NULL;
     int st = 4;
-    md->d_meta = NULL; md->d_w = NULL; md->n_groups = 0; md->d_scan = NULL;
+    md->d_meta = NULL; md->d_w = NULL; md->n_groups = 0;
     md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0;
     gcount = (int*)malloc(n_mels * sizeof(int)); gfirst = (int*)malloc(n_mels * sizeof(int));
     order = (int*)malloc(n_mels * sizeof(int)); owner = (int*)malloc(n_mels * sizeof(int));
@@ -473,7 +387,6 @@ int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t 
     if (!st && w_len) st = vvb_memcpy_h2d(md->d_w, packed, w_len * sizeof(float), stream);
     if (!st) st = vvb_stream_sync(stream);          /* the host staging arrays die below */
     if (!st) md->n_groups = groups;
-    if (!st) st = build_scan_tables(weights, n_mels, bins, meta, meta + n_mels, stream, md);
     if (!st) st = build_fused_tables(weights, n_mels, bins, meta, meta + n_mels, stream, md);
 done:
     free(meta); free(packed); free(order); free(gcount); free(gfirst); free(load); free(owner);
@@ -484,14 +397,6 @@ done:
 int vvdsp_internal_logmel(const mel_device* md, const float* d_power, size_t frames, size_t bins, size_t n_mels, float eps,
                           float* d_out, void* stream)
 {
-    if (md->d_scan) {
-        const int st = vvb_logmel_scan(d_power, frames, bins, md->d_scan, n_mels, eps, d_out, stream);
-        if (getenv("VVB_MEL_DEBUG")) fprintf(stderr, "vvb: log-mel %zu frames x %zu bins -> %zu bands: single-pass kernel %s\n", frames, bins, n_mels,
-                                             st == 6 ? "not applicable" : "used");
-        if (st != 6) return st;                     /* 6: this shape has no single-pass kernel (e.g. too many bins) */
-    } else if (getenv("VVB_MEL_DEBUG")) {
-        fprintf(stderr, "vvb: log-mel: filterbank has no single-pass tables (not a conventional filterbank)\n");
-    }
     return vvb_logmel(d_power, frames, bins, bins, md->d_meta, md->d_w, n_mels, md->n_groups, eps, d_out, stream);
 }
 
