@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Non-power-of-two fft_size (the speech-standard 25 ms / 10 ms framing at 16 kHz: nfft=400, hop=160), device-resident,
-CUDA-event timed: the chirp-z (Bluestein) path against the direct O(n^2) kernels (VVB_NO_BLUESTEIN=1).  One JSON line each."""
+"""Non-power-of-two fft_size and hops without a marching kernel, device-resident, CUDA-event timed: the speech-standard 25 ms /
+10 ms framing at 16 kHz (nfft=400, hop=160: mixed-radix Stockham kernels; VVB_NO_MIXED_RADIX=1: chirp-z; VVB_NO_BLUESTEIN=1:
+the direct O(n^2) kernels), a chirp-z size, power-of-two sizes with odd hops, a size beyond one fused kernel.  One JSON line each."""
 import json
 import os
 import sys
@@ -42,8 +43,9 @@ def run(nfft, hop, B, n, label, reps):
 if __name__ == "__main__":
     label = "direct" if os.environ.get("VVB_NO_BLUESTEIN") else "bluestein"
     small = label == "direct"
-    for nfft, hop in ((400, 160), (1000, 250)):
-        run(nfft, hop, 16 if small else 1024, 160_000, label, 2 if small else 5)
+    mixed = not small and not os.environ.get("VVB_NO_MIXED_RADIX")
+    run(400, 160, 16 if small else 1024, 160_000, "mixed-radix Stockham (Cfg200)" if mixed else label, 2 if small else 5)
+    run(1000, 250, 16 if small else 1024, 160_000, label, 2 if small else 5)
     if not small:
         # power-of-two sizes with hops that have no marching / pair kernel (generic forward kernel + slot overlap-add)
         for nfft, hop in ((512, 160), (1024, 160), (2048, 300)):

@@ -123,15 +123,19 @@ def test_pcm_decode(emu, oracle):
     pc.check_pcm_decode(emu, oracle, os.path.join(os.path.dirname(__file__), "golden"))
 
 
+def test_mixed_radix_speech_sizes(emu, oracle):
+    print(pc.check_bluestein(emu, oracle, [(400, 160), (320, 80)]))
+
+
 def test_bluestein_sizes(emu, oracle):
-    report = pc.check_bluestein(emu, oracle, [(400, 160), (33, 11), (96, 24), (1000, 250)])
+    report = pc.check_bluestein(emu, oracle, [(440, 160), (33, 11), (96, 24), (1000, 250)])
     print("error vs float64 truth (mine, reference):", report)
 
 
 def test_bluestein_unfused_and_direct_paths(emu, oracle, monkeypatch):
     """the multi-kernel chirp-z pipeline and the O(n^2) kernels stay selectable (read when a plan is created)"""
     monkeypatch.setenv("VVB_BLUESTEIN_UNFUSED", "1")
-    pc.check_bluestein(emu, oracle, [(400, 160), (100, 25)])
+    pc.check_bluestein(emu, oracle, [(440, 110), (100, 25)])
     monkeypatch.delenv("VVB_BLUESTEIN_UNFUSED")
     monkeypatch.setenv("VVB_NO_BLUESTEIN", "1")
     pc.check_bluestein(emu, oracle, [(100, 25)])

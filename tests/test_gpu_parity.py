@@ -342,10 +342,26 @@ def test_bluestein_above_4096(lib, oracle):
         assert np.abs(FftPlan(n, 2, -1, lib=lib).execute(r) - xr).max() < 1e-5
 
 
+def test_mixed_radix_speech_sizes(lib, oracle, monkeypatch):
+    """fft_size 400 / 320 (25 ms / 20 ms at 16 kHz) run register Stockham kernels with a 5-point leaf (Cfg200 / Cfg160) instead
+    of the chirp-z transform: same checks against float64 truth and the oracle, several hops, and against the chirp-z path"""
+    report = pc.check_bluestein(lib, oracle, [(400, 160), (400, 100), (320, 80), (320, 160), (400, 200)])
+    print("error vs float64 truth (mine, reference):", report)
+    x = np.stack([noise(900 + i, 16000) for i in range(3)])
+    for nfft, hop in ((400, 160), (320, 80)):
+        with Stft(nfft, hop, "hann", lib=lib) as h:
+            a = h.batch_forward(x, "complex", "center")
+        monkeypatch.setenv("VVB_NO_MIXED_RADIX", "1")
+        with Stft(nfft, hop, "hann", lib=lib) as h:
+            b = h.batch_forward(x, "complex", "center")
+        monkeypatch.delenv("VVB_NO_MIXED_RADIX")
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
+
+
 def test_bluestein_unfused_and_direct_paths(lib, oracle, monkeypatch):
     """the multi-kernel chirp-z pipeline and the O(n^2) kernels stay selectable (read when a plan is created)"""
     monkeypatch.setenv("VVB_BLUESTEIN_UNFUSED", "1")
-    pc.check_bluestein(lib, oracle, [(400, 160), (100, 25)])
+    pc.check_bluestein(lib, oracle, [(440, 110), (100, 25)])
     monkeypatch.delenv("VVB_BLUESTEIN_UNFUSED")
     monkeypatch.setenv("VVB_NO_BLUESTEIN", "1")
     pc.check_bluestein(lib, oracle, [(100, 25)])

@@ -162,7 +162,8 @@ template <class C> static void build_tables(std::vector<float>& blob, const floa
     for (int i = 0; i < N; ++i) {
         const float w = window ? window[i] : 1.0f;
         blob[TB::WIN + i] = w;
-        blob[TB::WSYN + i] = w * (1.0f / (float)M);   /* power-of-two scale: exact */
+        /* 1/M folded into the synthesis window: exact for the power-of-two sizes, one rounding otherwise */
+        blob[TB::WSYN + i] = ((M & (M - 1)) == 0) ? w * (1.0f / (float)M) : (float)((double)w / (double)M);
     }
     auto fill = [&](int off, int R, int NS) {
         for (int r = 1; r < R; ++r)
@@ -200,6 +201,9 @@ template <class C> static void build_tables(std::vector<float>& blob, const floa
 }
 
 static bool fast_size(size_t m) { return m == 128 || m == 256 || m == 512 || m == 1024 || m == 2048 || m == 4096; }
+/* real transforms of fft_size 2 m: the powers of two plus the mixed-radix speech framings 320 and 400 (Cfg160 / Cfg200);
+ * VVB_NO_MIXED_RADIX=1 sends those two through the chirp-z path like any other non-power-of-two size (read at creation) */
+static bool fast_real_size(size_t m) { return fast_size(m) || ((m == 160 || m == 200) && getenv("VVB_NO_MIXED_RADIX") == nullptr); }
 /* plan-API C2C (and the chirp-z transform built on it) also has a 256-thread, three-pass 8192-point kernel */
 static bool fast_c2c_size(size_t n) { return fast_size(n) || n == 8192; }
 static void build_c2c_tables(size_t n, std::vector<float>& blob);
@@ -284,12 +288,14 @@ extern "C" int vvb_engine_create(size_t nfft, size_t hop, const float* window, v
     vvb_engine* e = new (std::nothrow) vvb_engine();
     if (!e) return fail(4, "vvb_engine_create", "oom");
     e->nfft = nfft; e->hop = hop; e->sms = rt_num_sms();
-    e->fast = (nfft % 2 == 0) && fast_size(nfft / 2);
+    e->fast = (nfft % 2 == 0) && fast_real_size(nfft / 2);
     int st = 0;
     std::vector<float> blob;
     if (e->fast) {
         switch (nfft / 2) {
         case 128: build_tables<Cfg128>(blob, window, hop); break;
+        case 160: build_tables<Cfg160>(blob, window, hop); break;
+        case 200: build_tables<Cfg200>(blob, window, hop); break;
         case 256: build_tables<Cfg256>(blob, window, hop); break;
         case 512: build_tables<Cfg512>(blob, window, hop); break;
         case 1024: build_tables<Cfg1024>(blob, window, hop); break;

@@ -184,6 +184,34 @@ template <int N, int STRIDE, int OFF> struct Dit {
 template <int STRIDE, int OFF> struct Dit<1, STRIDE, OFF> {
     VVB_DEV static void run(const float2* in, float2* out) { out[0] = in[OFF]; }
 };
+/* 5-point DFT (the odd leaf of the radix-10 passes of fft_size 400 / 320), forward sign:
+ *     t1 = x1 + x4, t2 = x2 + x3, t3 = x1 - x4, t4 = x2 - x3
+ *     y0 = x0 + t1 + t2,  a = x0 + c1 t1 + c2 t2,  b = x0 + c2 t1 + c1 t2      (c1 = cos 72, c2 = cos 144 degrees)
+ *     p = s1 t3 + s2 t4,  q = s2 t3 - s1 t4                                    (s1 = sin 72, s2 = sin 144 degrees)
+ *     y1 = a - j p,  y4 = a + j p,  y2 = b - j q,  y3 = b + j q */
+template <int STRIDE, int OFF> struct Dit<5, STRIDE, OFF> {
+    VVB_DEV static void run(const float2* in, float2* out)
+    {
+        constexpr float c1 = TwC<5, 1>::c, c2 = TwC<5, 2>::c, s1 = TwC<5, 1>::s, s2 = TwC<5, 2>::s;
+        const float2 x0 = in[OFF], x1 = in[OFF + STRIDE], x2 = in[OFF + 2 * STRIDE], x3 = in[OFF + 3 * STRIDE], x4 = in[OFF + 4 * STRIDE];
+        const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+        out[0] = cadd(x0, cadd(t1, t2));
+        const float2 a = __ffma2_rn(splat(c2), t2, __ffma2_rn(splat(c1), t1, x0));
+        const float2 b = __ffma2_rn(splat(c1), t2, __ffma2_rn(splat(c2), t1, x0));
+        const float2 p = __ffma2_rn(splat(s2), t4, __fmul2_rn(splat(s1), t3));
+        const float2 q = __ffma2_rn(splat(-s1), t4, __fmul2_rn(splat(s2), t3));
+        out[1] = __fadd2_rn(a, make_float2(p.y, -p.x));                /* a - j p */
+        out[4] = __fadd2_rn(a, make_float2(-p.y, p.x));                /* a + j p */
+        out[2] = __fadd2_rn(b, make_float2(q.y, -q.x));
+        out[3] = __fadd2_rn(b, make_float2(-q.y, q.x));
+    }
+};
+/* (M - k) mod M for 0 <= k < M: a mask for the power-of-two sizes (unchanged code), a select for the others */
+template <int M> VVB_DEV int neg_mod(int k)
+{
+    if constexpr ((M & (M - 1)) == 0) return (M - k) & (M - 1);
+    else return k == 0 ? 0 : M - k;
+}
 
 /* in-place (register renaming) DFT of v[O..O+N), natural order in and out */
 template <int N, int O> VVB_DEV void fft_reg(float2* v)

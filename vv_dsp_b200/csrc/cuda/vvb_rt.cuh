@@ -88,6 +88,9 @@ using Cfg1024 = Cfg<1024, 32, 32, 32>;
 using Cfg2048 = Cfg<2048, 32, 32, 8, 8>;      /* T = 64 (two warps per frame), E = 32 */
 using Cfg4096 = Cfg<4096, 32, 32, 16, 8>;     /* T = 128, E = 32 */
 using Cfg8192 = Cfg<8192, 32, 32, 16, 16>;    /* T = 256, E = 32: plan-API C2C only */
+/* mixed radix (a 5-point leaf under the radix-2 tree): the speech framings fft_size 400 (25 ms at 16 kHz) and 320 (20 ms) */
+using Cfg200 = Cfg<200, 50, 10, 10, 2>;       /* T = 4 */
+using Cfg160 = Cfg<160, 20, 10, 4, 4>;        /* T = 8 */
 template <class C> struct Teams { static constexpr int G = (C::T >= 256) ? 1 : 256 / C::T; };   /* 256 threads per CTA */
 
 template <class C> constexpr size_t smem_fwd() { return sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3 + C::POST + 1) + 2 * Teams<C>::G * C::XBUF); }
