@@ -45,6 +45,9 @@ if __name__ == "__main__":
     small = label == "direct"
     mixed = not small and not os.environ.get("VVB_NO_MIXED_RADIX")
     run(400, 160, 16 if small else 1024, 160_000, "mixed-radix Stockham (Cfg200)" if mixed else label, 2 if small else 5)
+    if mixed:
+        run(480, 160, 1024, 160_000, "mixed-radix Stockham (Cfg240)", 5)
+        run(640, 160, 1024, 160_000, "mixed-radix Stockham (Cfg320)", 5)
     run(1000, 250, 16 if small else 1024, 160_000, label, 2 if small else 5)
     if not small:
         # power-of-two sizes with hops that have no marching / pair kernel (generic forward kernel + slot overlap-add)

@@ -26,7 +26,8 @@
  * results are in host memory.
  *
  * Every fft_size >= 1 is served on the GPU: powers of two in [256, 8192] by the fused
- * Stockham kernels (the throughput path), other sizes in [32, 4096] by the fused
+ * Stockham kernels (the throughput path), 320 / 400 / 480 / 640 by mixed-radix Stockham
+ * kernels, other sizes in [32, 4096] by the fused
  * chirp-z kernel, larger ones up to 2^22 by the chirp-z pipeline on four-step plans, the
  * rest by direct-DFT kernels (correct, O(n^2) like the reference's path for those
  * sizes).  There is no CPU fallback anywhere.

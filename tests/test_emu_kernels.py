@@ -124,7 +124,7 @@ def test_pcm_decode(emu, oracle):
 
 
 def test_mixed_radix_speech_sizes(emu, oracle):
-    print(pc.check_bluestein(emu, oracle, [(400, 160), (320, 80)]))
+    print(pc.check_bluestein(emu, oracle, [(400, 160), (320, 80), (480, 160), (640, 160)]))
 
 
 def test_bluestein_sizes(emu, oracle):

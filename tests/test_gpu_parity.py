@@ -343,12 +343,12 @@ def test_bluestein_above_4096(lib, oracle):
 
 
 def test_mixed_radix_speech_sizes(lib, oracle, monkeypatch):
-    """fft_size 400 / 320 (25 ms / 20 ms at 16 kHz) run register Stockham kernels with a 5-point leaf (Cfg200 / Cfg160) instead
+    """fft_size 400 / 320 / 480 / 640 (25 / 20 / 30 / 40 ms at 16 kHz) run register Stockham kernels with 5- and 3-point leaves instead
     of the chirp-z transform: same checks against float64 truth and the oracle, several hops, and against the chirp-z path"""
-    report = pc.check_bluestein(lib, oracle, [(400, 160), (400, 100), (320, 80), (320, 160), (400, 200)])
+    report = pc.check_bluestein(lib, oracle, [(400, 160), (400, 100), (320, 80), (320, 160), (400, 200), (480, 160), (480, 120), (640, 160)])
     print("error vs float64 truth (mine, reference):", report)
     x = np.stack([noise(900 + i, 16000) for i in range(3)])
-    for nfft, hop in ((400, 160), (320, 80)):
+    for nfft, hop in ((400, 160), (320, 80), (480, 160), (640, 320)):
         with Stft(nfft, hop, "hann", lib=lib) as h:
             a = h.batch_forward(x, "complex", "center")
         monkeypatch.setenv("VVB_NO_MIXED_RADIX", "1")

@@ -201,9 +201,12 @@ template <class C> static void build_tables(std::vector<float>& blob, const floa
 }
 
 static bool fast_size(size_t m) { return m == 128 || m == 256 || m == 512 || m == 1024 || m == 2048 || m == 4096; }
-/* real transforms of fft_size 2 m: the powers of two plus the mixed-radix speech framings 320 and 400 (Cfg160 / Cfg200);
- * VVB_NO_MIXED_RADIX=1 sends those two through the chirp-z path like any other non-power-of-two size (read at creation) */
-static bool fast_real_size(size_t m) { return fast_size(m) || ((m == 160 || m == 200) && getenv("VVB_NO_MIXED_RADIX") == nullptr); }
+/* real transforms of fft_size 2 m: the powers of two plus the mixed-radix speech / audio framings 320, 400, 480, 640;
+ * VVB_NO_MIXED_RADIX=1 sends those through the chirp-z path like any other non-power-of-two size (read at creation) */
+static bool fast_real_size(size_t m)
+{
+    return fast_size(m) || ((m == 160 || m == 200 || m == 240 || m == 320) && getenv("VVB_NO_MIXED_RADIX") == nullptr);
+}
 /* plan-API C2C (and the chirp-z transform built on it) also has a 256-thread, three-pass 8192-point kernel */
 static bool fast_c2c_size(size_t n) { return fast_size(n) || n == 8192; }
 static void build_c2c_tables(size_t n, std::vector<float>& blob);
@@ -296,6 +299,8 @@ extern "C" int vvb_engine_create(size_t nfft, size_t hop, const float* window, v
         case 128: build_tables<Cfg128>(blob, window, hop); break;
         case 160: build_tables<Cfg160>(blob, window, hop); break;
         case 200: build_tables<Cfg200>(blob, window, hop); break;
+        case 240: build_tables<Cfg240>(blob, window, hop); break;
+        case 320: build_tables<Cfg320>(blob, window, hop); break;
         case 256: build_tables<Cfg256>(blob, window, hop); break;
         case 512: build_tables<Cfg512>(blob, window, hop); break;
         case 1024: build_tables<Cfg1024>(blob, window, hop); break;

@@ -184,7 +184,21 @@ template <int N, int STRIDE, int OFF> struct Dit {
 template <int STRIDE, int OFF> struct Dit<1, STRIDE, OFF> {
     VVB_DEV static void run(const float2* in, float2* out) { out[0] = in[OFF]; }
 };
-/* 5-point DFT (the odd leaf of the radix-10 passes of fft_size 400 / 320), forward sign:
+/* 3-point DFT (odd leaf of the radix-12 pass of fft_size 480), forward sign:
+ *     t = x1 + x2,  d = x1 - x2,  y0 = x0 + t,  m = x0 - t/2,  y1 = m - j (sqrt3/2) d,  y2 = m + j (sqrt3/2) d */
+template <int STRIDE, int OFF> struct Dit<3, STRIDE, OFF> {
+    VVB_DEV static void run(const float2* in, float2* out)
+    {
+        constexpr float s1 = TwC<3, 1>::s;                            /* sin 120 degrees */
+        const float2 x0 = in[OFF], x1 = in[OFF + STRIDE], x2 = in[OFF + 2 * STRIDE];
+        const float2 t = cadd(x1, x2), d = __fmul2_rn(splat(s1), csub(x1, x2));
+        out[0] = cadd(x0, t);
+        const float2 m = __ffma2_rn(splat(-0.5f), t, x0);
+        out[1] = __fadd2_rn(m, make_float2(d.y, -d.x));               /* m - j d */
+        out[2] = __fadd2_rn(m, make_float2(-d.y, d.x));               /* m + j d */
+    }
+};
+/* 5-point DFT (the odd leaf of the radix-10 / radix-20 passes of fft_size 320 / 400 / 480 / 640), forward sign:
  *     t1 = x1 + x4, t2 = x2 + x3, t3 = x1 - x4, t4 = x2 - x3
  *     y0 = x0 + t1 + t2,  a = x0 + c1 t1 + c2 t2,  b = x0 + c2 t1 + c1 t2      (c1 = cos 72, c2 = cos 144 degrees)
  *     p = s1 t3 + s2 t4,  q = s2 t3 - s1 t4                                    (s1 = sin 72, s2 = sin 144 degrees)

@@ -91,6 +91,10 @@ using Cfg8192 = Cfg<8192, 32, 32, 16, 16>;    /* T = 256, E = 32: plan-API C2C o
 /* mixed radix (a 5-point leaf under the radix-2 tree): the speech framings fft_size 400 (25 ms at 16 kHz) and 320 (20 ms) */
 using Cfg200 = Cfg<200, 50, 10, 10, 2>;       /* T = 4 */
 using Cfg160 = Cfg<160, 20, 10, 4, 4>;        /* T = 8 */
+/* ... and with a 3-point leaf as well: fft_size 480 (30 ms at 16 kHz) and 640 (40 ms).  (960 = 2 x 12.20.2 with 60 points
+ * per thread spills ~200 bytes in every kernel: it stays on the chirp-z path.) */
+using Cfg240 = Cfg<240, 60, 12, 20>;          /* T = 4 */
+using Cfg320 = Cfg<320, 20, 20, 4, 4>;        /* T = 16 */
 template <class C> struct Teams { static constexpr int G = (C::T >= 256) ? 1 : 256 / C::T; };   /* 256 threads per CTA */
 
 template <class C> constexpr size_t smem_fwd() { return sizeof(float) * (2 * C::M + 2 * (C::TW2 + C::TW3 + C::POST + 1) + 2 * Teams<C>::G * C::XBUF); }

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
      * computed or kept in registers is: inter-pass twiddles as powers of a per-thread base (two-pass
      * configurations), split twiddles as per-thread value x compile-time rotation, and the window in
      * registers where E is small enough to keep two CTAs per SM. */
-    constexpr bool REGTW = (C::NP == 2) && !VVB_FWD_TABLE_TWIDDLES;
+    constexpr bool REGTW = (C::NP == 2) && (E <= 32) && !VVB_FWD_TABLE_TWIDDLES;    /* (E = 60: the bases and powers on top of 120 data registers spill) */
     constexpr bool WINREG = (E <= 16) && !VVB_FWD_TABLE_TWIDDLES;
     TwBase twb;
     if constexpr (REGTW) twb = load_tw_base2<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);

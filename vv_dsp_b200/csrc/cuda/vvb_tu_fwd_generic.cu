@@ -1,4 +1,4 @@
-/* vvb_tu_fwd_generic.cu -- stft_forward_kernel instantiations (fft_size 256 ... 8192 and the mixed-radix sizes 320 / 400, any hop). */
+/* vvb_tu_fwd_generic.cu -- stft_forward_kernel instantiations (fft_size 256 ... 8192 and the mixed-radix sizes 320 / 400 / 480 / 640, any hop). */
 #include "vvb_rt.cuh"
 
 namespace vvb {
@@ -35,6 +35,8 @@ int tu_fwd_generic(int m, const FwdArgs& a, int kind, int sms, void* stream)
     case 128: return launch_forward<Cfg128>(a, kind, sms, stream);
     case 160: return launch_forward<Cfg160>(a, kind, sms, stream);
     case 200: return launch_forward<Cfg200>(a, kind, sms, stream);
+    case 240: return launch_forward<Cfg240>(a, kind, sms, stream);
+    case 320: return launch_forward<Cfg320>(a, kind, sms, stream);
     case 256: return launch_forward<Cfg256>(a, kind, sms, stream);
     case 512: return launch_forward<Cfg512>(a, kind, sms, stream);
     case 1024: return launch_forward<Cfg1024>(a, kind, sms, stream);

@@ -43,6 +43,8 @@ template <bool OLA> static int dispatch_inverse(int m, const InvArgs& a, long lo
     case 128: return launch_inverse_t<Cfg128, OLA>(a, batch, sms, stream);
     case 160: return launch_inverse_t<Cfg160, OLA>(a, batch, sms, stream);
     case 200: return launch_inverse_t<Cfg200, OLA>(a, batch, sms, stream);
+    case 240: return launch_inverse_t<Cfg240, OLA>(a, batch, sms, stream);
+    case 320: return launch_inverse_t<Cfg320, OLA>(a, batch, sms, stream);
     case 256: return launch_inverse_t<Cfg256, OLA>(a, batch, sms, stream);
     case 512: return launch_inverse_t<Cfg512, OLA>(a, batch, sms, stream);
     case 1024: return launch_inverse_t<Cfg1024, OLA>(a, batch, sms, stream);
