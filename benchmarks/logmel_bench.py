@@ -53,3 +53,22 @@ with Stft(nfft, hop, "hann") as h:
     ms2 = e0.elapsed_time(e1) / 5
 print(json.dumps({"workload": f"STFT->MFCC, {B} x {n} samples, nfft={nfft} hop={hop}, {n_mels} mels, 13 coefficients", "ms": ms2,
                   "Msamples_per_s": B * n / ms2 / 1e3, "mfcc_stage_ms": ms2 - ms}))
+
+# the speech front end: 16 kHz, 25 ms / 10 ms frames (fft_size 400, hop 160: mixed-radix kernels), 80 bands
+B3, n3, nfft3, hop3 = 1024, 160_000, 400, 160
+x3 = torch.rand((B3, n3), device=dev) * 2 - 1
+st3, w3 = mel_filterbank(nfft3, n_mels, 16000.0, 0.0, 8000.0)
+F3 = 1 + (n3 - nfft3) // hop3
+out3 = torch.empty((B3, F3, n_mels), device=dev)
+with Stft(nfft3, hop3, "hann") as h:
+    h.set_stream(s.cuda_stream)
+    for _ in range(2):
+        h.batch_logmel(x3, w3, 1e-10, out=out3)
+    torch.cuda.synchronize()
+    e0.record(s)
+    for _ in range(5):
+        h.batch_logmel(x3, w3, 1e-10, out=out3)
+    e1.record(s); torch.cuda.synchronize()
+    ms3 = e0.elapsed_time(e1) / 5
+print(json.dumps({"workload": f"STFT->log-mel, {B3} x {n3} samples (10 s at 16 kHz), nfft={nfft3} hop={hop3}, {n_mels} mels", "ms": ms3,
+                  "Msamples_per_s": B3 * n3 / ms3 / 1e3, "path": "mixed-radix power kernel + log-mel kernel through a device scratch"}))
