@@ -239,6 +239,9 @@ template <int N, int O> VVB_DEV void fft_reg(float2* v)
 /* register slot of output r of an R-point fft_reg (identity: natural order) */
 VVB_CX int ct_bitrev(int r, int) { return r; }
 
+#ifndef VVB_SWIZZLE_884
+#define VVB_SWIZZLE_884 1             /* one-warp 8.8.4 configuration: XOR swizzle of the exchange buffer instead of padding (A/B builds: 0) */
+#endif
 /* ------------------------------------------------------------ team configuration */
 /* M complex points, E per thread, up to three passes with radices R1*R2*R3 == M */
 template <int M_, int E_, int R1_, int R2_, int R3_ = 1> struct Cfg {
@@ -253,8 +256,17 @@ template <int M_, int E_, int R1_, int R2_, int R3_ = 1> struct Cfg {
     static_assert(E_ % R1_ == 0 && E_ % R2_ == 0 && E_ % R3_ == 0, "E must be a multiple of every radix");
     static_assert(E_ >= 2 && (M_ / 2) % T == 0, "split step needs M/2 pairs divisible over the team");
     /* padded shared-memory position: one float2 of padding every R1 elements makes the
-     * stride-R1 writes of pass 1 hit 16 distinct bank pairs per half warp */
-    VVB_DEV static int pad(int i) { return i + i / R1_; }
+     * stride-R1 writes of pass 1 hit 16 distinct bank pairs per half warp.
+     * The one-warp 8.8.4 configuration (fft_size 256 ISTFT) is swizzled instead: with the padding its pass-2 / pass-3 reads
+     * (16 consecutive elements per half warp) spanned two padding steps and lanes 0 and 15 met in one bank pair -- ncu:
+     * 2 x the ideal wavefronts on all 16 loads, a quarter of the kernel's shared-memory traffic at 89 % of that peak.
+     * XOR of the bank-pair index with bits 4-6 and of its top bit with bit 6 of the element index keeps the stride-8 writes
+     * of pass 1, the (64 a + b) writes of pass 2 and the consecutive reads all conflict-free. */
+    VVB_DEV static int pad(int i)
+    {
+        if constexpr (VVB_SWIZZLE_884 && M_ == 256 && E_ == 8 && R1_ == 8 && R2_ == 8) return i ^ ((i >> 4) & 7) ^ (((i >> 6) & 1) << 3);
+        else return i + i / R1_;
+    }
 };
 
 /* team barrier: sub-warp and warp teams use __syncwarp (all teams of a warp run in

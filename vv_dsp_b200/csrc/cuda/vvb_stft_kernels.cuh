@@ -39,6 +39,9 @@
 #define VVB_INV_PAIRMERGE 0           /* marching ISTFT, 32 x 32: merge bins k and M-k together (0 = every thread merges all its bins alone,
                                          1 = partner values through warp shuffles, 2 = through the exchange buffer) */
 #endif
+#ifndef VVB_PAIR_TW3
+#define VVB_PAIR_TW3 true             /* pair ISTFT (fft_size 256 / 512): inter-pass twiddles computed from bases instead of 13-23 table loads */
+#endif
 #ifndef VVB_FWD_TABLE_TWIDDLES
 #define VVB_FWD_TABLE_TWIDDLES 0      /* 1: the generic forward kernel loads twiddles / window from shared memory (A/B builds) */
 #endif
@@ -1301,7 +1304,7 @@ __global__ void __launch_bounds__(32 * G, MINB) istft_pair_kernel(const PairArgs
                         }
                 }
                 if constexpr (VVB_INV_BASETW && C::R1 == 32 && C::R2 == 32 && C::NP == 2) team_fft_basetw<C>(v, xb, s_tw2, t, team);
-                else team_fft<C>(v, xb, s_tw2, s_tw3, t, team);
+                else team_fft_march<C, VVB_PAIR_TW3>(v, xb, s_tw2, s_tw3, t, team);      /* three passes: computed inter-pass twiddles */
                 /* v = (N x_{f+1}[i], N x_f[i]) for i = t + 32 (q + r NS/32) */
 #pragma unroll
                 for (int q = 0; q < L::NQ; ++q)
