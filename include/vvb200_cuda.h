@@ -33,6 +33,7 @@ int vvb_sm_clock_mhz(void* stream, double* mhz); /* diagnostics: SM clock right 
 int vvb_malloc(void** dptr, size_t bytes);
 int vvb_free(void* dptr);
 int vvb_host_alloc(void** hptr, size_t bytes);   /* pinned */
+int vvb_host_memory_is_device_visible(void);     /* 1: kernels may dereference vvb_host_alloc memory (unified addressing) */
 int vvb_host_free(void* hptr);
 int vvb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
 int vvb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
@@ -121,6 +122,7 @@ int vvb_pcm_to_planar(const void* d_interleaved, int format, size_t num_samples,
 /* ---- FFT engine (plan API): type 0 C2C, 1 R2C, 2 C2R; dir +1 / -1 */
 int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine** out);
 void vvb_fft_engine_destroy(vvb_fft_engine* e);
+int vvb_fft_engine_is_single_kernel(const vvb_fft_engine* e);   /* one kernel that reads its input once */
 int vvb_fft_exec(vvb_fft_engine* e, const void* d_in, void* d_out, size_t batch, void* stream);
 
 #ifdef __cplusplus

@@ -44,6 +44,7 @@ extern "C" int vvb_device_ready(void) { return 0; }
 extern "C" int vvb_malloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : fail(4, "malloc", "oom"); }
 extern "C" int vvb_free(void* p) { free(p); return 0; }
 extern "C" int vvb_host_alloc(void** p, size_t bytes) { return vvb_malloc(p, bytes); }
+extern "C" int vvb_host_memory_is_device_visible(void) { return 0; }
 extern "C" int vvb_host_free(void* p) { free(p); return 0; }
 extern "C" int vvb_memcpy_h2d(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
 extern "C" int vvb_memcpy_d2h(void* d, const void* s, size_t n, void*) { memcpy(d, s, n); return 0; }
@@ -96,6 +97,14 @@ extern "C" int vvb_device_ready(void)
 extern "C" int vvb_malloc(void** p, size_t bytes) { CK(cudaMalloc(p, bytes ? bytes : 1)); return 0; }
 extern "C" int vvb_free(void* p) { if (p) CK(cudaFree(p)); return 0; }
 extern "C" int vvb_host_alloc(void** p, size_t bytes) { CK(cudaMallocHost(p, bytes ? bytes : 1)); return 0; }
+extern "C" int vvb_host_memory_is_device_visible(void)
+{
+    int dev = 0, uva = 0, native = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaDeviceGetAttribute(&uva, cudaDevAttrUnifiedAddressing, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaDeviceGetAttribute(&native, cudaDevAttrCanUseHostPointerForRegisteredMem, dev) != cudaSuccess) { cudaGetLastError(); native = 0; }
+    return uva && native;
+}
 extern "C" int vvb_host_free(void* p) { if (p) CK(cudaFreeHost(p)); return 0; }
 extern "C" int vvb_memcpy_h2d(void* d, const void* s, size_t n, void* st) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, (cudaStream_t)st)); return 0; }
 extern "C" int vvb_memcpy_d2h(void* d, const void* s, size_t n, void* st) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, (cudaStream_t)st)); return 0; }
@@ -642,6 +651,15 @@ extern "C" int vvb_fft_engine_create(size_t n, int type, int dir, vvb_fft_engine
     if (st) { vvb_fft_engine_destroy(e); return st; }
     *out = e;
     return 0;
+}
+
+/* 1 when one transform is ONE kernel that reads its input once (Stockham, fused chirp-z): such a plan may run straight on
+ * mapped host memory; the multi-kernel pipelines and the O(n^2) kernels may not */
+extern "C" int vvb_fft_engine_is_single_kernel(const vvb_fft_engine* e)
+{
+    if (!e) return 0;
+    if (e->type == 0) return e->fast_c2c || (e->chirp && e->chirp->fused);
+    return e->real && (e->real->fast || (e->real->chirp && e->real->chirp->fused));
 }
 
 extern "C" void vvb_fft_engine_destroy(vvb_fft_engine* e)

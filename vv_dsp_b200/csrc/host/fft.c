@@ -27,6 +27,7 @@ struct vv_dsp_fft_plan {
     vvb_fft_engine* eng;
     void* stream;
     void *h_in, *h_out;      /* pinned staging */
+    int zero_copy;           /* vv_dsp_fft_execute runs the kernel on h_in / h_out directly */
     void *d_in, *d_out;
     size_t in_bytes, out_bytes;
 };
@@ -82,6 +83,7 @@ vv_dsp_status vv_dsp_fft_make_plan(size_t n, vv_dsp_fft_type type, vv_dsp_fft_di
     if (!st) st = vvb_stream_create(&p->stream);
     if (!st) st = vvb_host_alloc(&p->h_in, p->in_bytes);
     if (!st) st = vvb_host_alloc(&p->h_out, p->out_bytes);
+    p->zero_copy = !st && vvb_fft_engine_is_single_kernel(p->eng) && vvb_host_memory_is_device_visible() && getenv("VVB_PERFRAME_STAGED") == NULL;
     if (!st) st = vvb_malloc(&p->d_in, p->in_bytes);
     if (!st) st = vvb_malloc(&p->d_out, p->out_bytes);
     if (st) {
@@ -97,9 +99,14 @@ vv_dsp_status vv_dsp_fft_execute(const vv_dsp_fft_plan* plan, const void* in, vo
     int st;
     if (!plan || !in || !out) return VV_DSP_ERROR_NULL_POINTER;
     memcpy(plan->h_in, in, plan->in_bytes);
-    st = vvb_memcpy_h2d(plan->d_in, plan->h_in, plan->in_bytes, plan->stream);
-    if (!st) st = vvb_fft_exec(plan->eng, plan->d_in, plan->d_out, 1, plan->stream);
-    if (!st) st = vvb_memcpy_d2h(plan->h_out, plan->d_out, plan->out_bytes, plan->stream);
+    if (plan->zero_copy) {
+        /* single-kernel plans run straight on the pinned, device-visible staging buffers: one launch instead of three operations */
+        st = vvb_fft_exec(plan->eng, plan->h_in, plan->h_out, 1, plan->stream);
+    } else {
+        st = vvb_memcpy_h2d(plan->d_in, plan->h_in, plan->in_bytes, plan->stream);
+        if (!st) st = vvb_fft_exec(plan->eng, plan->d_in, plan->d_out, 1, plan->stream);
+        if (!st) st = vvb_memcpy_d2h(plan->h_out, plan->d_out, plan->out_bytes, plan->stream);
+    }
     if (!st) st = vvb_stream_sync(plan->stream);
     if (st) return VV_DSP_ERROR_INTERNAL;
     memcpy(out, plan->h_out, plan->out_bytes);

@@ -47,6 +47,7 @@ struct vv_dsp_stft {
     /* stream-ordered mode (vv_dsp_stft_set_async): host-space calls only enqueue work; a later call that
      * reads a device buffer produced chunk by chunk by an earlier one waits per chunk, on these events */
     int async;
+    int zero_copy;                    /* per-frame calls: the kernels read / write the pinned staging buffers directly */
     struct { const char* lo; const char* hi; void* ev; int valid; } dep[NDEP];
     int dep_next;
     size_t stage_target;              /* staging bytes per slot and direction */
@@ -140,6 +141,8 @@ vv_dsp_status vv_dsp_stft_create(const vv_dsp_stft_params* params, vv_dsp_stft**
     if (!st) st = vvb_host_alloc((void**)&h->h_in, h->nfft * sizeof(float));
     if (!st) st = vvb_host_alloc((void**)&h->h_spec, h->bins * sizeof(vvb_cpx));
     if (!st) st = vvb_host_alloc((void**)&h->h_frame, h->nfft * sizeof(float));
+    /* (emulator builds and VVB_PERFRAME_STAGED=1 keep the explicit copies) */
+    h->zero_copy = vvb_host_memory_is_device_visible() && getenv("VVB_PERFRAME_STAGED") == NULL;
     if (!st) st = vvb_malloc((void**)&h->d_in, h->nfft * sizeof(float));
     if (!st) st = vvb_malloc((void**)&h->d_spec, h->bins * sizeof(vvb_cpx));
     if (!st) st = vvb_malloc((void**)&h->d_frame, h->nfft * sizeof(float));
@@ -162,10 +165,16 @@ static vv_dsp_status process_impl(vv_dsp_stft* h, const vv_dsp_real* in, vv_dsp_
     size_t k;
     if (!h || !in || !out) return VV_DSP_ERROR_NULL_POINTER;
     memcpy(h->h_in, in, h->nfft * sizeof(float));
-    st = vvb_memcpy_h2d(h->d_in, h->h_in, h->nfft * sizeof(float), h->stream);
-    if (!st) st = vvb_stft_forward(h->eng, h->d_in, 1, h->nfft, h->nfft, 1, VVB_PAD_ZERO, VVB_OUT_COMPLEX,
-                                   h->d_spec, h->bins, h->stream);
-    if (!st) st = vvb_memcpy_d2h(h->h_spec, h->d_spec, h->bins * sizeof(vvb_cpx), h->stream);
+    if (h->zero_copy) {
+        /* one launch instead of copy + launch + copy: the pinned staging buffers are mapped into the device's address
+         * space (unified addressing), so the kernel reads the frame and writes the spectrum over the host link itself */
+        st = vvb_stft_forward(h->eng, h->h_in, 1, h->nfft, h->nfft, 1, VVB_PAD_ZERO, VVB_OUT_COMPLEX, h->h_spec, h->bins, h->stream);
+    } else {
+        st = vvb_memcpy_h2d(h->d_in, h->h_in, h->nfft * sizeof(float), h->stream);
+        if (!st) st = vvb_stft_forward(h->eng, h->d_in, 1, h->nfft, h->nfft, 1, VVB_PAD_ZERO, VVB_OUT_COMPLEX,
+                                       h->d_spec, h->bins, h->stream);
+        if (!st) st = vvb_memcpy_d2h(h->h_spec, h->d_spec, h->bins * sizeof(vvb_cpx), h->stream);
+    }
     if (!st) st = vvb_stream_sync(h->stream);
     if (st) return map_status(st);
     /* bins 0..nfft/2 from the device; the rest is the conjugate mirror of a real input's spectrum */
@@ -187,9 +196,13 @@ static vv_dsp_status reconstruct_impl(vv_dsp_stft* h, const vv_dsp_cpx* in, vv_d
         h->h_spec[k].re = 0.5f * (a.re + b.re);
         h->h_spec[k].im = 0.5f * (a.im - b.im);
     }
-    st = vvb_memcpy_h2d(h->d_spec, h->h_spec, h->bins * sizeof(vvb_cpx), h->stream);
-    if (!st) st = vvb_stft_inverse_frames(h->eng, h->d_spec, 1, h->bins, h->d_frame, h->stream);
-    if (!st) st = vvb_memcpy_d2h(h->h_frame, h->d_frame, n * sizeof(float), h->stream);
+    if (h->zero_copy) {
+        st = vvb_stft_inverse_frames(h->eng, h->h_spec, 1, h->bins, h->h_frame, h->stream);
+    } else {
+        st = vvb_memcpy_h2d(h->d_spec, h->h_spec, h->bins * sizeof(vvb_cpx), h->stream);
+        if (!st) st = vvb_stft_inverse_frames(h->eng, h->d_spec, 1, h->bins, h->d_frame, h->stream);
+        if (!st) st = vvb_memcpy_d2h(h->h_frame, h->d_frame, n * sizeof(float), h->stream);
+    }
     if (!st) st = vvb_stream_sync(h->stream);
     if (st) return map_status(st);
     for (i = 0; i < n; ++i) {
