@@ -518,6 +518,8 @@ static int launch_inverse_marching(vvb_engine* e, const InvArgs& a, long long ba
         if (!getenv("VVB_NO_WS")) r = tu_inv_ws_2048(e->hop, a, batch, e->sms, stream);
         if (r < 0) r = tu_inv_march_2048(e->hop, a, batch, e->sms, stream);
     }
+    /* (a producer / consumer split between two-warp teams was built for fft_size 4096 and measured slower: the consumer team
+     * holds two of the three passes and loses the half exchange, profiles/r02_ncu_full_istft_ws3_experiment.csv) */
     else if (e->nfft == 4096) r = tu_inv_march_4096(e->hop, a, batch, e->sms, stream);
     else if (e->nfft == 8192) r = tu_inv_march_8192(e->hop, a, batch, e->sms, stream);
     return r;
