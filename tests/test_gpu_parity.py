@@ -287,6 +287,46 @@ def test_full_size_batch_1024_spot_check_against_oracle(oracle):
     torch.cuda.empty_cache()
 
 
+def test_one_handle_per_thread_concurrently(lib, oracle):
+    """one handle (and one plan) per thread, like the reference (src/spectral/stft.c:13-18).  Four threads
+    run different sizes at once -- batched calls, the fused log-mel kernel, the per-frame API and a plan -- and every result
+    equals the one computed alone (ctypes releases the GIL, so the calls really overlap)."""
+    import threading
+    from vv_dsp_b200 import mel_filterbank
+    jobs = [(2048, 512), (512, 128), (400, 160), (4096, 1024)]
+    xs = [np.stack([noise(2100 + 10 * j + i, 30000) for i in range(4)]) for j in range(len(jobs))]
+    st, w = mel_filterbank(2048, 40, 16000.0, 0.0, 8000.0, lib=lib)
+    assert st == 0
+
+    def work(j, out):
+        nfft, hop = jobs[j]
+        res = []
+        with Stft(nfft, hop, "hann", lib=lib) as h:
+            for _ in range(3):
+                s = h.batch_forward(xs[j], "complex", "center")
+                y = h.batch_inverse(s, xs[j].shape[1], True)
+                res += [s, y]
+            if nfft == 2048:
+                res.append(h.batch_logmel(xs[j], w, 1e-6))
+            res.append(h.process(xs[j][0, :nfft]))
+        z = (xs[j][0, :256] + 1j * xs[j][1, :256]).astype(np.complex64)
+        res.append(FftPlan(256, 0, +1, lib=lib).execute(z))
+        out[j] = res
+
+    alone, together = {}, {}
+    for j in range(len(jobs)):
+        work(j, alone)
+    threads = [threading.Thread(target=work, args=(j, together)) for j in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for j in range(len(jobs)):
+        assert len(alone[j]) == len(together[j])
+        for a, b in zip(alone[j], together[j]):
+            assert np.array_equal(a, b), jobs[j]
+
+
 def test_stream_sharding_nccl():
     """config-4 style frame-range sharding over NCCL; needs >= 2 GPUs (skipped on a 1-GPU box)"""
     import os
