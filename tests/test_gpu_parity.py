@@ -38,7 +38,7 @@ def test_reference_known_answers(lib):
 
 
 @pytest.mark.parametrize("nfft,hop,win", [(2048, 512, "hann"), (1024, 256, "hamming"), (256, 64, "boxcar"),
-                                          (4096, 1024, "hann"), (64, 32, "hann"), (12, 5, "boxcar"), (200, 50, "hann")])
+                                          (4096, 1024, "hann"), (64, 32, "hann"), (12, 5, "boxcar"), (200, 50, "hann"), (400, 160, "hann")])
 def test_per_frame_api(lib, oracle, nfft, hop, win):
     pc.check_per_frame_api(lib, oracle, nfft, hop, win)
 
@@ -285,6 +285,23 @@ def test_full_size_batch_1024_spot_check_against_oracle(oracle):
             assert torch.equal(lm[i], alone[0]), i
     del x, s, y, lm
     torch.cuda.empty_cache()
+
+
+def test_per_frame_api_with_explicit_copies(lib, oracle, monkeypatch):
+    """per-frame calls normally run their kernel on the pinned staging buffers (zero-copy); VVB_PERFRAME_STAGED=1 keeps
+    the copy + launch + copy sequence: both must give the same bits"""
+    x = noise(31, 2048)
+    z = (noise(32, 512) + 1j * noise(33, 512)).astype(np.complex64)
+    with Stft(2048, 512, "hann", lib=lib) as h:
+        a = h.process(x)
+    fa = FftPlan(512, 0, +1, lib=lib).execute(z)
+    monkeypatch.setenv("VVB_PERFRAME_STAGED", "1")
+    pc.check_per_frame_api(lib, oracle, 2048, 512, "hann")
+    pc.check_per_frame_api(lib, oracle, 400, 160, "hamming")
+    with Stft(2048, 512, "hann", lib=lib) as h:
+        b = h.process(x)
+    fb = FftPlan(512, 0, +1, lib=lib).execute(z)
+    assert np.array_equal(a, b) and np.array_equal(fa, fb)
 
 
 def test_one_handle_per_thread_concurrently(lib, oracle):
