@@ -43,11 +43,14 @@ namespace vvb {
 #define VVB_WS_DIRECT 0               /* producer reads the half spectrum straight from global memory into the merge registers
                                          (no TMA stage: the stage cost 64 shared-memory write + 64 read wavefronts per frame) */
 #endif
+/* register split of the two roles (8 producer + 8 consumer warps x 32 lanes x (P + C) = 64 K).  Same-box A/B, interleaved
+ * launches, headline shape: 104 / 152 -> 1.995 ms, 96 / 160 -> 1.933, 112 / 144 -> 1.926, 120 / 136 -> 2.245 (on a
+ * power-capped box at 1.68 GHz): the multiples of 16 win by 3 %; 96 / 160 also spills least at the other hops */
 #ifndef VVB_WS_PRODUCER_REGS
-#define VVB_WS_PRODUCER_REGS 104
+#define VVB_WS_PRODUCER_REGS 96
 #endif
 #ifndef VVB_WS_CONSUMER_REGS
-#define VVB_WS_CONSUMER_REGS 152
+#define VVB_WS_CONSUMER_REGS 160
 #endif
 
 template <int REGS> VVB_DEV void setmaxnreg_dec()
