@@ -475,6 +475,20 @@ def main():
             dt1 = run1()
             line["cpu_baseline_1thread"] = {"value": B1 * N_SAMPLES / dt1 / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
                                             "sample": f"{B1} signals x {N_SAMPLES} samples, same loop, {dt1:.1f} s"}
+            # also the forward + re^2 + im^2 loop (configs[1] as literally stated), all cores, a few seconds
+            try:
+                import numpy as np
+                from oracle.oracle import Oracle, Reference
+                impl = Reference() if Reference.available() else Oracle()
+                xp = np.random.default_rng(4321).uniform(-1, 1, (cores * 32, N_SAMPLES)).astype(np.float32)
+                tp0 = time.perf_counter()
+                impl.batch_power(xp, NFFT, HOP, "hann", threads=cores, want_output=False)
+                dtp = time.perf_counter() - tp0
+                line["cpu_baseline_power"] = {"value": xp.shape[0] * N_SAMPLES / dtp / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+                                              "sample": f"{xp.shape[0]} signals x {N_SAMPLES} samples, vv_dsp_stft_process + re^2 + im^2 per frame, {dtp:.1f} s",
+                                              "gpu_value": B * N_SAMPLES / (pow_ms * 1e-3) / 1e6}
+            except Exception as exc:                        # a reported extra, never fatal
+                line["cpu_baseline_power"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
