@@ -322,6 +322,21 @@ def check_mel_fused_random_filterbanks(lib, seeds=range(6), nfft=2048, hop=512):
         assert np.array_equal(fused, chained, equal_nan=True), (seed, n_mels, frames)
 
 
+def check_mel_host_pipeline(lib, nfft=2048, hop=512, n=9000, batch=7):
+    """host signals through the fused log-mel kernel in several chunks (two staging sets, two streams): the same bytes as
+    one device-resident call; log-mel to host and to device memory, MFCC on top"""
+    from vv_dsp_b200 import mel_filterbank
+    st, w = mel_filterbank(nfft, 40, 16000.0, 0.0, 8000.0, lib=lib)
+    assert st == 0
+    x = np.stack([noise(2500 + i, n) for i in range(batch)])
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        lm = h.batch_logmel(x, w, 1e-6, "center")                     # chunked by VVB_STAGE_TARGET_BYTES (set by the caller)
+        mf = h.batch_mfcc(x, w, 13, lifter=22.0, log_epsilon=1e-6, convention="center")
+        one = np.stack([h.batch_logmel(x[i:i + 1], w, 1e-6, "center")[0] for i in range(batch)])
+        one_mf = np.stack([h.batch_mfcc(x[i:i + 1], w, 13, lifter=22.0, log_epsilon=1e-6, convention="center")[0] for i in range(batch)])
+    assert np.array_equal(lm, one) and np.array_equal(mf, one_mf)
+
+
 def check_mfcc(lib, oracle):
     """vv_dsp_mfcc, the MFCC plan and the batched STFT -> MFCC chain against the oracle (same float32 sums as the
     reference: only the logf feeding the DCT may differ in the last ulp)."""

@@ -95,6 +95,11 @@ def test_mel_fused_random_filterbanks(emu):
     pc.check_mel_fused_random_filterbanks(emu)
 
 
+def test_mel_host_pipeline(emu, monkeypatch):
+    monkeypatch.setenv("VVB_STAGE_TARGET_BYTES", "100000")            # two signals per chunk: four chunks
+    pc.check_mel_host_pipeline(emu)
+
+
 def test_mfcc(emu, oracle):
     pc.check_mfcc(emu, oracle)
 

@@ -177,6 +177,13 @@ def test_mel_fused_random_filterbanks(lib):
     pc.check_mel_fused_random_filterbanks(lib, seeds=range(25))
 
 
+def test_mel_host_pipeline(lib, monkeypatch):
+    monkeypatch.setenv("VVB_STAGE_TARGET_BYTES", "100000")
+    pc.check_mel_host_pipeline(lib)
+    monkeypatch.setenv("VVB_STAGE_TARGET_BYTES", "3000000")
+    pc.check_mel_host_pipeline(lib, n=200000, batch=11)
+
+
 def test_mfcc(lib, oracle):
     pc.check_mfcc(lib, oracle)
 

@@ -588,7 +588,7 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
     fused = !st && h->mel.d_fw && vvb_stft_forward_logmel_ok(h->eng, h->mel.f_segments, h->mel.f_prow, n_mels);
     if (getenv("VVB_MEL_DEBUG")) fprintf(stderr, "vvb: STFT -> log-mel: %s\n", fused ? "one fused kernel" : "power kernel + log-mel kernel");
     if (fused) {
-        const size_t stage_target = (size_t)192 << 20;
+        const size_t stage_target = h->stage_target;                   /* VVB_STAGE_TARGET_BYTES applies here too */
         cs = batch;
         if (signals_space == VV_DSP_MEM_HOST || out_space == VV_DSP_MEM_HOST) {
             const size_t per = (n ? n : 1) * sizeof(float) + frames * n_mels * sizeof(float);
@@ -618,6 +618,42 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
             if (!st) st = vvb_malloc((void**)&h->d_logmel_scratch, cs * frames * n_mels * sizeof(float));
             if (!st) h->logmel_scratch_bytes = cs * frames * n_mels * sizeof(float);
         }
+    }
+    if (!st && fused && signals_space == VV_DSP_MEM_HOST && batch > cs) {
+        /* host signals through the fused kernel, more than one chunk: two staging sets on the handle's two slot streams, so
+         * the upload of chunk c + 1 overlaps the kernel and the download of chunk c (a single stream serialises them) */
+        float *px[2] = {NULL, NULL}, *po[2] = {NULL, NULL}, *pl[2] = {NULL, NULL};
+        void* ps[2] = {NULL, NULL};
+        size_t c = 0;
+        int k;
+        for (k = 0; k < 2 && !st; ++k) {
+            st = slot_reserve(&h->slot[k], 0, 0);                          /* makes sure the slot's stream exists */
+            ps[k] = h->slot[k].stream;
+            if (!st) st = vvb_stream_sync(ps[k]);
+            if (!st) st = vvb_malloc((void**)&px[k], cs * (n ? n : 1) * sizeof(float));
+            if (!st && out_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&po[k], cs * frames * width * sizeof(float));
+            if (!st && n_coeffs) st = vvb_malloc((void**)&pl[k], cs * frames * n_mels * sizeof(float));
+        }
+        if (!st) st = vvb_stream_sync(stream);                              /* device-side operands may still be in flight */
+        for (done = 0; done < batch && !st; done += cs, ++c) {
+            const size_t nb = (batch - done < cs) ? batch - done : cs;
+            float* o_dev = (out_space == VV_DSP_MEM_HOST) ? po[c & 1] : out + done * frames * width;
+            float* lm_dev = n_coeffs ? pl[c & 1] : o_dev;
+            void* sq = ps[c & 1];
+            if (c >= 2) st = vvb_stream_sync(sq);                           /* this set's previous chunk has left */
+            if (!st && n) st = vvb_memcpy2d_h2d(px[c & 1], n * sizeof(float), signals + done * signal_pitch, signal_pitch * sizeof(float),
+                                                n * sizeof(float), nb, sq);
+            if (!st) st = vvb_stft_forward_logmel(h->eng, px[c & 1], nb, n, n ? n : 1, frames, pad, h->mel.d_fw, h->mel.d_fseg,
+                                                  h->mel.f_segments, h->mel.f_prow, n_mels, log_epsilon, lm_dev, sq);
+            if (!st && n_coeffs) st = vvb_mfcc(lm_dev, nb * frames, n_mels, n_coeffs, h->mfcc.d_table, h->mfcc.d_lifter, o_dev, sq);
+            if (!st && out_space == VV_DSP_MEM_HOST)
+                st = vvb_memcpy_d2h(out + done * frames * width, po[c & 1], nb * frames * width * sizeof(float), sq);
+        }
+        for (k = 0; k < 2; ++k) {
+            if (ps[k]) { int s2 = vvb_stream_sync(ps[k]); if (!st) st = s2; }
+            vvb_free(px[k]); vvb_free(po[k]); vvb_free(pl[k]);
+        }
+        return map_status(st);
     }
     if (!st && signals_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&d_x, cs * (n ? n : 1) * sizeof(float));
     if (!st && out_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&d_o, cs * frames * width * sizeof(float));
