@@ -207,6 +207,13 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_logmel(
 /* The same chain followed by the MFCC stage of vv_dsp_mfcc (unnormalised DCT-II of every log-mel frame, first
  * num_mfcc_coeffs kept, liftering when lifter_coeff > 0): out is [batch][frames][num_mfcc_coeffs].  Frame for
  * frame equal to vv_dsp_mfcc(vv_dsp_compute_log_mel_spectrogram(|process|^2)). */
+/* vv_dsp_stft_batch_logmel fed with HOST rows of WAV samples (format 16 / 24 / 32 PCM or -32 float32, mono, signal_pitch in
+ * samples): uploaded undecoded, converted on the device like vv_dsp_stft_batch_forward_pcm; the same log-mel rows bit for bit. */
+VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_logmel_pcm(
+    vv_dsp_stft* h, const void* pcm, int format, size_t batch, size_t n, size_t signal_pitch,
+    vv_dsp_frame_convention convention, const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
+    vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames);
+
 VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_mfcc(
     vv_dsp_stft* h,
     const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch, size_t n, size_t signal_pitch,

@@ -335,6 +335,15 @@ def check_mel_host_pipeline(lib, nfft=2048, hop=512, n=9000, batch=7):
         one = np.stack([h.batch_logmel(x[i:i + 1], w, 1e-6, "center")[0] for i in range(batch)])
         one_mf = np.stack([h.batch_mfcc(x[i:i + 1], w, 13, lifter=22.0, log_epsilon=1e-6, convention="center")[0] for i in range(batch)])
     assert np.array_equal(lm, one) and np.array_equal(mf, one_mf)
+    # ... and fed with 16-bit PCM (uploaded undecoded): the same rows as the float call on the decoded samples
+    from vv_dsp_b200 import pcm_to_planar
+    raw = np.random.default_rng(3).integers(-32768, 32768, (batch, n), dtype=np.int16)
+    xf = np.stack([pcm_to_planar(raw[i].tobytes(), 16, 1, lib=lib)[0] for i in range(batch)])
+    with Stft(nfft, hop, "hann", lib=lib) as h:
+        assert np.array_equal(h.batch_logmel_pcm(raw, w, 16, 1e-6, "center"), h.batch_logmel(xf, w, 1e-6, "center"))
+    with Stft(512, 128, "hann", lib=lib) as h:                         # a size without the fused kernel: the chained path
+        st2, w2 = mel_filterbank(512, 26, 16000.0, 0.0, 8000.0, lib=lib)
+        assert np.array_equal(h.batch_logmel_pcm(raw, w2, 16, 1e-6, "valid"), h.batch_logmel(xf, w2, 1e-6, "valid"))
 
 
 def check_mfcc(lib, oracle):

@@ -79,6 +79,8 @@ class Library:
         "vv_dsp_compute_log_mel_spectrogram": (C.c_int, [_vp, _sz, _sz, _vp, _sz, C.c_float, _vp]),
         "vv_dsp_stft_batch_logmel": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, _vp, _sz, C.c_float, _vp, C.c_int,
                                                C.POINTER(_sz)]),
+        "vv_dsp_stft_batch_logmel_pcm": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, _vp, _sz, C.c_float, _vp, C.c_int,
+                                                   C.POINTER(_sz)]),
         "vv_dsp_stft_batch_mfcc": (C.c_int, [_vp, _vp, C.c_int, _sz, _sz, _sz, C.c_int, _vp, _sz, C.c_float, _sz, C.c_float, _vp, C.c_int,
                                              C.POINTER(_sz)]),
         "vv_dsp_mfcc": (C.c_int, [_vp, _sz, _sz, _sz, C.c_int, C.c_float, _vp]),
@@ -513,6 +515,26 @@ class Stft:
                                                CONVENTIONS[convention], _ptr(weights), weights.shape[0], log_epsilon,
                                                _ptr(out), DEVICE if _is_device(out) else HOST, C.byref(nf))
         _check(self.lib, st, "vv_dsp_stft_batch_logmel")
+        return out
+
+    def batch_logmel_pcm(self, pcm, weights, fmt=16, log_epsilon=1e-10, convention="valid", out=None):
+        """vv_dsp_stft_batch_logmel_pcm: pcm = HOST [batch, n] WAV samples (int16 / int32 / float32, or uint8 [batch, 3 n] for
+        24-bit), uploaded undecoded; returns [batch, frames, n_mels] log-mel rows (numpy, or the torch CUDA tensor `out`)"""
+        dt = {16: np.int16, 32: np.int32, -32: np.float32, 24: np.uint8}[fmt]
+        pcm = np.ascontiguousarray(pcm, dt)
+        weights = np.ascontiguousarray(weights, np.float32)
+        assert pcm.ndim == 2 and weights.shape[1] == self.bins
+        batch, n = int(pcm.shape[0]), int(pcm.shape[1]) // (3 if fmt == 24 else 1)
+        frames = self.num_frames(n, convention)
+        if out is None:
+            out = np.empty((batch, frames, weights.shape[0]), np.float32)
+        if _is_device(out):
+            self._check_device_tensor(out, "float32", "out")
+            self._bind_torch_stream(out)
+        nf = _sz(0)
+        st = self.lib.vv_dsp_stft_batch_logmel_pcm(self._h, _ptr(pcm), fmt, batch, n, n, CONVENTIONS[convention], _ptr(weights),
+                                                   weights.shape[0], log_epsilon, _ptr(out), DEVICE if _is_device(out) else HOST, C.byref(nf))
+        _check(self.lib, st, "vv_dsp_stft_batch_logmel_pcm")
         return out
 
     def batch_mfcc(self, signals, weights, num_coeffs, lifter=0.0, log_epsilon=1e-10, convention="valid", out=None):

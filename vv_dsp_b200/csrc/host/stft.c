@@ -542,7 +542,9 @@ vv_dsp_status vv_dsp_stft_spectrogram(vv_dsp_stft* h, const vv_dsp_real* signal,
 /* Chunks of signals whose power spectrogram fits a bounded device scratch; per chunk the fused power
  * kernel and the HBM-bound log-mel kernel run back to back on one stream. */
 /* STFT -> power -> log-mel [-> MFCC when n_coeffs > 0]; `width` = floats per output frame */
-static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch,
+/* pcm_format 0: float32 signals; 16 / 24 / 32 / -32: HOST rows of WAV samples, decoded on the device chunk by chunk (see
+ * batch_forward_impl) */
+static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const void* signals_v, int pcm_format, vv_dsp_mem_space signals_space, size_t batch,
                                      size_t n, size_t signal_pitch, vv_dsp_frame_convention convention,
                                      const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
                                      size_t n_coeffs, vv_dsp_real lifter,
@@ -551,11 +553,15 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
     const size_t scratch_target = (size_t)768 << 20;
     const size_t width = n_coeffs ? n_coeffs : n_mels;
     size_t frames, per_signal, cs, done, i;
+    const vv_dsp_real* signals = (const vv_dsp_real*)signals_v;
+    const size_t bps = pcm_format ? (size_t)(pcm_format < 0 ? -pcm_format : pcm_format) / 8 : sizeof(float);
     float *d_power, *d_x = NULL, *d_o = NULL;
+    void* d_raw = NULL;
     unsigned long long hash = 1469598103934665603ull;
     void* stream;
     int st = 0, pad, fused;
     if (!h || !signals || !filterbank_weights || !out) return VV_DSP_ERROR_NULL_POINTER;
+    if (pcm_format && signals_space != VV_DSP_MEM_HOST) return VV_DSP_ERROR_UNSUPPORTED;
     if ((unsigned)convention > 3u || (unsigned)signals_space > 1u || (unsigned)out_space > 1u) return VV_DSP_ERROR_OUT_OF_RANGE;
     if (n_mels == 0) return VV_DSP_ERROR_INVALID_SIZE;
     if (log_epsilon < 0.0f) return VV_DSP_ERROR_OUT_OF_RANGE;
@@ -623,7 +629,7 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
         /* host signals through the fused kernel, more than one chunk: two staging sets on the handle's two slot streams, so
          * the upload of chunk c + 1 overlaps the kernel and the download of chunk c (a single stream serialises them) */
         float *px[2] = {NULL, NULL}, *po[2] = {NULL, NULL}, *pl[2] = {NULL, NULL};
-        void* ps[2] = {NULL, NULL};
+        void *ps[2] = {NULL, NULL}, *pr[2] = {NULL, NULL};
         size_t c = 0;
         int k;
         for (k = 0; k < 2 && !st; ++k) {
@@ -631,6 +637,7 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
             ps[k] = h->slot[k].stream;
             if (!st) st = vvb_stream_sync(ps[k]);
             if (!st) st = vvb_malloc((void**)&px[k], cs * (n ? n : 1) * sizeof(float));
+            if (!st && pcm_format) st = vvb_malloc(&pr[k], cs * (n ? n : 1) * bps);
             if (!st && out_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&po[k], cs * frames * width * sizeof(float));
             if (!st && n_coeffs) st = vvb_malloc((void**)&pl[k], cs * frames * n_mels * sizeof(float));
         }
@@ -641,8 +648,13 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
             float* lm_dev = n_coeffs ? pl[c & 1] : o_dev;
             void* sq = ps[c & 1];
             if (c >= 2) st = vvb_stream_sync(sq);                           /* this set's previous chunk has left */
-            if (!st && n) st = vvb_memcpy2d_h2d(px[c & 1], n * sizeof(float), signals + done * signal_pitch, signal_pitch * sizeof(float),
-                                                n * sizeof(float), nb, sq);
+            if (!st && n && pcm_format) {
+                st = vvb_memcpy2d_h2d(pr[c & 1], n * bps, (const char*)signals_v + done * signal_pitch * bps, signal_pitch * bps, n * bps, nb, sq);
+                if (!st) st = vvb_pcm_to_planar(pr[c & 1], pcm_format, nb * n, 1, px[c & 1], nb * n, sq);
+            } else if (!st && n) {
+                st = vvb_memcpy2d_h2d(px[c & 1], n * sizeof(float), signals + done * signal_pitch, signal_pitch * sizeof(float),
+                                      n * sizeof(float), nb, sq);
+            }
             if (!st) st = vvb_stft_forward_logmel(h->eng, px[c & 1], nb, n, n ? n : 1, frames, pad, h->mel.d_fw, h->mel.d_fseg,
                                                   h->mel.f_segments, h->mel.f_prow, n_mels, log_epsilon, lm_dev, sq);
             if (!st && n_coeffs) st = vvb_mfcc(lm_dev, nb * frames, n_mels, n_coeffs, h->mfcc.d_table, h->mfcc.d_lifter, o_dev, sq);
@@ -651,11 +663,12 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
         }
         for (k = 0; k < 2; ++k) {
             if (ps[k]) { int s2 = vvb_stream_sync(ps[k]); if (!st) st = s2; }
-            vvb_free(px[k]); vvb_free(po[k]); vvb_free(pl[k]);
+            vvb_free(px[k]); vvb_free(po[k]); vvb_free(pl[k]); vvb_free(pr[k]);
         }
         return map_status(st);
     }
     if (!st && signals_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&d_x, cs * (n ? n : 1) * sizeof(float));
+    if (!st && pcm_format) st = vvb_malloc(&d_raw, cs * (n ? n : 1) * bps);
     if (!st && out_space == VV_DSP_MEM_HOST) st = vvb_malloc((void**)&d_o, cs * frames * width * sizeof(float));
     for (done = 0; done < batch && !st; done += cs) {
         const size_t nb = (batch - done < cs) ? batch - done : cs;
@@ -663,7 +676,13 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
         size_t xp = signal_pitch;
         float* o_dev = out + done * frames * width;
         float* lm_dev;
-        if (signals_space == VV_DSP_MEM_HOST) {
+        if (pcm_format) {
+            if (n) {
+                st = vvb_memcpy2d_h2d(d_raw, n * bps, (const char*)signals_v + done * signal_pitch * bps, signal_pitch * bps, n * bps, nb, stream);
+                if (!st) st = vvb_pcm_to_planar(d_raw, pcm_format, nb * n, 1, d_x, nb * n, stream);
+            }
+            x_dev = d_x; xp = n ? n : 1;
+        } else if (signals_space == VV_DSP_MEM_HOST) {
             if (n) st = vvb_memcpy2d_h2d(d_x, n * sizeof(float), signals + done * signal_pitch, signal_pitch * sizeof(float),
                                          n * sizeof(float), nb, stream);
             x_dev = d_x; xp = n ? n : 1;
@@ -685,9 +704,23 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const vv_dsp_real* signals,
     /* device-resident calls only enqueue (scratch and filterbank live in the handle); host buffers: synchronous */
     if (signals_space == VV_DSP_MEM_HOST || out_space == VV_DSP_MEM_HOST) {
         int s2 = vvb_stream_sync(stream); if (!st) st = s2;
-        vvb_free(d_x); vvb_free(d_o);
+        vvb_free(d_x); vvb_free(d_o); vvb_free(d_raw);
     }
     return map_status(st);
+}
+
+vv_dsp_status vv_dsp_stft_batch_logmel_pcm(vv_dsp_stft* h, const void* pcm, int format, size_t batch, size_t n, size_t signal_pitch,
+                                           vv_dsp_frame_convention convention, const vv_dsp_real* filterbank_weights, size_t n_mels,
+                                           vv_dsp_real log_epsilon, vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames)
+{
+    int prev;
+    vv_dsp_status st;
+    if (format != 16 && format != 24 && format != 32 && format != -32) return VV_DSP_ERROR_OUT_OF_RANGE;
+    prev = dev_enter(h);
+    st = batch_mel_chain(h, pcm, format, VV_DSP_MEM_HOST, batch, n, signal_pitch, convention, filterbank_weights, n_mels, log_epsilon, 0, 0.0f,
+                         out, out_space, out_frames);
+    dev_leave(prev);
+    return st;
 }
 
 vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch,
@@ -696,7 +729,7 @@ vv_dsp_status vv_dsp_stft_batch_logmel(vv_dsp_stft* h, const vv_dsp_real* signal
                                        vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames)
 {
     const int prev = dev_enter(h);
-    const vv_dsp_status st = batch_mel_chain(h, signals, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels,
+    const vv_dsp_status st = batch_mel_chain(h, signals, 0, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels,
                                              log_epsilon, 0, 0.0f, out, out_space, out_frames);
     dev_leave(prev);
     return st;
@@ -712,7 +745,7 @@ vv_dsp_status vv_dsp_stft_batch_mfcc(vv_dsp_stft* h, const vv_dsp_real* signals,
     vv_dsp_status st;
     if (num_mfcc_coeffs == 0) return VV_DSP_ERROR_INVALID_SIZE;
     prev = dev_enter(h);
-    st = batch_mel_chain(h, signals, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels, log_epsilon,
+    st = batch_mel_chain(h, signals, 0, signals_space, batch, n, signal_pitch, convention, filterbank_weights, n_mels, log_epsilon,
                          num_mfcc_coeffs, lifter_coeff, out, out_space, out_frames);
     dev_leave(prev);
     return st;
