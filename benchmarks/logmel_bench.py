@@ -71,4 +71,4 @@ with Stft(nfft3, hop3, "hann") as h:
     e1.record(s); torch.cuda.synchronize()
     ms3 = e0.elapsed_time(e1) / 5
 print(json.dumps({"workload": f"STFT->log-mel, {B3} x {n3} samples (10 s at 16 kHz), nfft={nfft3} hop={hop3}, {n_mels} mels", "ms": ms3,
-                  "Msamples_per_s": B3 * n3 / ms3 / 1e3, "path": "mixed-radix power kernel + log-mel kernel through a device scratch"}))
+                  "Msamples_per_s": B3 * n3 / ms3 / 1e3, "path": "power kernel + log-mel kernel through a device scratch" if os.environ.get("VVB_MEL_UNFUSED") else "one fused kernel (mixed-radix generic kernel, band sums per warp)"}))

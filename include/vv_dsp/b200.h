@@ -195,8 +195,9 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_stream_time_roundtrip(vv_dsp_stft_str
  * out[b][f][m] = logf(sum_k |X_bf[k]|^2 W[m][k] + log_epsilon), i.e. vv_dsp_compute_log_mel_spectrogram
  * applied to the power output of vv_dsp_stft_batch_forward.  filterbank_weights: HOST, dense
  * [n_mels][fft_size/2+1] as produced by vv_dsp_mel_filterbank_create.  out: [batch][frames][n_mels]
- * float32.  Two kernels (power, then an HBM-bound log-mel kernel) chained on the device per chunk of
- * signals; the power spectrogram only ever lives in a bounded device scratch buffer. */
+ * float32.  ONE kernel from samples to log-mel rows (no power spectrogram in device memory) at fft_size 2048 with hop N/8, N/4,
+ * N/2 and at every Stockham size <= 1024 (256 / 512 / 1024, 320 / 400 / 480 / 640) with any hop; elsewhere two kernels (power,
+ * then an HBM-bound log-mel kernel) chained per chunk of signals through a bounded device scratch.  Same rows either way. */
 VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_logmel(
     vv_dsp_stft* h,
     const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch, size_t n, size_t signal_pitch,
@@ -204,9 +205,6 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_logmel(
     const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
     vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames);
 
-/* The same chain followed by the MFCC stage of vv_dsp_mfcc (unnormalised DCT-II of every log-mel frame, first
- * num_mfcc_coeffs kept, liftering when lifter_coeff > 0): out is [batch][frames][num_mfcc_coeffs].  Frame for
- * frame equal to vv_dsp_mfcc(vv_dsp_compute_log_mel_spectrogram(|process|^2)). */
 /* vv_dsp_stft_batch_logmel fed with HOST rows of WAV samples (format 16 / 24 / 32 PCM or -32 float32, mono, signal_pitch in
  * samples): uploaded undecoded, converted on the device like vv_dsp_stft_batch_forward_pcm; the same log-mel rows bit for bit. */
 VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_logmel_pcm(
@@ -214,6 +212,9 @@ VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_logmel_pcm(
     vv_dsp_frame_convention convention, const vv_dsp_real* filterbank_weights, size_t n_mels, vv_dsp_real log_epsilon,
     vv_dsp_real* out, vv_dsp_mem_space out_space, size_t* out_frames);
 
+/* The same chain followed by the MFCC stage of vv_dsp_mfcc (unnormalised DCT-II of every log-mel frame, first
+ * num_mfcc_coeffs kept, liftering when lifter_coeff > 0): out is [batch][frames][num_mfcc_coeffs].  Frame for
+ * frame equal to vv_dsp_mfcc(vv_dsp_compute_log_mel_spectrogram(|process|^2)). */
 VV_DSP_NODISCARD vv_dsp_status vv_dsp_stft_batch_mfcc(
     vv_dsp_stft* h,
     const vv_dsp_real* signals, vv_dsp_mem_space signals_space, size_t batch, size_t n, size_t signal_pitch,

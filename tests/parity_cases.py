@@ -293,6 +293,57 @@ def check_mel_fused(lib, oracle, cases=((512, 80, 48000.0), (256, 128, 48000.0),
             assert np.abs(e - er).max() <= 1e-4 * er.max()
 
 
+def check_mel_fused_cta(lib, oracle, cases=((400, 160, 80, 16000.0), (512, 128, 26, 16000.0), (1024, 256, 40, 44100.0), (256, 64, 23, 8000.0),
+                                           (320, 160, 40, 16000.0), (480, 160, 64, 16000.0), (640, 160, 80, 16000.0), (512, 100, 128, 48000.0)),
+                        n=7000, batch=4, capfd=None):
+    """STFT -> log-mel in ONE kernel for the sizes of the generic forward kernel (sub-warp teams: every warp keeps the power rows
+    of its frames in shared memory and sums the bands there) against the chained power and log-mel kernels (VVB_MEL_UNFUSED=1): bit for
+    bit, zero-padded and centred frames, frame counts that are no multiple of the CTA's frame group, filterbanks with an empty
+    band, holes, negative weights and a wide out-of-order band; MFCC on top; and against the oracle's chain.  With capfd the
+    library's VVB_MEL_DEBUG line proves which path ran."""
+    import os
+    from vv_dsp_b200 import mel_filterbank
+    rng = np.random.default_rng(19)
+    for nfft, hop, n_mels, sr in cases:
+        x = np.stack([noise(260 + i, n + 31 * i)[:n] for i in range(batch)])
+        st, w = mel_filterbank(nfft, n_mels, sr, 0.0, sr / 2, lib=lib)
+        assert st == 0
+        odd = w.copy()
+        odd[1] = 0.0
+        odd[n_mels // 2, ::3] = 0.0
+        odd[n_mels - 2] *= -1.0
+        odd[0, :nfft // 8] = rng.uniform(0, 1e-3, nfft // 8).astype(np.float32)
+        with Stft(nfft, hop, "hann", lib=lib) as h:
+            for wb in (w, odd):
+                for conv in ("valid", "center"):
+                    if capfd is not None:
+                        capfd.readouterr()
+                        os.environ["VVB_MEL_DEBUG"] = "1"
+                    try:
+                        fused = h.batch_logmel(x, wb, 1e-6, conv)
+                    finally:
+                        os.environ.pop("VVB_MEL_DEBUG", None)
+                    if capfd is not None:
+                        assert "one fused kernel" in capfd.readouterr().err, (nfft, hop)
+                    fused_mf = h.batch_mfcc(x, wb, min(13, n_mels), lifter=22.0, log_epsilon=1e-6, convention=conv)
+                    os.environ["VVB_MEL_UNFUSED"] = "1"
+                    try:
+                        chained = h.batch_logmel(x, wb, 1e-6, conv)
+                        chained_mf = h.batch_mfcc(x, wb, min(13, n_mels), lifter=22.0, log_epsilon=1e-6, convention=conv)
+                    finally:
+                        del os.environ["VVB_MEL_UNFUSED"]
+                    assert fused.shape == chained.shape
+                    assert np.array_equal(fused, chained, equal_nan=True), (nfft, hop, conv, np.nanmax(np.abs(fused - chained)))
+                    assert np.array_equal(fused_mf, chained_mf, equal_nan=True), (nfft, hop, conv)
+            one = h.batch_logmel(x[1:2, :nfft + 3], w, 1e-6, "valid")    # a single frame, and a signal shorter than a frame
+            assert one.shape == (1, 1, n_mels) and np.array_equal(one[0], h.batch_logmel(x[1:2, :nfft + hop], w, 1e-6, "valid")[0, :1])
+            assert h.batch_logmel(x[:1, :nfft - 1], w, 1e-6, "valid").shape == (1, 0, n_mels)
+            ref = np.stack([oracle.log_mel(np.abs(oracle.stft(x[i], nfft, hop)) ** 2, w, 1e-6) for i in range(2)])
+            lm = h.batch_logmel(x[:2], w, 1e-6, "valid")
+            e, er = np.exp(lm.astype(np.float64)), np.exp(ref.astype(np.float64))
+            assert np.abs(e - er).max() <= 1e-4 * er.max(), (nfft, hop)
+
+
 def check_mel_fused_random_filterbanks(lib, seeds=range(6), nfft=2048, hop=512):
     """The fused kernel takes ANY weight matrix whose lane schedule fits: random band counts, supports, orders, holes and
     signs, odd and even frame counts per signal (pair flush), against the chained kernels bit for bit."""

@@ -91,6 +91,11 @@ def test_mel_fused(emu, oracle):
     pc.check_mel_fused(emu, oracle, cases=((512, 80, 48000.0), (1024, 40, 16000.0)), n=6000, batch=3)
 
 
+def test_mel_fused_cta(emu, oracle, capfd):
+    pc.check_mel_fused_cta(emu, oracle, cases=((400, 160, 80, 16000.0), (512, 128, 26, 16000.0), (1024, 256, 40, 44100.0), (256, 64, 23, 8000.0),
+                                               (320, 160, 40, 16000.0)), n=4000, batch=3, capfd=capfd)
+
+
 def test_mel_fused_random_filterbanks(emu):
     pc.check_mel_fused_random_filterbanks(emu)
 

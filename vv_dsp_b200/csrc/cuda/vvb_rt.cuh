@@ -115,6 +115,7 @@ template <> struct March<Cfg4096> { static constexpr int G = 2, MINB = 1; };   /
 /* m = fft_size / 2 of a size with a Stockham kernel; `batch` of a forward launch travels in FwdArgs::num_groups.
  * The marching / pair entries return -1 when (fft_size, hop) has no such kernel. */
 int tu_fwd_generic(int m, const FwdArgs& a, int kind, int sms, void* stream);
+int tu_fwd_logmel(int m, const FwdArgs& a, int sms, void* stream, bool probe);      /* generic kernel + mel_phase per warp; 6: no such kernel / schedule too long */
 int tu_fwd_march_2048(size_t hop, const FwdArgs& a, int kind, int sms, void* stream);
 int tu_fwd_march_4096(size_t hop, const FwdArgs& a, int kind, int sms, void* stream);
 int tu_fwd_march_8192(size_t hop, const FwdArgs& a, int kind, int sms, void* stream);

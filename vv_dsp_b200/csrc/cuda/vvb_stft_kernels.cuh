@@ -48,7 +48,7 @@
 
 namespace vvb {
 
-enum { OUT_COMPLEX = 0, OUT_POWER = 1, OUT_MAGNITUDE = 2, OUT_LOGMEL = 3 };   /* OUT_LOGMEL: marching kernel only, see mel_phase */
+enum { OUT_COMPLEX = 0, OUT_POWER = 1, OUT_MAGNITUDE = 2, OUT_LOGMEL = 3 };   /* OUT_LOGMEL: marching kernel and generic kernel with sub-warp teams, see mel_phase */
 constexpr int MEL_U = 4;              /* fused log-mel: four-tap groups ("quads") per schedule segment */
 enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
 
@@ -282,6 +282,25 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
     float2* s_xb = s_post + C::POST + 1;                              /* +1 keeps 16 B alignment */
     copy_table(s_win, a.tables + TB::WIN, N);
     copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3 + C::POST));
+    /* OUT_LOGMEL in this kernel (sub-warp teams: fft_size 256 ... 1024 and the speech framings): a warp's 32 / T teams make
+     * consecutive frames; each team leaves its power row in shared memory and the warp then runs mel_phase<2> on every pair of
+     * rows with the lane schedules of csrc/host/mel.c -- no CTA barrier, so the band sums of one warp overlap the transforms of
+     * the others.  Per pair of teams: [even frame's row | band sums of both frames | odd frame's row], row tails stay zero. */
+    float4* s_melw = nullptr;
+    int2* s_melseg = nullptr;
+    float* s_rows = nullptr;
+    int nmp = 0, pstride = 0;
+    if constexpr (OUT == OUT_LOGMEL) {
+        static_assert(T <= 16 && G % 2 == 0, "two or more teams per warp");
+        s_melw = reinterpret_cast<float4*>(smem + ((N + 2 * (C::TW2 + C::TW3 + C::POST + 1) + 2 * G * C::XBUF + 3) & ~3));
+        s_melseg = reinterpret_cast<int2*>(s_melw + a.mel_S * MEL_U * 32);
+        s_rows = reinterpret_cast<float*>(s_melseg + a.mel_S * 32);
+        nmp = (a.n_mels + 31) & ~31;
+        pstride = 2 * a.mel_prow + 2 * nmp;
+        copy_table(reinterpret_cast<float*>(s_melw), reinterpret_cast<const float*>(a.mel_w), a.mel_S * MEL_U * 32 * 4);
+        copy_table(reinterpret_cast<float*>(s_melseg), reinterpret_cast<const float*>(a.mel_seg), a.mel_S * 32 * 2);
+        for (int i = threadIdx.x; i < (G / 2) * pstride; i += blockDim.x) s_rows[i] = 0.f;
+    }
     __syncthreads();
 
     const int team = threadIdx.x / T, t = threadIdx.x % T;
@@ -365,7 +384,30 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
 
         /* ---- split step: X[k] = (Z[k] + conj Z[M-k])/2 - (j/2) W_N^k (Z[k] - conj Z[M-k]) */
         const long long row = ((long long)b * a.frames + f) * a.out_pitch;
-        if constexpr (VVB_FWD_HALF_SPLIT && !VVB_FWD_TABLE_TWIDDLES) {
+        if constexpr (OUT == OUT_LOGMEL) {
+            static_assert(VVB_FWD_HALF_SPLIT && !VVB_FWD_TABLE_TWIDDLES, "the fused log-mel phase takes the half-column split");
+            constexpr int TPW = 32 / T;                               /* teams (= consecutive frames) per warp */
+            publish_upper_half<C>(v, xb, t, typename make_iseq<E / 2>::type{});
+            team_sync<T>(team);
+            if (active) {                                             /* the power row goes to shared memory */
+                float* pw = s_rows + (team >> 1) * pstride + ((team & 1) ? a.mel_prow + 2 * nmp : 0);
+                split_pairs_half<C, OUT, (C::M <= 2048)>(v, xb, hw_t, s_post, t, pw, 0, typename make_iseq<E / 2>::type{});
+                if (t == 0) {
+                    const float2 A = v[column_slot<C, E / 2>()];
+                    emit_bin<OUT>(pw, M / 2, make_float2(A.x, -A.y));
+                }
+            }
+            const int lane = threadIdx.x & 31, wteam = (threadIdx.x >> 5) * TPW, fw = f - (team - wteam);
+#pragma unroll 1
+            for (int q = 0; q < TPW / 2; ++q) {
+                const int fe = fw + 2 * q;                            /* the same for all lanes of the warp */
+                if (fe >= a.frames) break;
+                float* pb = s_rows + ((wteam >> 1) + q) * pstride;
+                const long long orow = (long long)b * a.frames + fe;
+                if (fe + 1 < a.frames) mel_phase<2>(a, s_melw, s_melseg, pb, pb + a.mel_prow + 2 * nmp, pb + a.mel_prow, lane, orow, orow + 1);
+                else mel_phase<1>(a, s_melw, s_melseg, pb, pb, pb + a.mel_prow, lane, orow, orow);
+            }
+        } else if constexpr (VVB_FWD_HALF_SPLIT && !VVB_FWD_TABLE_TWIDDLES) {
             publish_upper_half<C>(v, xb, t, typename make_iseq<E / 2>::type{});
             team_sync<T>(team);
             if (active) {
