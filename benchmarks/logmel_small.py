@@ -30,8 +30,13 @@ def timed(fn, reps=10):
 
 
 B = 1024
-for nfft, hop, sr, n, n_mels in ((400, 160, 16000.0, 160_000, 80), (512, 160, 16000.0, 160_000, 80), (512, 128, 16000.0, 160_000, 40),
-                                 (640, 160, 16000.0, 160_000, 80), (256, 64, 8000.0, 160_000, 26), (1024, 256, 48000.0, 480_000, 80)):
+SHAPES = ((400, 160, 16000.0, 160_000, 80), (512, 160, 16000.0, 160_000, 80), (512, 128, 16000.0, 160_000, 40),
+          (640, 160, 16000.0, 160_000, 80), (256, 64, 8000.0, 160_000, 26), (1024, 256, 48000.0, 480_000, 80))
+only = [int(v) for v in os.environ.get("LOGMEL_SMALL_NFFT", "").split(",") if v]        # e.g. "400" for an ncu capture
+fused_only = bool(os.environ.get("LOGMEL_SMALL_FUSED_ONLY"))                              # 3 warm-up launches + 1: ncu --launch-skip 3
+for nfft, hop, sr, n, n_mels in SHAPES:
+    if only and nfft not in only:
+        continue
     x = torch.rand((B, n), device=dev) * 2 - 1
     st, w = mel_filterbank(nfft, n_mels, sr, 0.0, sr / 2)
     F = 1 + (n - nfft) // hop
@@ -39,7 +44,10 @@ for nfft, hop, sr, n, n_mels in ((400, 160, 16000.0, 160_000, 80), (512, 160, 16
     power = torch.empty((B, F, nfft // 2 + 1), device=dev)
     with Stft(nfft, hop, "hann") as h:
         h.set_stream(s.cuda_stream)
-        ms_fused = timed(lambda: h.batch_logmel(x, w, 1e-10, out=out))
+        ms_fused = timed(lambda: h.batch_logmel(x, w, 1e-10, out=out), 1 if fused_only else 10)
+        if fused_only:
+            print(json.dumps({"nfft": nfft, "hop": hop, "fused_ms": ms_fused}))
+            continue
         a = out.clone()
         os.environ["VVB_MEL_UNFUSED"] = "1"
         try:
@@ -47,9 +55,15 @@ for nfft, hop, sr, n, n_mels in ((400, 160, 16000.0, 160_000, 80), (512, 160, 16
         finally:
             del os.environ["VVB_MEL_UNFUSED"]
         same = bool(torch.equal(a, out))
+        os.environ["VVB_MEL_ROW_SPREAD_OFF"] = "1"
+        try:
+            ms_nospread = timed(lambda: h.batch_logmel(x, w, 1e-10, out=out))
+        finally:
+            del os.environ["VVB_MEL_ROW_SPREAD_OFF"]
+        ms_fused2 = timed(lambda: h.batch_logmel(x, w, 1e-10, out=out))
         ms_pow = timed(lambda: h.batch_forward(x, out=power, kind="power"))
     alg = (B * n * 4 + B * F * n_mels * 4) / 1e9
     print(json.dumps({"workload": f"STFT->log-mel, {B} x {n} samples, nfft={nfft} hop={hop}, {n_mels} mels", "fused_ms": round(ms_fused, 4),
-                      "chained_ms": round(ms_chain, 4), "power_kernel_ms": round(ms_pow, 4), "bit_identical": same,
+                      "fused_again_ms": round(ms_fused2, 4), "fused_rows_back_to_back_ms": round(ms_nospread, 4), "chained_ms": round(ms_chain, 4), "power_kernel_ms": round(ms_pow, 4), "bit_identical": same,
                       "Msamples_per_s": round(B * n / ms_fused / 1e3, 1), "algorithmic_GB": round(alg, 4), "GBps": round(alg / ms_fused * 1e3, 1)}))
     del x, out, power, a

@@ -88,6 +88,14 @@ VVB_CX size_t mel_smem_bytes(int G, int mel_S, int n_mels, int mel_prow, int pai
            (pair ? sizeof(float) * (size_t)G * (size_t)mel_prow : 0);
 }
 
+/* OUT_LOGMEL in the generic forward kernel: per pair of teams [even frame's power row | band sums of both frames | pad | odd
+ * frame's row | pad].  The pads put the rows of the 32 / T teams of a warp T banks apart (odd row = T, pair stride = 2 T mod 32),
+ * so the split step's row stores -- lane t of every team writes bin k0 + t -- never meet in a bank (ncu before: 23 % of the
+ * kernel's shared-memory store wavefronts were conflicts between the two teams of a warp). */
+VVB_CX int mel_up_mod32(int x, int r) { return x + ((r - x) & 31); }                       /* smallest y >= x with y = r mod 32 */
+VVB_CX int mel_rowb_offset(int mel_prow, int nmp, int T) { return mel_up_mod32(mel_prow + 2 * nmp, T & 31); }
+VVB_CX int mel_pair_stride(int mel_prow, int nmp, int T) { return mel_up_mod32(mel_rowb_offset(mel_prow, nmp, T) + mel_prow, (2 * T) & 31); }
+
 struct InvArgs {
     const float2* spec;      /* [batch][frames][spec_pitch] */
     long long spec_pitch;
@@ -285,18 +293,19 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
     /* OUT_LOGMEL in this kernel (sub-warp teams: fft_size 256 ... 1024 and the speech framings): a warp's 32 / T teams make
      * consecutive frames; each team leaves its power row in shared memory and the warp then runs mel_phase<2> on every pair of
      * rows with the lane schedules of csrc/host/mel.c -- no CTA barrier, so the band sums of one warp overlap the transforms of
-     * the others.  Per pair of teams: [even frame's row | band sums of both frames | odd frame's row], row tails stay zero. */
+     * the others.  Per pair of teams: [even frame's row | band sums of both frames | odd frame's row] (mel_pair_stride), row tails stay zero. */
     float4* s_melw = nullptr;
     int2* s_melseg = nullptr;
     float* s_rows = nullptr;
-    int nmp = 0, pstride = 0;
+    int nmp = 0, pstride = 0, rowb = 0;
     if constexpr (OUT == OUT_LOGMEL) {
         static_assert(T <= 16 && G % 2 == 0, "two or more teams per warp");
         s_melw = reinterpret_cast<float4*>(smem + ((N + 2 * (C::TW2 + C::TW3 + C::POST + 1) + 2 * G * C::XBUF + 3) & ~3));
         s_melseg = reinterpret_cast<int2*>(s_melw + a.mel_S * MEL_U * 32);
         s_rows = reinterpret_cast<float*>(s_melseg + a.mel_S * 32);
         nmp = (a.n_mels + 31) & ~31;
-        pstride = 2 * a.mel_prow + 2 * nmp;
+        rowb = a.mel_pair ? mel_rowb_offset(a.mel_prow, nmp, T) : a.mel_prow + 2 * nmp;       /* here mel_pair = 1: rows spread over the banks */
+        pstride = a.mel_pair ? mel_pair_stride(a.mel_prow, nmp, T) : 2 * a.mel_prow + 2 * nmp;
         copy_table(reinterpret_cast<float*>(s_melw), reinterpret_cast<const float*>(a.mel_w), a.mel_S * MEL_U * 32 * 4);
         copy_table(reinterpret_cast<float*>(s_melseg), reinterpret_cast<const float*>(a.mel_seg), a.mel_S * 32 * 2);
         for (int i = threadIdx.x; i < (G / 2) * pstride; i += blockDim.x) s_rows[i] = 0.f;
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
             publish_upper_half<C>(v, xb, t, typename make_iseq<E / 2>::type{});
             team_sync<T>(team);
             if (active) {                                             /* the power row goes to shared memory */
-                float* pw = s_rows + (team >> 1) * pstride + ((team & 1) ? a.mel_prow + 2 * nmp : 0);
+                float* pw = s_rows + (team >> 1) * pstride + ((team & 1) ? rowb : 0);
                 split_pairs_half<C, OUT, (C::M <= 2048)>(v, xb, hw_t, s_post, t, pw, 0, typename make_iseq<E / 2>::type{});
                 if (t == 0) {
                     const float2 A = v[column_slot<C, E / 2>()];
@@ -404,7 +413,7 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
                 if (fe >= a.frames) break;
                 float* pb = s_rows + ((wteam >> 1) + q) * pstride;
                 const long long orow = (long long)b * a.frames + fe;
-                if (fe + 1 < a.frames) mel_phase<2>(a, s_melw, s_melseg, pb, pb + a.mel_prow + 2 * nmp, pb + a.mel_prow, lane, orow, orow + 1);
+                if (fe + 1 < a.frames) mel_phase<2>(a, s_melw, s_melseg, pb, pb + rowb, pb + a.mel_prow, lane, orow, orow + 1);
                 else mel_phase<1>(a, s_melw, s_melseg, pb, pb, pb + a.mel_prow, lane, orow, orow);
             }
         } else if constexpr (VVB_FWD_HALF_SPLIT && !VVB_FWD_TABLE_TWIDDLES) {
@@ -1125,7 +1134,7 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
      * configuration instead re-reads the five bases from shared memory every frame (team_fft_basetw below):
      * they are live only during the twiddle phase, 26 of the 31 LDS.64 disappear, 2.02 -> 1.91 ms. */
     constexpr bool REGTW = false;
-    TwBase twb;
+    [[maybe_unused]] TwBase twb;
     if constexpr (REGTW) twb = load_tw_base<C>(reinterpret_cast<const float2*>(a.tables + TB::TW2), t);
     const int F = a.frames;
     const long long total = (long long)a.num_items * F;               /* num_items carries the batch */
@@ -1141,7 +1150,7 @@ __global__ void __launch_bounds__(C::T* G, MINB) istft_march_kernel(const InvArg
         const int emit_end = (f_end == F && a.tail_edge) ? f_end + PERIOD - 1 : f_end;   /* hop-blocks [f_begin, emit_end) are ours */
         const int emit_begin = max(f_begin, a.halo_frames);            /* halo frames: overlap only, nothing emitted */
         const int fr0 = f_begin - min(PERIOD - 1, f_begin);            /* halo frames re-synthesised */
-        const float2* specb = a.spec + (long long)b * F * a.spec_pitch;
+        [[maybe_unused]] const float2* specb = a.spec + (long long)b * F * a.spec_pitch;
         float* yb = a.y + (long long)b * a.y_pitch;
         const bool y8 = (reinterpret_cast<uintptr_t>(yb) & 7) == 0;    /* 64-bit stores possible for this signal's row */
         g0 += f_end - f_begin;

@@ -1,6 +1,7 @@
 /* vvb_tu_fwd_logmel.cu -- stft_forward_kernel<..., OUT_LOGMEL>: samples -> log-mel rows in one kernel for the sizes of the generic
  * forward kernel with sub-warp teams (fft_size 256, 512, 1024 and the speech framings 320 / 400 / 480 / 640), any hop: every warp
  * runs mel_phase on the power rows its own teams have just left in shared memory. */
+#include <cstdlib>
 #include "vvb_rt.cuh"
 
 namespace vvb {
@@ -9,7 +10,7 @@ template <class C> static size_t logmel_smem(const FwdArgs& a)
 {
     constexpr size_t G = Teams<C>::G;
     const size_t nmp = ((size_t)a.n_mels + 31) & ~(size_t)31;
-    return ((smem_fwd<C>() + 15) & ~(size_t)15) + (size_t)a.mel_S * 32 * (16 * MEL_U + 8) + sizeof(float) * (G / 2) * (2 * (size_t)a.mel_prow + 2 * nmp);
+    return ((smem_fwd<C>() + 15) & ~(size_t)15) + (size_t)a.mel_S * 32 * (16 * MEL_U + 8) + sizeof(float) * (G / 2) * (size_t)mel_pair_stride(a.mel_prow, (int)nmp, C::T);
 }
 template <class C> static int launch_forward_logmel(FwdArgs a, int sms, void* stream, bool probe)
 {
@@ -17,6 +18,7 @@ template <class C> static int launch_forward_logmel(FwdArgs a, int sms, void* st
     const size_t smem = logmel_smem<C>(a);
     if (smem > 227 * 1024) return 6;                             /* schedule too long for the shared memory left: chained kernels */
     if (probe) return 0;
+    a.mel_pair = getenv("VVB_MEL_ROW_SPREAD_OFF") ? 0 : 1;       /* A/B switch: power rows T banks apart (default) or back to back */
     a.groups_per_signal = (a.frames + G - 1) / G;
     static OccCache occ;
     auto kern = stft_forward_kernel<C, G, OUT_LOGMEL>;
