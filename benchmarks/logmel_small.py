@@ -55,15 +55,18 @@ for nfft, hop, sr, n, n_mels in SHAPES:
         finally:
             del os.environ["VVB_MEL_UNFUSED"]
         same = bool(torch.equal(a, out))
-        os.environ["VVB_MEL_ROW_SPREAD_OFF"] = "1"
-        try:
-            ms_nospread = timed(lambda: h.batch_logmel(x, w, 1e-10, out=out))
-        finally:
-            del os.environ["VVB_MEL_ROW_SPREAD_OFF"]
         ms_fused2 = timed(lambda: h.batch_logmel(x, w, 1e-10, out=out))
         ms_pow = timed(lambda: h.batch_forward(x, out=power, kind="power"))
+    os.environ["VVB_MEL_UNIT4"] = "1"          # read when a handle builds its lane schedules: four quads per segment as in the marching kernel
+    try:
+        with Stft(nfft, hop, "hann") as h4:
+            h4.set_stream(s.cuda_stream)
+            ms_unit4 = timed(lambda: h4.batch_logmel(x, w, 1e-10, out=out))
+            same = same and bool(torch.equal(a, out))
+    finally:
+        del os.environ["VVB_MEL_UNIT4"]
     alg = (B * n * 4 + B * F * n_mels * 4) / 1e9
     print(json.dumps({"workload": f"STFT->log-mel, {B} x {n} samples, nfft={nfft} hop={hop}, {n_mels} mels", "fused_ms": round(ms_fused, 4),
-                      "fused_again_ms": round(ms_fused2, 4), "fused_rows_back_to_back_ms": round(ms_nospread, 4), "chained_ms": round(ms_chain, 4), "power_kernel_ms": round(ms_pow, 4), "bit_identical": same,
+                      "fused_again_ms": round(ms_fused2, 4), "fused_unit4_ms": round(ms_unit4, 4), "chained_ms": round(ms_chain, 4), "power_kernel_ms": round(ms_pow, 4), "bit_identical": same,
                       "Msamples_per_s": round(B * n / ms_fused / 1e3, 1), "algorithmic_GB": round(alg, 4), "GBps": round(alg / ms_fused * 1e3, 1)}))
     del x, out, power, a

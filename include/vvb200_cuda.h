@@ -77,13 +77,14 @@ int vvb_engine_is_fast(const vvb_engine* e);   /* 1 if nfft has a Stockham kerne
 int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, size_t n, size_t x_pitch, size_t frames,
                      int pad_mode, int out_kind, void* d_out, size_t out_pitch, void* stream);
 /* STFT -> log-mel in one kernel (no power spectrogram in HBM): d_out = [batch][frames][n_mels].  d_mel_w / d_mel_seg: the lane
- * schedules built by the host (csrc/host/mel.c, build_fused_tables): mel_segments segments of four quads per lane, power
+ * schedules built by the host (csrc/host/mel.c, build_fused_tables): mel_segments segments of mel_unit quads per lane (4; the
+ * generic kernel also takes 2), power
  * row of mel_prow floats.  Plans: fft_size 2048 with hop N/8, N/4, N/2 (marching kernel) and every Stockham size <= 1024 with
  * any hop (generic kernel).  Returns 6 when the plan or the schedule has no fused kernel. */
-int vvb_stft_forward_logmel_ok(const vvb_engine* e, size_t mel_segments, size_t mel_prow, size_t n_mels);
+int vvb_stft_forward_logmel_ok(const vvb_engine* e, size_t mel_segments, size_t mel_prow, size_t mel_unit, size_t n_mels);
 int vvb_stft_forward_logmel(vvb_engine* e, const float* d_x, size_t batch, size_t n, size_t x_pitch, size_t frames, int pad_mode,
-                            const float* d_mel_w, const int* d_mel_seg, size_t mel_segments, size_t mel_prow, size_t n_mels,
-                            float eps, float* d_out, void* stream);
+                            const float* d_mel_w, const int* d_mel_seg, size_t mel_segments, size_t mel_prow, size_t mel_unit,
+                            size_t n_mels, float eps, float* d_out, void* stream);
 
 /* overlap-add synthesis of d_spec [batch][frames][spec_pitch] into d_y [batch][y_pitch]
  * (n_out valid samples each).  d_inv_norm: table set built by vvb_norm_tables_build, or

@@ -362,7 +362,7 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
         a.frames = (int)frames; a.hop = (int)e->hop; a.pad_mode = pad_mode;
         a.out = d_out; a.out_pitch = (long long)out_pitch; a.tables = e->d_tables;
         a.num_groups = (int)batch; a.groups_per_signal = 0;
-        a.mel_w = nullptr; a.mel_seg = nullptr; a.mel_S = 0; a.mel_prow = 0; a.n_mels = 0; a.mel_eps = 0.f; a.mel_pair = 0;
+        a.mel_w = nullptr; a.mel_seg = nullptr; a.mel_S = 0; a.mel_prow = 0; a.n_mels = 0; a.mel_eps = 0.f; a.mel_pair = 0; a.mel_unit = 0;
         if (!getenv("VVB_NO_MARCH")) {           /* zero padding and centred reflect padding both */
             int r = -1;
             /* (at fft_size 512 / 1024 the 2-pass generic forward kernel is faster than a 3-pass marching one) */
@@ -413,24 +413,25 @@ extern "C" int vvb_stft_forward(vvb_engine* e, const float* d_x, size_t batch, s
 
 /* STFT -> power -> log-mel in ONE kernel (stft_march_kernel<..., OUT_LOGMEL>, see mel_phase): no power spectrogram in HBM.
  * Returns 6 when this plan / schedule has no fused kernel (the caller then chains the power and log-mel kernels). */
-static FwdArgs logmel_probe_args(size_t mel_segments, size_t mel_prow, size_t n_mels)
+static FwdArgs logmel_probe_args(size_t mel_segments, size_t mel_prow, size_t mel_unit, size_t n_mels)
 {
     FwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.mel_S = (int)mel_segments; a.mel_prow = (int)mel_prow; a.n_mels = (int)n_mels;
+    a.mel_S = (int)mel_segments; a.mel_prow = (int)mel_prow; a.mel_unit = (int)mel_unit; a.n_mels = (int)n_mels;
     return a;
 }
 /* does this plan / schedule have a fused STFT -> log-mel kernel?  (same conditions as the launch below, nothing is enqueued) */
-extern "C" int vvb_stft_forward_logmel_ok(const vvb_engine* e, size_t mel_segments, size_t mel_prow, size_t n_mels)
+extern "C" int vvb_stft_forward_logmel_ok(const vvb_engine* e, size_t mel_segments, size_t mel_prow, size_t mel_unit, size_t n_mels)
 {
     using C = Cfg1024;
     if (!e || !e->fast || getenv("VVB_MEL_UNFUSED")) return 0;
     if (e->nfft <= 1024) {        /* generic forward kernel, sub-warp teams: any hop; 3 = the band sums run per warp on pairs of its frames */
         if (mel_segments == 0 || mel_segments > 64 || n_mels == 0 || n_mels > 1024 || (mel_prow & 3) || mel_prow < e->nfft / 2 + 1) return 0;
+        if (mel_unit != 2 && mel_unit != 4) return 0;
         if (getenv("VVB_MEL_NO_GENERIC")) return 0;
-        return tu_fwd_logmel((int)(e->nfft / 2), logmel_probe_args(mel_segments, mel_prow, n_mels), e->sms, nullptr, true) == 0 ? 3 : 0;
+        return tu_fwd_logmel((int)(e->nfft / 2), logmel_probe_args(mel_segments, mel_prow, mel_unit, n_mels), e->sms, nullptr, true) == 0 ? 3 : 0;
     }
-    if (e->nfft != 2048 || getenv("VVB_NO_MARCH")) return 0;
+    if (e->nfft != 2048 || mel_unit != MEL_U || getenv("VVB_NO_MARCH")) return 0;
     if (e->hop != 256 && e->hop != 512 && e->hop != 1024) return 0;
     if (mel_segments == 0 || mel_segments > 64 || n_mels == 0 || n_mels > 1024 || (mel_prow & 3)) return 0;
     /* the power row sits in the lower half of the exchange buffer; its tail past the last bin is re-zeroed by one store per lane */
@@ -444,13 +445,13 @@ extern "C" int vvb_stft_forward_logmel_ok(const vvb_engine* e, size_t mel_segmen
 }
 
 extern "C" int vvb_stft_forward_logmel(vvb_engine* e, const float* d_x, size_t batch, size_t n, size_t x_pitch, size_t frames, int pad_mode,
-                                       const float* d_mel_w, const int* d_mel_seg, size_t mel_segments, size_t mel_prow, size_t n_mels,
-                                       float eps, float* d_out, void* stream)
+                                       const float* d_mel_w, const int* d_mel_seg, size_t mel_segments, size_t mel_prow, size_t mel_unit,
+                                       size_t n_mels, float eps, float* d_out, void* stream)
 {
     if (!e || !d_x || !d_out || !d_mel_w || !d_mel_seg) return fail(1, "vvb_stft_forward_logmel", "null");
     if (batch == 0 || frames == 0) return 0;
     if (frames > 0x7fffffffu || batch > 0x7fffffffu) return fail(2, "vvb_stft_forward_logmel", "too many frames");
-    const int mode = vvb_stft_forward_logmel_ok(e, mel_segments, mel_prow, n_mels);
+    const int mode = vvb_stft_forward_logmel_ok(e, mel_segments, mel_prow, mel_unit, n_mels);
     if (!mode) return 6;
     FwdArgs a;
     a.x = d_x; a.x_pitch = (long long)x_pitch; a.n = (long long)n;
@@ -458,7 +459,7 @@ extern "C" int vvb_stft_forward_logmel(vvb_engine* e, const float* d_x, size_t b
     a.out = d_out; a.out_pitch = (long long)n_mels; a.tables = e->d_tables;
     a.num_groups = (int)batch; a.groups_per_signal = 0;
     a.mel_w = reinterpret_cast<const float4*>(d_mel_w); a.mel_seg = reinterpret_cast<const int2*>(d_mel_seg);
-    a.mel_S = (int)mel_segments; a.mel_prow = (int)mel_prow; a.n_mels = (int)n_mels; a.mel_eps = eps; a.mel_pair = mode == 2;
+    a.mel_S = (int)mel_segments; a.mel_prow = (int)mel_prow; a.mel_unit = (int)mel_unit; a.n_mels = (int)n_mels; a.mel_eps = eps; a.mel_pair = mode == 2;
     if (mode == 3) return tu_fwd_logmel((int)(e->nfft / 2), a, e->sms, stream, false);
     const int r = tu_fwd_march_2048(e->hop, a, OUT_LOGMEL, e->sms, stream);
     return r < 0 ? 6 : r;

@@ -77,6 +77,7 @@ struct FwdArgs {
     const float4* mel_w;     /* [mel_S * MEL_U][32]: the four weights of lane l's quad at schedule step i */
     const int2* mel_seg;     /* [mel_S][32]: { float offset of the segment's first quad in the power row, reset | (band + 1) << 1 } */
     int mel_S, mel_prow, n_mels;
+    int mel_unit;            /* quads per schedule segment: MEL_U in the marching kernel, 2 or 4 in the generic kernel */
     int mel_pair;            /* 1: the band sums of two consecutive frames of a warp run together and share every weight load */
     float mel_eps;
 };
@@ -88,13 +89,25 @@ VVB_CX size_t mel_smem_bytes(int G, int mel_S, int n_mels, int mel_prow, int pai
            (pair ? sizeof(float) * (size_t)G * (size_t)mel_prow : 0);
 }
 
-/* OUT_LOGMEL in the generic forward kernel: per pair of teams [even frame's power row | band sums of both frames | pad | odd
- * frame's row | pad].  The pads put the rows of the 32 / T teams of a warp T banks apart (odd row = T, pair stride = 2 T mod 32),
- * so the split step's row stores -- lane t of every team writes bin k0 + t -- never meet in a bank (ncu before: 23 % of the
- * kernel's shared-memory store wavefronts were conflicts between the two teams of a warp). */
+/* OUT_LOGMEL in the generic forward kernel: the NF = min(4, 32 / T) teams of a group make consecutive frames and leave their
+ * power rows in [row 0 | band sums of the NF frames | pad | row 1 | pad | ... ].  The pads put the rows of a warp's teams T banks
+ * apart (row j of a group at j T, group stride NF T mod 32), so the split step's row stores -- lane t of every team writes bin
+ * k0 + t -- never meet in a bank (ncu before: 23 % of the kernel's shared-memory store wavefronts were such conflicts). */
 VVB_CX int mel_up_mod32(int x, int r) { return x + ((r - x) & 31); }                       /* smallest y >= x with y = r mod 32 */
-VVB_CX int mel_rowb_offset(int mel_prow, int nmp, int T) { return mel_up_mod32(mel_prow + 2 * nmp, T & 31); }
-VVB_CX int mel_pair_stride(int mel_prow, int nmp, int T) { return mel_up_mod32(mel_rowb_offset(mel_prow, nmp, T) + mel_prow, (2 * T) & 31); }
+VVB_CX int mel_row_offset(int j, int mel_prow, int nmp, int T, int NF, bool spread)
+{
+    int off = 0;
+    for (int i = 1; i <= j; ++i) {
+        const int end = (i == 1) ? mel_prow + NF * nmp : off + mel_prow;
+        off = spread ? mel_up_mod32(end, (i * T) & 31) : end;
+    }
+    return off;
+}
+VVB_CX int mel_group_stride(int mel_prow, int nmp, int T, int NF, bool spread)
+{
+    const int end = (NF == 1 ? mel_prow + nmp : mel_row_offset(NF - 1, mel_prow, nmp, T, NF, spread) + mel_prow);
+    return spread ? mel_up_mod32(end, (NF * T) & 31) : end;
+}
 
 struct InvArgs {
     const float2* spec;      /* [batch][frames][spec_pitch] */
@@ -205,6 +218,56 @@ VVB_DEV void mel_phase(const FwdArgs& a, const float4* s_w, const int2* s_seg, c
     }
     __syncwarp();                                                      /* the rows and the band sums are free again */
 }
+/* mel_phase for the generic forward kernel: NF consecutive frames of one signal (rows at base + roff[j], band sums behind row 0)
+ * share every weight load -- per quad 4 shared-memory wavefronts of weights and 4 per frame -- with U quads per segment; the first
+ * `nact` frames exist and leave as ONE contiguous run of nact * n_mels logarithms. */
+template <int NF, int U>
+VVB_DEV void mel_phase_multi(const FwdArgs& a, const float4* s_w, const int2* s_seg, const float* base, const int (&roff)[NF], int nmp,
+                             int t, long long out_row0, int nact)
+{
+    __syncwarp();                                                      /* the power rows are complete */
+    float* mout = const_cast<float*>(base) + a.mel_prow;
+    float acc[NF];
+#pragma unroll
+    for (int j = 0; j < NF; ++j) acc[j] = 0.f;
+    const float4* wq = s_w + t;
+#pragma unroll 1
+    for (int s = 0; s < a.mel_S; ++s) {
+        const int2 d = s_seg[s * 32 + t];
+        if (d.y & 1) {
+#pragma unroll
+            for (int j = 0; j < NF; ++j) acc[j] = 0.f;
+        }
+        const float* p = base + d.x;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float4 w = wq[(s * U + u) * 32];
+#pragma unroll
+            for (int j = 0; j < NF; ++j) {
+                const float4 x = *reinterpret_cast<const float4*>(p + roff[j] + 4 * u);
+                acc[j] = __fadd_rn(acc[j], __fmul_rn(x.x, w.x));
+                acc[j] = __fadd_rn(acc[j], __fmul_rn(x.y, w.y));
+                acc[j] = __fadd_rn(acc[j], __fmul_rn(x.z, w.z));
+                acc[j] = __fadd_rn(acc[j], __fmul_rn(x.w, w.w));
+            }
+        }
+        if (d.y >> 1) {
+#pragma unroll
+            for (int j = 0; j < NF; ++j) mout[j * nmp + (d.y >> 1) - 1] = acc[j];
+        }
+    }
+    __syncwarp();
+    float* o = reinterpret_cast<float*>(a.out) + out_row0 * a.out_pitch;      /* out_pitch = n_mels: the frames' rows are contiguous */
+    const int count = nact * a.n_mels;
+    for (int i = t; i < count; i += 32) {
+        int j = 0, m = i;
+#pragma unroll
+        for (int q = 1; q < NF; ++q) if (i >= q * a.n_mels) { j = q; m = i - q * a.n_mels; }
+        o[i] = logf(mout[j * nmp + m] + a.mel_eps);
+    }
+    __syncwarp();                                                      /* the rows and the band sums are free again */
+}
+
 /* X[k] = sm/2 - g, X[M-k] = conj(sm/2 + g) with sm = A + conj(Bc), g = ((sin + j cos)/2) (A - conj(Bc)) */
 VVB_DEV void split_math(float2 A, float2 Bc, float2 hw, float2& x0, float2& x1)
 {
@@ -291,24 +354,30 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
     copy_table(s_win, a.tables + TB::WIN, N);
     copy_table(reinterpret_cast<float*>(s_tw2), a.tables + TB::TW2, 2 * (C::TW2 + C::TW3 + C::POST));
     /* OUT_LOGMEL in this kernel (sub-warp teams: fft_size 256 ... 1024 and the speech framings): a warp's 32 / T teams make
-     * consecutive frames; each team leaves its power row in shared memory and the warp then runs mel_phase<2> on every pair of
-     * rows with the lane schedules of csrc/host/mel.c -- no CTA barrier, so the band sums of one warp overlap the transforms of
-     * the others.  Per pair of teams: [even frame's row | band sums of both frames | odd frame's row] (mel_pair_stride), row tails stay zero. */
+     * consecutive frames; each team leaves its power row in shared memory and the warp then runs mel_phase_multi on every group
+     * of NF rows with the lane schedules of csrc/host/mel.c -- no CTA barrier, so the band sums of one warp overlap the
+     * transforms of the others.  Layout per group: mel_row_offset / mel_group_stride; row tails stay zero. */
+    constexpr int TPW = T <= 32 ? 32 / T : 1;                         /* teams (= consecutive frames) per warp */
+    constexpr int NF = TPW < 4 ? (TPW < 2 ? 1 : TPW) : 4;             /* frames that share the weight loads */
     float4* s_melw = nullptr;
     int2* s_melseg = nullptr;
     float* s_rows = nullptr;
-    int nmp = 0, pstride = 0, rowb = 0;
+    int nmp = 0, gstride = 0, my_row = 0;
+    int roff[NF];
     if constexpr (OUT == OUT_LOGMEL) {
-        static_assert(T <= 16 && G % 2 == 0, "two or more teams per warp");
+        static_assert(T <= 16 && G % NF == 0, "two or more teams per warp");
         s_melw = reinterpret_cast<float4*>(smem + ((N + 2 * (C::TW2 + C::TW3 + C::POST + 1) + 2 * G * C::XBUF + 3) & ~3));
-        s_melseg = reinterpret_cast<int2*>(s_melw + a.mel_S * MEL_U * 32);
+        s_melseg = reinterpret_cast<int2*>(s_melw + a.mel_S * a.mel_unit * 32);
         s_rows = reinterpret_cast<float*>(s_melseg + a.mel_S * 32);
         nmp = (a.n_mels + 31) & ~31;
-        rowb = a.mel_pair ? mel_rowb_offset(a.mel_prow, nmp, T) : a.mel_prow + 2 * nmp;       /* here mel_pair = 1: rows spread over the banks */
-        pstride = a.mel_pair ? mel_pair_stride(a.mel_prow, nmp, T) : 2 * a.mel_prow + 2 * nmp;
-        copy_table(reinterpret_cast<float*>(s_melw), reinterpret_cast<const float*>(a.mel_w), a.mel_S * MEL_U * 32 * 4);
+        const bool spread = (a.mel_pair & 1) != 0;                    /* (A/B switch: rows T banks apart, or back to back) */
+#pragma unroll
+        for (int j = 0; j < NF; ++j) roff[j] = mel_row_offset(j, a.mel_prow, nmp, T, NF, spread);
+        gstride = mel_group_stride(a.mel_prow, nmp, T, NF, spread);
+        my_row = (int)(threadIdx.x / T / NF) * gstride + mel_row_offset((int)(threadIdx.x / T) % NF, a.mel_prow, nmp, T, NF, spread);
+        copy_table(reinterpret_cast<float*>(s_melw), reinterpret_cast<const float*>(a.mel_w), a.mel_S * a.mel_unit * 32 * 4);
         copy_table(reinterpret_cast<float*>(s_melseg), reinterpret_cast<const float*>(a.mel_seg), a.mel_S * 32 * 2);
-        for (int i = threadIdx.x; i < (G / 2) * pstride; i += blockDim.x) s_rows[i] = 0.f;
+        for (int i = threadIdx.x; i < (G / NF) * gstride; i += blockDim.x) s_rows[i] = 0.f;
     }
     __syncthreads();
 
@@ -395,11 +464,10 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
         const long long row = ((long long)b * a.frames + f) * a.out_pitch;
         if constexpr (OUT == OUT_LOGMEL) {
             static_assert(VVB_FWD_HALF_SPLIT && !VVB_FWD_TABLE_TWIDDLES, "the fused log-mel phase takes the half-column split");
-            constexpr int TPW = 32 / T;                               /* teams (= consecutive frames) per warp */
             publish_upper_half<C>(v, xb, t, typename make_iseq<E / 2>::type{});
             team_sync<T>(team);
             if (active) {                                             /* the power row goes to shared memory */
-                float* pw = s_rows + (team >> 1) * pstride + ((team & 1) ? rowb : 0);
+                float* pw = s_rows + my_row;
                 split_pairs_half<C, OUT, (C::M <= 2048)>(v, xb, hw_t, s_post, t, pw, 0, typename make_iseq<E / 2>::type{});
                 if (t == 0) {
                     const float2 A = v[column_slot<C, E / 2>()];
@@ -408,13 +476,24 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
             }
             const int lane = threadIdx.x & 31, wteam = (threadIdx.x >> 5) * TPW, fw = f - (team - wteam);
 #pragma unroll 1
-            for (int q = 0; q < TPW / 2; ++q) {
-                const int fe = fw + 2 * q;                            /* the same for all lanes of the warp */
+            for (int q = 0; q < TPW / NF; ++q) {
+                const int fe = fw + NF * q;                           /* the same for all lanes of the warp */
                 if (fe >= a.frames) break;
-                float* pb = s_rows + ((wteam >> 1) + q) * pstride;
+                const float* pb = s_rows + (wteam / NF + q) * gstride;
                 const long long orow = (long long)b * a.frames + fe;
-                if (fe + 1 < a.frames) mel_phase<2>(a, s_melw, s_melseg, pb, pb + rowb, pb + a.mel_prow, lane, orow, orow + 1);
-                else mel_phase<1>(a, s_melw, s_melseg, pb, pb, pb + a.mel_prow, lane, orow, orow);
+                const int nact = min(NF, a.frames - fe);
+                if constexpr (NF == 2) {
+                    /* two frames per warp (T = 16): the marching kernel's phase, four quads per segment (same-box A/B against
+                     * mel_phase_multi<2, U>: fft_size 1024 2.92 vs 3.04 (U = 4) / 3.09 ms (U = 2), 640: 1.45 vs 1.54 / 1.53 ms) */
+                    float* mo = const_cast<float*>(pb) + a.mel_prow;
+                    if (nact == 2) mel_phase<2>(a, s_melw, s_melseg, pb, pb + roff[1], mo, lane, orow, orow + 1);
+                    else mel_phase<1>(a, s_melw, s_melseg, pb, pb, mo, lane, orow, orow);
+                } else {
+                    /* four frames share the weight loads (T <= 8); short bands take two quads per segment (fft_size 400:
+                     * 1.19 -> 1.11 ms with four frames, -> 1.09 ms with two-quad segments; 256: 1.15 -> 1.02 -> 0.98 ms) */
+                    if (a.mel_unit == 2) mel_phase_multi<NF, 2>(a, s_melw, s_melseg, pb, roff, nmp, lane, orow, nact);
+                    else mel_phase_multi<NF, 4>(a, s_melw, s_melseg, pb, roff, nmp, lane, orow, nact);
+                }
             }
         } else if constexpr (VVB_FWD_HALF_SPLIT && !VVB_FWD_TABLE_TWIDDLES) {
             publish_upper_half<C>(v, xb, t, typename make_iseq<E / 2>::type{});

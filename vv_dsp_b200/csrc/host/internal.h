@@ -5,8 +5,8 @@
 
 /* device-resident sparse mel filterbank: meta = lo | len | off per band, packed non-zero weights */
 /* d_fw / d_fseg (may be NULL): lane schedules of the fused STFT -> log-mel kernel (f_segments segments per lane, power row of
- * f_prow floats), see mel.c build_fused_tables */
-typedef struct mel_device { int* d_meta; float* d_w; size_t n_groups; float* d_fw; int* d_fseg; size_t f_segments, f_prow; } mel_device;
+ * f_prow floats, f_unit quads per segment), see mel.c build_fused_tables */
+typedef struct mel_device { int* d_meta; float* d_w; size_t n_groups; float* d_fw; int* d_fseg; size_t f_segments, f_prow, f_unit; } mel_device;
 int vvdsp_internal_mel_device_build(const float* dense_weights, size_t n_mels, size_t bins, void* stream, mel_device* md);
 void vvdsp_internal_mel_device_free(mel_device* md);
 /* log-mel of densely packed power rows on the device (the four-tap group kernels) */

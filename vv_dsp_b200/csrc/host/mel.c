@@ -87,7 +87,7 @@ void vv_dsp_mel_filterbank_free(vv_dsp_real* filterbank_weights, size_t n_mels)
 void vvdsp_internal_mel_device_free(mel_device* md)
 {
     vvb_free(md->d_meta); vvb_free(md->d_w); vvb_free(md->d_fw); vvb_free(md->d_fseg);
-    md->d_meta = NULL; md->d_w = NULL; md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0;
+    md->d_meta = NULL; md->d_w = NULL; md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0; md->f_unit = 0;
 }
 
 /* Lane schedules of the fused STFT -> log-mel kernel (csrc/cuda/vvb_stft_kernels.cuh, mel_phase).  The warp that has just
@@ -109,11 +109,11 @@ void vvdsp_internal_mel_device_free(mel_device* md)
  * band up to `slack` quads early (zero weights) where its last segment has room: 260 -> 108 wavefronts per frame for the
  * 80-band / 1025-bin filterbank, against 96 without any conflict.  Idle segments read the least loaded residue.
  * Not built (the chained kernels serve the call) when the schedule would exceed FUSED_MAX_STEPS quad steps. */
-#define FUSED_U 4
 #define FUSED_LANES 32
 #define FUSED_MAX_STEPS 48
 typedef struct fused_sched {
     size_t S, n_mels;
+    int U;                      /* quads per segment: 4, or 2 where the bands are short (small bin counts) */
     const int *nseg, *q0;
     int* delta;                 /* quads a band starts early */
     int* list;                  /* [32][n_mels]: bands of schedule v in execution order */
@@ -128,12 +128,12 @@ static void fused_residues(const fused_sched* fs, int v, int* res)
     int i, j;
     for (i = 0; i < fs->count[v]; ++i) {
         const int b = fs->list[(size_t)v * fs->n_mels + (size_t)i];
-        for (j = 0; j < fs->nseg[b]; ++j) res[s++] = (fs->q0[b] - fs->delta[b] + j * FUSED_U) & 7;
+        for (j = 0; j < fs->nseg[b]; ++j) res[s++] = (fs->q0[b] - fs->delta[b] + j * fs->U) & 7;
     }
     while (s < fs->S) res[s++] = -1;
 }
 
-/* shared-memory wavefronts of the power-row loads per frame: per quarter warp and segment, FUSED_U loads of max-multiplicity */
+/* shared-memory wavefronts of the power-row loads per frame: per quarter warp and segment, U loads of max-multiplicity */
 static long fused_cost(const fused_sched* fs, int* scratch)
 {
     long total = 0;
@@ -146,13 +146,63 @@ static long fused_cost(const fused_sched* fs, int* scratch)
             for (i = 0; i < 8; ++i) { const int r = scratch[(size_t)i * fs->S + s]; if (r < 0) ++idle; else ++cnt[r]; }
             while (idle-- > 0) { int least = 0; for (k = 1; k < 8; ++k) if (cnt[k] < cnt[least]) least = k; ++cnt[least]; }
             for (k = 0; k < 8; ++k) if (cnt[k] > worst) worst = cnt[k];
-            total += (long)worst * FUSED_U;
+            total += (long)worst * fs->U;
         }
     }
     return total;
 }
 
-static int build_fused_tables(const float* weights, size_t n_mels, size_t bins, const int* lo, const int* len, void* stream, mel_device* md)
+/* segments per lane the best-fit-decreasing placement needs with `unit` quads per segment (0: none within FUSED_MAX_STEPS) */
+static size_t fused_min_segments(const int* lo, const int* len, size_t n_mels, int unit)
+{
+    int load[FUSED_LANES];
+    size_t m, l, total = 0, S;
+    int maxseg = 1;
+    int* nseg = (int*)malloc(n_mels * sizeof(int));
+    int* order = (int*)malloc(n_mels * sizeof(int));
+    if (!nseg || !order) { free(nseg); free(order); return 0; }
+    for (m = 0; m < n_mels; ++m) {
+        const int first = len[m] > 0 ? lo[m] : 0, end = len[m] > 0 ? lo[m] + len[m] : 1;
+        size_t q = m;
+        nseg[m] = ((end + 3) / 4 - first / 4 + unit - 1) / unit;
+        if (nseg[m] > maxseg) maxseg = nseg[m];
+        total += (size_t)nseg[m];
+        while (q > 0 && nseg[order[q - 1]] < nseg[m]) { order[q] = order[q - 1]; --q; }
+        order[q] = (int)m;
+    }
+    S = (total + FUSED_LANES - 1) / FUSED_LANES;
+    if (S < (size_t)maxseg) S = (size_t)maxseg;
+    for (; S * (size_t)unit <= FUSED_MAX_STEPS; ++S) {
+        int ok = 1;
+        for (l = 0; l < FUSED_LANES; ++l) load[l] = 0;
+        for (m = 0; m < n_mels && ok; ++m) {
+            int best = -1;
+            for (l = 0; l < FUSED_LANES; ++l)
+                if (load[l] + nseg[order[m]] <= (int)S && (best < 0 || load[l] > load[best])) best = (int)l;
+            if (best < 0) ok = 0; else load[best] += nseg[order[m]];
+        }
+        if (ok) break;
+    }
+    free(nseg); free(order);
+    return S * (size_t)unit <= FUSED_MAX_STEPS ? S : 0;
+}
+
+/* Quads per segment.  The marching kernel (fft_size 2048) and the generic forward kernel with two frames per warp (fft_size 512,
+ * 640, 1024) are written for four.  With four frames per warp (fft_size <= 480: at most 241 bins) the generic kernel takes two or
+ * four: with short bands (five taps at fft_size 400 / 80 bands) a four-quad segment is mostly zero padding, so the choice goes by
+ * the shared-memory wavefronts of a segment: ~6 of bookkeeping + 20 per quad (weights once, four power rows). */
+static int fused_choose_unit(const int* lo, const int* len, size_t n_mels, size_t bins)
+{
+    size_t s2, s4;
+    if (bins > 241 || getenv("VVB_MEL_UNIT4")) return 4;
+    s2 = fused_min_segments(lo, len, n_mels, 2);
+    s4 = fused_min_segments(lo, len, n_mels, 4);
+    if (!s2) return 4;
+    if (!s4) return 2;
+    return s2 * (6 + 20 * 2) < s4 * (6 + 20 * 4) ? 2 : 4;
+}
+
+static int build_fused_tables(const float* weights, size_t n_mels, size_t bins, const int* lo, const int* len, int unit, void* stream, mel_device* md)
 {
     int *nseg = NULL, *q0 = NULL, *nq = NULL, *order = NULL, *seg = NULL, *scratch = NULL;
     int load[FUSED_LANES];
@@ -162,7 +212,8 @@ static int build_fused_tables(const float* weights, size_t n_mels, size_t bins, 
     int st = 0, maxseg = 1, ok = 0, p;
     unsigned long long rng = 0x9E3779B97F4A7C15ull;
     long cost;
-    md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0;
+    const int FUSED_U = unit;
+    md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0; md->f_unit = 0;
     memset(&fs, 0, sizeof(fs));
     if (n_mels == 0 || n_mels > 1024 || bins == 0 || bins > (1u << 20)) return 0;
     nseg = (int*)malloc(n_mels * sizeof(int)); q0 = (int*)malloc(n_mels * sizeof(int)); nq = (int*)malloc(n_mels * sizeof(int));
@@ -200,7 +251,7 @@ static int build_fused_tables(const float* weights, size_t n_mels, size_t bins, 
         if (ok) break;
     }
     if (!ok) goto done;                                                /* no schedule short enough: not an error */
-    fs.S = S; fs.n_mels = n_mels; fs.nseg = nseg; fs.q0 = q0;
+    fs.S = S; fs.n_mels = n_mels; fs.nseg = nseg; fs.q0 = q0; fs.U = unit;
     for (p = 0; p < FUSED_LANES; ++p) fs.perm[p] = p;
     scratch = (int*)malloc(8 * S * sizeof(int));
     if (!scratch) { st = 4; goto done; }
@@ -286,7 +337,7 @@ static int build_fused_tables(const float* weights, size_t n_mels, size_t bins, 
     if (!st) st = vvb_memcpy_h2d(md->d_fw, wq, S * FUSED_U * FUSED_LANES * 4 * sizeof(float), stream);
     if (!st) st = vvb_memcpy_h2d(md->d_fseg, seg, S * FUSED_LANES * 2 * sizeof(int), stream);
     if (!st) st = vvb_stream_sync(stream);
-    if (!st) { md->f_segments = S; md->f_prow = 4 * prow_quads; }
+    if (!st) { md->f_segments = S; md->f_prow = 4 * prow_quads; md->f_unit = (size_t)unit; }
     else { vvb_free(md->d_fw); vvb_free(md->d_fseg); md->d_fw = NULL; md->d_fseg = NULL; }
 done:
     free(nseg); free(q0); free(nq); free(order); free(fs.delta); free(fs.list); free(scratch); free(wq); free(seg);
@@ -301,7 +352,7 @@ int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t 
     float* packed = NULL;
     int st = 4;
     md->d_meta = NULL; md->d_w = NULL; md->n_groups = 0;
-    md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0;
+    md->d_fw = NULL; md->d_fseg = NULL; md->f_segments = 0; md->f_prow = 0; md->f_unit = 0;
     gcount = (int*)malloc(n_mels * sizeof(int)); gfirst = (int*)malloc(n_mels * sizeof(int));
     order = (int*)malloc(n_mels * sizeof(int)); owner = (int*)malloc(n_mels * sizeof(int));
     load = (int*)malloc(128 * sizeof(int));
@@ -387,7 +438,7 @@ int vvdsp_internal_mel_device_build(const float* weights, size_t n_mels, size_t 
     if (!st && w_len) st = vvb_memcpy_h2d(md->d_w, packed, w_len * sizeof(float), stream);
     if (!st) st = vvb_stream_sync(stream);          /* the host staging arrays die below */
     if (!st) md->n_groups = groups;
-    if (!st) st = build_fused_tables(weights, n_mels, bins, meta, meta + n_mels, stream, md);
+    if (!st) st = build_fused_tables(weights, n_mels, bins, meta, meta + n_mels, fused_choose_unit(meta, meta + n_mels, n_mels, bins), stream, md);
 done:
     free(meta); free(packed); free(order); free(gcount); free(gfirst); free(load); free(owner);
     if (st) vvdsp_internal_mel_device_free(md);

@@ -591,7 +591,7 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const void* signals_v, int 
     }
     /* one kernel from samples to log-mel rows where the plan has it (fft_size 2048 marching kernel): the power spectrogram
      * then never exists in HBM and there is no scratch; chunks only bound the host staging buffers */
-    fused = !st && h->mel.d_fw && vvb_stft_forward_logmel_ok(h->eng, h->mel.f_segments, h->mel.f_prow, n_mels);
+    fused = !st && h->mel.d_fw && vvb_stft_forward_logmel_ok(h->eng, h->mel.f_segments, h->mel.f_prow, h->mel.f_unit, n_mels);
     if (getenv("VVB_MEL_DEBUG")) fprintf(stderr, "vvb: STFT -> log-mel: %s\n", fused ? "one fused kernel" : "power kernel + log-mel kernel");
     if (fused) {
         const size_t stage_target = h->stage_target;                   /* VVB_STAGE_TARGET_BYTES applies here too */
@@ -656,7 +656,7 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const void* signals_v, int 
                                       n * sizeof(float), nb, sq);
             }
             if (!st) st = vvb_stft_forward_logmel(h->eng, px[c & 1], nb, n, n ? n : 1, frames, pad, h->mel.d_fw, h->mel.d_fseg,
-                                                  h->mel.f_segments, h->mel.f_prow, n_mels, log_epsilon, lm_dev, sq);
+                                                  h->mel.f_segments, h->mel.f_prow, h->mel.f_unit, n_mels, log_epsilon, lm_dev, sq);
             if (!st && n_coeffs) st = vvb_mfcc(lm_dev, nb * frames, n_mels, n_coeffs, h->mfcc.d_table, h->mfcc.d_lifter, o_dev, sq);
             if (!st && out_space == VV_DSP_MEM_HOST)
                 st = vvb_memcpy_d2h(out + done * frames * width, po[c & 1], nb * frames * width * sizeof(float), sq);
@@ -691,7 +691,7 @@ static vv_dsp_status batch_mel_chain(vv_dsp_stft* h, const void* signals_v, int 
         lm_dev = n_coeffs ? h->d_logmel_scratch : o_dev;
         if (fused) {
             if (!st) st = vvb_stft_forward_logmel(h->eng, x_dev, nb, n, xp, frames, pad, h->mel.d_fw, h->mel.d_fseg, h->mel.f_segments,
-                                                  h->mel.f_prow, n_mels, log_epsilon, lm_dev, stream);
+                                                  h->mel.f_prow, h->mel.f_unit, n_mels, log_epsilon, lm_dev, stream);
         } else {
             if (!st) st = vvb_stft_forward(h->eng, x_dev, nb, n, xp, frames, pad, VVB_OUT_POWER, d_power, h->bins, stream);
             if (!st) st = vvdsp_internal_logmel(&h->mel, d_power, nb * frames, h->bins, n_mels, log_epsilon, lm_dev, stream);
