@@ -392,9 +392,20 @@ def check_mel_host_pipeline(lib, nfft=2048, hop=512, n=9000, batch=7):
     xf = np.stack([pcm_to_planar(raw[i].tobytes(), 16, 1, lib=lib)[0] for i in range(batch)])
     with Stft(nfft, hop, "hann", lib=lib) as h:
         assert np.array_equal(h.batch_logmel_pcm(raw, w, 16, 1e-6, "center"), h.batch_logmel(xf, w, 1e-6, "center"))
-    with Stft(512, 128, "hann", lib=lib) as h:                         # a size without the fused kernel: the chained path
+    with Stft(512, 128, "hann", lib=lib) as h:                         # the generic forward kernel's fused flavour
         st2, w2 = mel_filterbank(512, 26, 16000.0, 0.0, 8000.0, lib=lib)
         assert np.array_equal(h.batch_logmel_pcm(raw, w2, 16, 1e-6, "valid"), h.batch_logmel(xf, w2, 1e-6, "valid"))
+        # the other WAV sample formats: 24-bit packed, 32-bit PCM, float32
+        rng = np.random.default_rng(4)
+        r24 = rng.integers(0, 256, (batch, 3 * n), dtype=np.uint8)
+        r32 = rng.integers(-2**31, 2**31, (batch, n), dtype=np.int64).astype(np.int32)
+        rf = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+        for fmt, rawf in ((24, r24), (32, r32), (-32, rf)):
+            dec = np.stack([pcm_to_planar(rawf[i].tobytes(), fmt, 1, lib=lib)[0] for i in range(batch)])
+            assert np.array_equal(h.batch_logmel_pcm(rawf, w2, fmt, 1e-6, "center"), h.batch_logmel(dec, w2, 1e-6, "center")), fmt
+    with Stft(4096, 1024, "hann", lib=lib) as h:                       # a size without a fused kernel: the chained path
+        st3, w3 = mel_filterbank(4096, 40, 48000.0, 0.0, 24000.0, lib=lib)
+        assert np.array_equal(h.batch_logmel_pcm(raw, w3, 16, 1e-6, "center"), h.batch_logmel(xf, w3, 1e-6, "center"))
 
 
 def check_mfcc(lib, oracle):
