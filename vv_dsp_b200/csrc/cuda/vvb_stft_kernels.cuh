@@ -49,6 +49,9 @@
 namespace vvb {
 
 enum { OUT_COMPLEX = 0, OUT_POWER = 1, OUT_MAGNITUDE = 2, OUT_LOGMEL = 3 };   /* OUT_LOGMEL: marching kernel and generic kernel with sub-warp teams, see mel_phase */
+#ifndef VVB_MEL_NF_MAX
+#define VVB_MEL_NF_MAX 4             /* generic forward kernel, fused log-mel: frames of a warp that share the weight loads (A/B builds: 8) */
+#endif
 constexpr int MEL_U = 4;              /* fused log-mel: four-tap groups ("quads") per schedule segment */
 enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
 
@@ -222,10 +225,17 @@ VVB_DEV void mel_phase(const FwdArgs& a, const float4* s_w, const int2* s_seg, c
  * share every weight load -- per quad 4 shared-memory wavefronts of weights and 4 per frame -- with U quads per segment; the first
  * `nact` frames exist and leave as ONE contiguous run of nact * n_mels logarithms. */
 template <int NF, int U>
-VVB_DEV void mel_phase_multi(const FwdArgs& a, const float4* s_w, const int2* s_seg, const float* base, const int (&roff)[NF], int nmp,
+VVB_DEV void mel_phase_multi(const FwdArgs& a, const float4* s_w, const int2* s_seg, const float* base, int T, int nmp,
                              int t, long long out_row0, int nact)
 {
     __syncwarp();                                                      /* the power rows are complete */
+    int roff[NF];                                                      /* (recomputed here: NF registers less across the transform) */
+    roff[0] = 0;
+#pragma unroll
+    for (int j = 1; j < NF; ++j) {
+        const int end = (j == 1) ? a.mel_prow + NF * nmp : roff[j - 1] + a.mel_prow;
+        roff[j] = (a.mel_pair & 1) ? mel_up_mod32(end, (j * T) & 31) : end;
+    }
     float* mout = const_cast<float*>(base) + a.mel_prow;
     float acc[NF];
 #pragma unroll
@@ -358,12 +368,12 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
      * of NF rows with the lane schedules of csrc/host/mel.c -- no CTA barrier, so the band sums of one warp overlap the
      * transforms of the others.  Layout per group: mel_row_offset / mel_group_stride; row tails stay zero. */
     constexpr int TPW = T <= 32 ? 32 / T : 1;                         /* teams (= consecutive frames) per warp */
-    constexpr int NF = TPW < 4 ? (TPW < 2 ? 1 : TPW) : 4;             /* frames that share the weight loads */
+    constexpr int NF = TPW < VVB_MEL_NF_MAX ? (TPW < 2 ? 1 : TPW) : VVB_MEL_NF_MAX;   /* frames that share the weight loads */
     float4* s_melw = nullptr;
     int2* s_melseg = nullptr;
     float* s_rows = nullptr;
     int nmp = 0, gstride = 0, my_row = 0;
-    int roff[NF];
+    int rowb = 0;                                                     /* NF == 2: the odd frame's row */
     if constexpr (OUT == OUT_LOGMEL) {
         static_assert(T <= 16 && G % NF == 0, "two or more teams per warp");
         s_melw = reinterpret_cast<float4*>(smem + ((N + 2 * (C::TW2 + C::TW3 + C::POST + 1) + 2 * G * C::XBUF + 3) & ~3));
@@ -371,8 +381,7 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
         s_rows = reinterpret_cast<float*>(s_melseg + a.mel_S * 32);
         nmp = (a.n_mels + 31) & ~31;
         const bool spread = (a.mel_pair & 1) != 0;                    /* (A/B switch: rows T banks apart, or back to back) */
-#pragma unroll
-        for (int j = 0; j < NF; ++j) roff[j] = mel_row_offset(j, a.mel_prow, nmp, T, NF, spread);
+        rowb = mel_row_offset(1, a.mel_prow, nmp, T, NF, spread);
         gstride = mel_group_stride(a.mel_prow, nmp, T, NF, spread);
         my_row = (int)(threadIdx.x / T / NF) * gstride + mel_row_offset((int)(threadIdx.x / T) % NF, a.mel_prow, nmp, T, NF, spread);
         copy_table(reinterpret_cast<float*>(s_melw), reinterpret_cast<const float*>(a.mel_w), a.mel_S * a.mel_unit * 32 * 4);
@@ -486,13 +495,13 @@ __global__ void __launch_bounds__(C::T* G, (C::E <= 16 ? 2 : 1)) stft_forward_ke
                     /* two frames per warp (T = 16): the marching kernel's phase, four quads per segment (same-box A/B against
                      * mel_phase_multi<2, U>: fft_size 1024 2.92 vs 3.04 (U = 4) / 3.09 ms (U = 2), 640: 1.45 vs 1.54 / 1.53 ms) */
                     float* mo = const_cast<float*>(pb) + a.mel_prow;
-                    if (nact == 2) mel_phase<2>(a, s_melw, s_melseg, pb, pb + roff[1], mo, lane, orow, orow + 1);
+                    if (nact == 2) mel_phase<2>(a, s_melw, s_melseg, pb, pb + rowb, mo, lane, orow, orow + 1);
                     else mel_phase<1>(a, s_melw, s_melseg, pb, pb, mo, lane, orow, orow);
                 } else {
                     /* four frames share the weight loads (T <= 8); short bands take two quads per segment (fft_size 400:
                      * 1.19 -> 1.11 ms with four frames, -> 1.09 ms with two-quad segments; 256: 1.15 -> 1.02 -> 0.98 ms) */
-                    if (a.mel_unit == 2) mel_phase_multi<NF, 2>(a, s_melw, s_melseg, pb, roff, nmp, lane, orow, nact);
-                    else mel_phase_multi<NF, 4>(a, s_melw, s_melseg, pb, roff, nmp, lane, orow, nact);
+                    if (a.mel_unit == 2) mel_phase_multi<NF, 2>(a, s_melw, s_melseg, pb, T, nmp, lane, orow, nact);
+                    else mel_phase_multi<NF, 4>(a, s_melw, s_melseg, pb, T, nmp, lane, orow, nact);
                 }
             }
         } else if constexpr (VVB_FWD_HALF_SPLIT && !VVB_FWD_TABLE_TWIDDLES) {

@@ -8,7 +8,7 @@ namespace vvb {
 
 template <class C> static size_t logmel_smem(const FwdArgs& a)
 {
-    constexpr int G = Teams<C>::G, TPW = 32 / C::T, NF = TPW < 4 ? TPW : 4;
+    constexpr int G = Teams<C>::G, TPW = 32 / C::T, NF = TPW < VVB_MEL_NF_MAX ? TPW : VVB_MEL_NF_MAX;
     const int nmp = (a.n_mels + 31) & ~31;
     return ((smem_fwd<C>() + 15) & ~(size_t)15) + (size_t)a.mel_S * 32 * (16 * (size_t)a.mel_unit + 8) +
            sizeof(float) * (G / NF) * (size_t)mel_group_stride(a.mel_prow, nmp, C::T, NF, true);
@@ -16,7 +16,7 @@ template <class C> static size_t logmel_smem(const FwdArgs& a)
 template <class C> static int launch_forward_logmel(FwdArgs a, int sms, void* stream, bool probe)
 {
     constexpr int G = Teams<C>::G;
-    if (32 / C::T < 4 && a.mel_unit != MEL_U) return 6;       /* two frames per warp: mel_phase<2>, written for MEL_U quads per segment */
+    if (32 / C::T == 2 && a.mel_unit != MEL_U) return 6;       /* two frames per warp: mel_phase<2>, written for MEL_U quads per segment */
     const size_t smem = logmel_smem<C>(a);
     if (smem > 227 * 1024) return 6;                             /* schedule too long for the shared memory left: chained kernels */
     if (probe) return 0;
