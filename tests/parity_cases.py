@@ -344,6 +344,35 @@ def check_mel_fused_cta(lib, oracle, cases=((400, 160, 80, 16000.0), (512, 128, 
             assert np.abs(e - er).max() <= 1e-4 * er.max(), (nfft, hop)
 
 
+def check_mel_fused_fallback(lib, capfd=None):
+    """Filterbanks whose band sums do not fit the fused kernel's shared memory (200 bands at fft_size 400) or whose lane schedule
+    is too long to build (400 bands at 1024) take the chained kernels -- silently and with the same rows; 128 bands still fuse."""
+    import os
+    from vv_dsp_b200 import mel_filterbank
+    rng = np.random.default_rng(23)
+    for nfft, hop, n_mels, sr, expect in ((400, 160, 200, 16000.0, "power kernel + log-mel kernel"), (400, 160, 128, 16000.0, "one fused kernel"),
+                                          (1024, 256, 400, 48000.0, "power kernel + log-mel kernel"), (256, 64, 128, 8000.0, "one fused kernel")):
+        st, w = mel_filterbank(nfft, n_mels, sr, 0.0, sr / 2, lib=lib)
+        assert st == 0
+        x = rng.uniform(-1, 1, (3, nfft * 9 + 17)).astype(np.float32)
+        with Stft(nfft, hop, "hann", lib=lib) as h:
+            if capfd is not None:
+                capfd.readouterr()
+                os.environ["VVB_MEL_DEBUG"] = "1"
+            try:
+                a = h.batch_logmel(x, w, 1e-6, "center")
+            finally:
+                os.environ.pop("VVB_MEL_DEBUG", None)
+            if capfd is not None:
+                assert expect in capfd.readouterr().err, (nfft, n_mels)
+            os.environ["VVB_MEL_UNFUSED"] = "1"
+            try:
+                b = h.batch_logmel(x, w, 1e-6, "center")
+            finally:
+                del os.environ["VVB_MEL_UNFUSED"]
+            assert a.shape == (3, h.num_frames(x.shape[1], "center"), n_mels) and np.array_equal(a, b), (nfft, n_mels)
+
+
 def check_mel_fused_random_filterbanks(lib, seeds=range(6), nfft=2048, hop=512):
     """The fused kernel takes ANY weight matrix whose lane schedule fits: random band counts, supports, orders, holes and
     signs, odd and even frame counts per signal (pair flush), against the chained kernels bit for bit."""

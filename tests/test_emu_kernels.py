@@ -96,6 +96,10 @@ def test_mel_fused_cta(emu, oracle, capfd):
                                                (320, 160, 40, 16000.0)), n=4000, batch=3, capfd=capfd)
 
 
+def test_mel_fused_fallback(emu, capfd):
+    pc.check_mel_fused_fallback(emu, capfd)
+
+
 def test_mel_fused_random_filterbanks(emu):
     pc.check_mel_fused_random_filterbanks(emu)
 

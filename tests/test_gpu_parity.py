@@ -179,6 +179,10 @@ def test_mel_fused_in_generic_kernel_equals_chained_kernels(lib, oracle, capfd):
     pc.check_mel_fused_cta(lib, oracle, cases=((400, 160, 80, 16000.0), (1024, 256, 128, 48000.0)), n=160000, batch=37)
 
 
+def test_mel_fused_fallback_to_chained_kernels(lib, capfd):
+    pc.check_mel_fused_fallback(lib, capfd)
+
+
 def test_mel_fused_random_filterbanks(lib):
     pc.check_mel_fused_random_filterbanks(lib, seeds=range(25))
 
